@@ -1,0 +1,27 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+FIXTURES = os.path.join(GOLDEN, "reference_fixtures")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    """Outputs of the reference's own sources (tests/golden/make_golden.py)."""
+    return np.load(os.path.join(GOLDEN, "ref_vectors.npz"))
+
+
+@pytest.fixture(scope="session")
+def fixtures_dir():
+    return FIXTURES
