@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py -- CG iterations/s (+ SpMV GFLOP/s and HBM GB/s against the roofline) of the SparseBench hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload sell256|crs128|ccrs128|...] [--impl reference]
+
+A step is ONE CG iteration (CGSolver.c:107-129: p-update, halo exchange, SpMV, two dot products, x/r update)
+over the synthetic HPCG 27-point stencil matrix named by the workload; the default workload is BASELINE.json
+configs[2]/[3]: 256^3 rows per GPU, SELL-C-sigma (C=32, sigma=256), fp64, z-stacked row blocks over N GPUs (weak
+scaling). One JSON line is printed by rank 0. See DESIGN.md section "Measurement" for every field.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (nx, ny, nz per GPU, format, C, sigma, description)
+    "sell256": (256, 256, 256, "SCS", 32, 256, "HPCG 27-pt stencil 256^3 per GPU, SELL-C-sigma (C=32, sigma=256), fp64 CG"),
+    "crs256": (256, 256, 256, "CRS", 0, 0, "HPCG 27-pt stencil 256^3 per GPU, CRS, fp64 CG"),
+    "ccrs256": (256, 256, 256, "CCRS", 0, 0, "HPCG 27-pt stencil 256^3 per GPU, CCRS, fp64 CG"),
+    "crs128": (128, 128, 128, "CRS", 0, 0, "HPCG 27-pt stencil 128^3 per GPU, CRS, fp64 CG"),
+    "sell128": (128, 128, 128, "SCS", 32, 256, "HPCG 27-pt stencil 128^3 per GPU, SELL-C-sigma (C=32, sigma=256), fp64 CG"),
+    "ccrs128": (128, 128, 128, "CCRS", 0, 0, "HPCG 27-pt stencil 128^3 per GPU, CCRS, fp64 CG"),
+    "sell64": (64, 64, 64, "SCS", 32, 256, "HPCG 27-pt stencil 64^3 per GPU, SELL-C-sigma (C=32, sigma=256), fp64 CG (smoke size)"),
+}
+
+
+def stencil_nnz(nx, ny, nz_total):
+    return (3 * nx - 2) * (3 * ny - 2) * (3 * nz_total - 2)
+
+
+def local_nnz(nx, ny, nz, rank, size):
+    """stored non-zeros of rank's z-slab (matrix.c:63-96)"""
+    per_line = (3 * nx - 2) * (3 * ny - 2)
+    total = 0
+    for z in range(nz):
+        gz = rank * nz + z
+        total += per_line * (1 + (gz > 0) + (gz < nz * size - 1))
+    return total
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.tmp = None
+
+    def start(self):
+        try:
+            self.tmp = tempfile.NamedTemporaryFile(mode="w+", suffix=".csv", delete=False)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = [l.strip().split(", ") for l in open(self.tmp.name) if l.strip()]
+        os.unlink(self.tmp.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for i, nme in enumerate(names):
+                    if r[5 + i].strip().lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def reference_arm(args, nx, ny, nz, desc, world):
+    """The reference's own CPU implementation (oracle/_ref/libref_CRS_fast.so = its sources with its shipped flags
+    -O3 -ffast-math -fopenmp, CRS format: the only format whose reference build works), all host threads, driven
+    in the CGSolver.c:94-128 order so that exactly K iterations are timed after W warm-up iterations."""
+    from oracle import ref
+    kind = "reference"
+    threads = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
+    if not ref.available("CRS_fast"):
+        return None
+    L = ref.load("CRS_fast")
+    # bounded sample: one rank's block of the workload (nx*ny*nz rows), at most 128 z-planes
+    snz = min(nz, args.ref_planes)
+    frac = (nx * ny * snz) / float(nx * ny * nz * world)
+    g = ref.generate(nx, ny, snz, False, "CRS_fast")
+    A = ref.convert_crs(g, "CRS_fast")
+    n = A.nr
+    rp = np.ctypeslib.as_array(C.cast(A.rowPtr, C.POINTER(C.c_uint32)), (n + 1,))
+    lens = np.diff(rp.astype(np.int64))
+    b = 27.0 - (lens - 1.0)
+    x = np.zeros(n); r = np.zeros(n); p = np.zeros(n); Ap = np.zeros(n)
+    P = lambda a: a.ctypes.data
+    res = C.c_double(0.0)
+    L.waxpby(n, 1.0, P(x), 0.0, P(x), P(p))
+    L.spMVM(C.byref(A), P(p), P(Ap))
+    L.waxpby(n, 1.0, P(b), -1.0, P(Ap), P(r))
+    L.ddot(n, P(r), P(r), C.byref(res))
+    rtrans = res.value
+    t0 = None
+    K, W = args.steps, args.warmup
+    for k in range(1, W + K + 1):
+        if k == W + 1:
+            t0 = time.perf_counter()
+        if k == 1:
+            L.waxpby(n, 1.0, P(r), 0.0, P(r), P(p))
+        else:
+            old = rtrans
+            L.ddot(n, P(r), P(r), C.byref(res)); rtrans = res.value
+            L.waxpby(n, 1.0, P(r), rtrans / old, P(p), P(p))
+        L.spMVM(C.byref(A), P(p), P(Ap))
+        L.ddot(n, P(p), P(Ap), C.byref(res))
+        alpha = rtrans / res.value
+        L.waxpby(n, 1.0, P(x), alpha, P(p), P(x))
+        L.waxpby(n, 1.0, P(r), -alpha, P(Ap), P(r))
+    dt = time.perf_counter() - t0
+    sample_its = K / dt
+    value = sample_its * frac          # a full step covers 1/frac times the sampled rows
+    sample = ("%dx%dx%d rows of the %dx%dx%d global problem (%.4g of one step's rows), CRS, %d OpenMP threads, "
+              "%d iterations after %d warm-up; full-step rate = sample rate x %.4g"
+              % (nx, ny, snz, nx, ny, nz * world, frac, threads, K, W, frac))
+    return dict(value=value, sample_its=sample_its, ms_per_step=1e3 / value, cores=threads, kind=kind, sample=sample,
+                final_residual=float(np.sqrt(rtrans)))
+
+
+# ----------------------------------------------------------------------------------------------- main arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="sell256", choices=sorted(WORKLOADS))
+    ap.add_argument("--ref-planes", type=int, default=128, help="z-planes of the CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    nx, ny, nz, fmt, Cc, sigma, desc = WORKLOADS[args.workload]
+    K, W = args.steps, args.warmup
+    metric, unit = "cg_iterations_per_sec", "it/s"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r = reference_arm(args, nx, ny, nz, desc, world)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_CRS_fast.so was not built"}))
+            return 0
+        line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": unit, "n_gpus": args.gpus, "steps": K,
+                "warmup": W, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": desc, "nx": nx, "ny": ny, "nz_per_gpu": nz, "format": "CRS (reference CPU build)"},
+                "cpu_baseline": {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from sparsebench_b200 import api
+    L = api.lib()
+    if L.sbDeviceCount() < 1:
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    ndev = L.sbDeviceCount()
+    dev = local % ndev
+    torch.cuda.set_device(dev)
+    L.sbSetDevice(dev)
+    comm = api.Comm()
+    comm.rank, comm.size = 0, 1
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+        nbytes = L.sbCommUniqueIdBytes()
+        idbuf = (C.c_char * nbytes)()
+        if rank == 0:
+            L.sbCommGetUniqueId(idbuf)
+        t = torch.frombuffer(bytearray(idbuf.raw), dtype=torch.uint8).cuda()
+        dist.broadcast(t, 0)
+        raw = bytes(t.cpu().numpy().tobytes())
+        L.sbCommInitRank(C.byref(comm), rank, world, dev, raw)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        L.sbDeviceSynchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- setup (untimed): generate on the device, partition, convert
+    t_setup = time.perf_counter()
+    g = api.matrixGenerate(nx, ny, nz, rank, world, device=True)
+    L.commPartition(C.byref(comm), C.byref(g))
+    fmt_id = {"CRS": api.FMT_CRS, "SCS": api.FMT_SCS, "CCRS": api.FMT_CCRS}[fmt]
+    A = api.convertMatrix(fmt_id, g, Cc, sigma)
+    if fmt != "CCRS":
+        L.sbFreeGMatrix(C.byref(g))
+    barrier()
+    t_setup = time.perf_counter() - t_setup
+    N = nx * ny * nz
+    nnz = local_nnz(nx, ny, nz, rank, world)
+    nc = N + comm.externalCount
+    val_bytes = 16 if fmt == "CCRS" else 12
+    B_spmv = 12 * nnz + 8 * nc + 8 * N            # algorithmic bytes, true nnz
+    B_spmv_fmt = val_bytes * nnz + 8 * nc + 8 * N
+    F_spmv = 2 * nnz
+    B_it = B_spmv + 72 * N
+    F_it = 2 * nnz + 10 * N
+
+    def new_solver(flags, itermax, b=None, x=None):
+        p = api.Parameter(b"generate", nx, ny, nz, itermax, 0.0)
+        info = api.CGInfo()
+        info.flags = flags
+        hist = np.zeros(itermax + 4)
+        info.history = hist.ctypes.data_as(C.POINTER(C.c_double))
+        info.historyCap = len(hist)
+        if b is not None:
+            info.b = b
+        if x is not None:
+            info.x = x
+        S = L.sbCGCreate(C.byref(comm), C.byref(p), C.byref(A), fmt_id, C.byref(info))
+        return S, info, hist, p
+
+    timer = api.EventTimer()
+    sampler = ClockSampler(dev)
+
+    # ---- timed region: W warm-up iterations, then exactly K iterations, inputs resident in HBM
+    S, info, hist, _p = new_solver(api.CG_FUSED, W + K + 1)
+    L.sbCGIterate(S, W + 1)
+    barrier()
+    sampler.start()
+    launches0 = L.sbKernelLaunchCount()
+    timer.start()
+    kdone = L.sbCGIterate(S, W + K + 1)
+    ms = timer.stop_ms()
+    launches = L.sbKernelLaunchCount() - launches0
+    barrier()
+    clocks = sampler.stop()
+    ms = max_over_ranks(ms)
+    L.sbCGFinish(S, C.byref(info), ms)
+    assert kdone == W + K + 1, "CG stopped early: k=%d" % kdone
+    resid0, resid = float(hist[0]), float(hist[info.nhist - 1])
+    value = K / (ms * 1e-3)
+
+    # ---- per-kernel device times inside the same loop (CUDA events on the launching stream)
+    S2, info2, _h2, _p2 = new_solver(api.CG_FUSED | api.CG_PROFILE, W + K + 1)
+    L.sbCGIterate(S2, W + K + 1)
+    L.sbCGFinish(S2, C.byref(info2), 0.0)
+    region = {api.REGIONS[i]: info2.regionMs[i] / (W + K) for i in range(5)}
+    spmv_ms = region["spmv"]
+    peak, peak_src = peaks()
+    achieved = B_spmv / (spmv_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.workload)
+        except Exception:
+            traffic = None
+
+    # ---- the reference's `-t spmv` mode (main.c:200-216): x = 1, back-to-back SpMVs, no fused dot
+    xs = api.to_device(np.ones(8), slots=nc + 64)
+    L.sbCopyToDevice(xs.ptr, np.ones(N).ctypes.data, 8 * N)
+    ys = api.DeviceBuffer(8 * (N + 64 + 32))
+    for _ in range(3):
+        api.spMVM(A, xs, ys)
+    barrier()
+    timer.start()
+    for _ in range(K):
+        api.spMVM(A, xs, ys)
+    spmv_only_ms = max_over_ranks(timer.stop_ms()) / K
+    xs.free(); ys.free()
+
+    # ---- e2e: the same iterations through sbSolveCG with HOST (pinned) b and x: upload, solve, download
+    e2e = None
+    if not args.no_e2e:
+        hb = L.sbAllocateHost(8 * N)
+        hx = L.sbAllocateHost(8 * N)
+        b_np = np.ctypeslib.as_array(C.cast(hb, C.POINTER(C.c_double)), (N,))
+        x_np = np.ctypeslib.as_array(C.cast(hx, C.POINTER(C.c_double)), (N,))
+        lens = np.full(N, 27.0)
+        b_np[:] = 1.0   # any right-hand side; values do not change the work per iteration
+        x_np[:] = 0.0
+        del lens
+        p = api.Parameter(b"generate", nx, ny, nz, K + 1, 0.0)
+        einfo = api.CGInfo()
+        einfo.flags = api.CG_FUSED | api.CG_HOST_VECTORS
+        ehist = np.zeros(K + 8)
+        einfo.history = ehist.ctypes.data_as(C.POINTER(C.c_double))
+        einfo.historyCap = len(ehist)
+        einfo.b, einfo.x = hb, hx
+        barrier()
+        t0 = time.perf_counter()
+        ke = L.sbSolveCG(C.byref(comm), C.byref(p), C.byref(A), fmt_id, C.byref(einfo))
+        L.sbDeviceSynchronize()
+        dt = time.perf_counter() - t0
+        dt = max_over_ranks(dt)
+        e2e = {"value": (ke - 1) / dt, "unit": unit, "h2d_bytes_per_step": 2 * 8 * N / (ke - 1),
+               "d2h_bytes_per_step": (8 * N + 8 * ke) / (ke - 1),
+               "what": "sbSolveCG(host b, host x0 -> host x): H2D of b and x0, %d iterations with a D2H residual scalar "
+                       "each, D2H of x; matrix resident (convertMatrix is setup, as in the reference)" % (ke - 1),
+               "ms_per_step": dt * 1e3 / (ke - 1)}
+        L.sbFreeHost(hb); L.sbFreeHost(hx)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            sub = argparse.Namespace(**vars(args))
+            sub.steps, sub.warmup = min(K, 20), 3
+            r = reference_arm(sub, nx, ny, nz, desc, 1)
+            if r:
+                cpu = {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+        except Exception as e:  # the CPU leg must never take the GPU numbers down with it
+            cpu = {"value": None, "unit": unit, "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % (e,)}
+
+    if rank == 0:
+        line = {
+            "metric": metric, "value": value * 1.0, "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": desc, "nx": nx, "ny": ny, "nz_per_gpu": nz, "format": fmt, "C": Cc, "sigma": sigma,
+                       "rows_per_gpu": N, "nnz_rank0": nnz, "parallelism": "row-block x%d" % world,
+                       "l2": "inputs larger than L2: %.2f GB of matrix + vectors streamed per iteration vs 126 MB L2" % (B_it / 1e9),
+                       "setup_s": round(t_setup, 2)},
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "spmv (%s) fused with p.Ap" % fmt, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": B_spmv, "avg_launch_ms": spmv_ms,
+                         "frac_of_nominal_8000": achieved / 8000.0},
+            "cpu_baseline": cpu,
+            "spmv": {"gflops": F_spmv / (spmv_only_ms * 1e-3) / 1e9, "gbs": B_spmv / (spmv_only_ms * 1e-3) / 1e9,
+                     "gbs_format_bytes": B_spmv_fmt / (spmv_only_ms * 1e-3) / 1e9, "ms": spmv_only_ms,
+                     "frac_of_peak": B_spmv / (spmv_only_ms * 1e-3) / 1e9 / peak, "mode": "x=1, back-to-back (main.c:200-216)"},
+            "cg": {"gbs_per_gpu": B_it / (ms / K * 1e-3) / 1e9, "gflops_per_gpu": F_it / (ms / K * 1e-3) / 1e9,
+                   "frac_of_peak": B_it / (ms / K * 1e-3) / 1e9 / peak, "kernel_ms_per_iteration": region,
+                   "residual_initial": resid0, "residual_final": resid, "max_error_vs_xexact": info.maxError},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        L.commFinalize(C.byref(comm))
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

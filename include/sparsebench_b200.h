@@ -1,0 +1,247 @@
+/* sparsebench_b200 -- C ABI of the B200-native SparseBench CG/SpMV hot path.
+ *
+ * Every entry point below replaces one reference interface (cited file:line, paths relative to the
+ * SparseBench tree). Struct layouts are the reference's for CG_UINT = unsigned int, CG_FLOAT = double
+ * (util.h:35-53), so host code that only forwards the structs keeps working. What changes:
+ *   - array members filled by convertMatrix() and everything returned by allocate() are DEVICE pointers;
+ *   - x / y / w / p vectors handed to spMVM, waxpby, ddot, commExchange are DEVICE pointers
+ *     (obtained from allocate()); scalars (alpha, beta, *result, Parameter) stay on the host;
+ *   - errors follow the reference convention: message on stderr + exit(EXIT_FAILURE)
+ *     (allocate.c:19-33, comm.c:462-468). A missing/failed CUDA device is such an error: there is
+ *     no CPU fallback anywhere in this library.
+ * The reference selects the matrix format at link time (Makefile:20,32-34): one object defines
+ * convertMatrix/spMVM for the -D<FMT> Matrix typedef (matrix.h:14-22). Here the three formats live in
+ * one library under sbCRS_/sbSCS_/sbCCRS_ prefixes; libsparsebench_b200_<FMT>.so re-exports them
+ * under the reference's bare names (convertMatrix, spMVM, solveCG) for link-time substitution, and
+ * defining CRS, SCS or CCRS before including this header gives the same mapping at compile time.
+ */
+#ifndef SPARSEBENCH_B200_H
+#define SPARSEBENCH_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdio.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef unsigned int CG_UINT;   /* util.h:35-38 (UINT_TYPE=1) */
+typedef double CG_FLOAT;        /* util.h:49-52 (PRECISION=2) */
+
+/* ---------------------------------------------------------------- data structures */
+typedef struct {                /* matrix.h:24-27 (16 bytes: 4 B padding after col) */
+  CG_UINT col;
+  CG_FLOAT val;
+} Entry;
+
+typedef struct {                /* matrix.h:29-35 */
+  CG_UINT nr, nc, nnz;
+  CG_UINT totalNr, totalNnz;
+  CG_UINT startRow, stopRow;
+  CG_UINT* rowPtr;              /* host (reference generator/reader) or device (sbGenerateDevice) */
+  Entry* entries;
+} GMatrix;
+
+typedef struct {                /* CRSMatrix.h:9-16 */
+  CG_UINT nr, nc, nnz;
+  CG_UINT totalNr, totalNnz;
+  CG_UINT startRow, stopRow;
+  CG_UINT* rowPtr;              /* device, nr+1 */
+  CG_UINT* colInd;              /* device, rowPtr[nr] valid entries */
+  CG_FLOAT* val;                /* device */
+} SbCRSMatrix;
+
+typedef struct {                /* SCSMatrix.h:13-27 */
+  CG_UINT nr, nc, nnz;
+  CG_UINT totalNr, totalNnz;
+  CG_UINT startRow, stopRow;
+  CG_UINT* colInd;              /* device, nElems, reference numbering (un-permuted columns) */
+  CG_FLOAT* val;                /* device, nElems */
+  CG_UINT C, sigma;             /* INPUTS: set by the caller before convertMatrix (matrix-SCS.c:40) */
+  CG_UINT nrPadded, nChunks;
+  CG_UINT nElems;
+  CG_UINT* chunkPtr;            /* device, nChunks+1 */
+  CG_UINT* chunkLens;           /* device, nChunks */
+  CG_UINT* oldToNewPerm;        /* device, nr */
+  CG_UINT* newToOldPerm;        /* device, nr */
+} SbSCSMatrix;
+
+typedef struct {                /* CCRSMatrix.h:9-20: same field order as GMatrix */
+  CG_UINT nr, nc, nnz;
+  CG_UINT totalNr, totalNnz;
+  CG_UINT startRow, stopRow;
+  CG_UINT* rowPtr;              /* device */
+  Entry* entries;               /* device, 16-byte {col,val} records */
+} SbCCRSMatrix;
+
+#if defined(CRS)
+typedef SbCRSMatrix Matrix;
+#define convertMatrix sbCRS_convertMatrix
+#define spMVM sbCRS_spMVM
+#define solveCG sbCRS_solveCG
+#elif defined(SCS)
+typedef SbSCSMatrix Matrix;
+#define convertMatrix sbSCS_convertMatrix
+#define spMVM sbSCS_spMVM
+#define solveCG sbSCS_solveCG
+#elif defined(CCRS)
+typedef SbCCRSMatrix Matrix;
+#define convertMatrix sbCCRS_convertMatrix
+#define spMVM sbCCRS_spMVM
+#define solveCG sbCCRS_solveCG
+#endif
+
+typedef struct {                /* matrix.h:37-41 */
+  int row;
+  int col;
+  double val;
+} MMEntry;
+
+typedef struct {                /* matrix.h:43-49 */
+  size_t count;
+  int nr, nnz;
+  int totalNr, totalNnz;
+  int startRow, stopRow;
+  MMEntry* entries;
+} MMMatrix;
+
+typedef struct {                /* parameter.h:8-13 */
+  char* filename;
+  int nx, ny, nz;
+  int itermax;
+  double eps;
+} Parameter;
+
+enum { SB_MAX = 0, SB_SUM = 1 };   /* comm.h:25 `enum op { MAX = 0, SUM }` */
+
+typedef struct {                /* comm.h:27-46, the _MPI member set is always present */
+  int rank;
+  int size;
+  FILE* logFile;
+  int externalCount;
+  int totalSendCount;
+  int* elementsToSend;          /* host copy (bit-exact vs comm.c:116-182); device copy kept internally */
+  int indegree;
+  int outdegree;
+  int* sources;
+  int* recvCounts;
+  int* rdispls;
+  int* destinations;
+  int* sendCounts;
+  int* sdispls;
+  CG_FLOAT* sendBuffer;         /* device, totalSendCount */
+  void* communicator;           /* replaces MPI_Comm: opaque handle (NCCL communicator, peer windows, streams) */
+} Comm;
+
+/* ---------------------------------------------------------------- runtime (allocate.c, timing.c) */
+/* allocate.h:9 -- device allocation (alignment honoured up to 512 B); exits on failure */
+void* allocate(size_t alignment, size_t bytesize);
+void sbFree(void* devPtr);
+void* sbAllocateHost(size_t bytesize);               /* pinned host memory for staging */
+void sbFreeHost(void* hostPtr);
+void sbCopyToDevice(void* dev, const void* host, size_t bytes);
+void sbCopyToHost(void* host, const void* dev, size_t bytes);
+void sbDeviceSynchronize(void);
+/* timing.h:8-9 -- monotonic seconds AFTER draining the device, so PROFILE(tag, call) (profiler.h:18-21)
+ * around asynchronous launches still measures the call */
+double getTimeStamp(void);
+double getTimeResolution(void);
+/* CUDA-event timing on the library's stream (replaces getTimeStamp pairs in measurement code) */
+void* sbTimerCreate(void);
+void sbTimerStart(void* timer);
+double sbTimerStopMs(void* timer);                   /* records stop, waits for it, returns milliseconds */
+void sbTimerDestroy(void* timer);
+int sbDeviceCount(void);
+void sbSetDevice(int device);
+void sbFlushL2(void);                                /* overwrites a buffer larger than L2 */
+size_t sbKernelLaunchCount(void);                    /* number of this library's kernel launches so far */
+
+/* ---------------------------------------------------------------- matrix sources */
+/* matrix.h:52-53 / matrix.c:30-121 -- HPCG 27-pt / 7-pt block of rank `rank` of `size`, host arrays */
+void matrixGenerate(GMatrix* m, Parameter* p, int rank, int size, bool use_7pt_stencil);
+/* same matrix, generated directly in device memory (rowPtr/entries are device pointers) */
+void sbGenerateDevice(GMatrix* m, Parameter* p, int rank, int size, bool use_7pt_stencil);
+void sbFreeGMatrix(GMatrix* m);                      /* releases host or device arrays of a GMatrix */
+
+/* ---------------------------------------------------------------- format plugins */
+/* matrix.h:57 convertMatrix / solver.h:13 spMVM, one pair per format. `im` may hold host or device arrays. */
+void sbCRS_convertMatrix(SbCRSMatrix* m, GMatrix* im);                        /* matrix-CRS.c:12-44 */
+void sbCRS_spMVM(SbCRSMatrix* m, const CG_FLOAT* x, CG_FLOAT* y);             /* matrix-CRS.c:46-65 */
+void sbSCS_convertMatrix(SbSCSMatrix* m, GMatrix* im);                        /* matrix-SCS.c:31-196 (w/o :42-43) */
+void sbSCS_spMVM(SbSCSMatrix* m, const CG_FLOAT* x, CG_FLOAT* y);             /* matrix-SCS.c:198-228 */
+void sbCCRS_convertMatrix(SbCCRSMatrix* m, GMatrix* im);                      /* matrix-CCRS.c:12 (alias intent) */
+void sbCCRS_spMVM(SbCCRSMatrix* m, const CG_FLOAT* x, CG_FLOAT* y);           /* matrix-CCRS.c:14-31 */
+void sbCRS_destroyMatrix(SbCRSMatrix* m);
+void sbSCS_destroyMatrix(SbSCSMatrix* m);
+void sbCCRS_destroyMatrix(SbCCRSMatrix* m);
+
+/* ---------------------------------------------------------------- Krylov vector kernels (solver.c) */
+void waxpby(const CG_UINT n, const CG_FLOAT alpha, const CG_FLOAT* x, const CG_FLOAT beta,
+    const CG_FLOAT* y, CG_FLOAT* w);                                          /* solver.h:15-20, solver.c:16-39 */
+void ddot(const CG_UINT n, const CG_FLOAT* x, const CG_FLOAT* y, CG_FLOAT* result); /* solver.h:22-25, solver.c:41-62 */
+
+/* ---------------------------------------------------------------- CG driver (CGSolver.c) */
+int sbCRS_solveCG(Comm* comm, Parameter* param, SbCRSMatrix* m);              /* solver.h:11, CGSolver.c:62-141 */
+int sbSCS_solveCG(Comm* comm, Parameter* param, SbSCSMatrix* m);
+int sbCCRS_solveCG(Comm* comm, Parameter* param, SbCCRSMatrix* m);
+
+enum { SB_FMT_CRS = 0, SB_FMT_SCS = 1, SB_FMT_CCRS = 2 };
+enum {
+  SB_CG_FUSED = 1,        /* single-pass fused kernels + device-resident scalars (default product path) */
+  SB_CG_PRINT = 2,        /* print the reference's stdout lines (CGSolver.c:102,119,133,58) */
+  SB_CG_HOST_VECTORS = 4, /* b / x are HOST buffers: upload b,x0 and download x inside the call */
+  SB_CG_NO_OVERLAP = 8,   /* multi-GPU: do not overlap the halo exchange with interior rows */
+  SB_CG_PROFILE = 16      /* CUDA events around every kernel of the loop -> regionMs (measurement runs only) */
+};
+enum { SB_REGION_UPDATE_P = 0, SB_REGION_EXCHANGE, SB_REGION_SPMV, SB_REGION_ALLREDUCE, SB_REGION_UPDATE_XR, SB_REGION_COUNT };
+typedef struct {
+  int flags;
+  const CG_FLOAT* b;      /* right-hand side, nr entries; NULL -> initVectors rule (CGSolver.c:19-38) */
+  CG_FLOAT* x;            /* in: start vector, out: solution, nr entries (original row order); NULL -> x0 = 0, discarded */
+  double* history;        /* host, capacity historyCap: history[0] initial ||r||, history[k] = normr of iteration k */
+  int historyCap;
+  int nhist;              /* out */
+  double solveMs;         /* out: device time of the iteration loop (CUDA events), CGSolver.c:106,130 */
+  double maxError;        /* out: max|x - 1| for generated matrices (CGSolver.c:40-60), else -1 */
+  double regionMs[SB_REGION_COUNT]; /* out (SB_CG_PROFILE): device time per kernel class, replaces _t[] of profiler.c:17 */
+} SbCGInfo;
+/* solveCG with explicit right-hand side / history capture; returns the reference's k */
+int sbSolveCG(Comm* comm, Parameter* param, void* matrix, int fmt, SbCGInfo* info);
+/* the same solve in three steps, so that a harness can time exactly K iterations after W warm-up iterations:
+ * create = allocate + initVectors + pre-loop (CGSolver.c:69-102); iterate = run the loop while
+ * k < min(untilK, itermax) && normr > eps, asynchronously (returns k); finish = drain, report, free. */
+void* sbCGCreate(Comm* comm, Parameter* param, void* matrix, int fmt, SbCGInfo* info);
+int sbCGIterate(void* solver, int untilK);
+int sbCGFinish(void* solver, SbCGInfo* info, double loopMs);
+
+/* ---------------------------------------------------------------- communication (comm.c) */
+void commInit(Comm* c, int argc, char** argv);                                /* comm.h:48, comm.c:863-878 */
+void commFinalize(Comm* c);                                                   /* comm.h:49, comm.c:893-910 */
+void commPartition(Comm* c, GMatrix* m);                                      /* comm.h:51, comm.c:414-625 */
+void commExchange(Comm* c, CG_UINT numRows, CG_FLOAT* x);                     /* comm.h:57, comm.c:627-651 */
+void commReduction(CG_FLOAT* v, int op);                                      /* comm.h:58, comm.c:653-662 (host scalar) */
+void commDistributeMatrix(Comm* c, MMMatrix* m, MMMatrix* mLocal);            /* comm.h:50, comm.c:311-412 (single rank) */
+/* bootstrap pieces used when another launcher (torchrun) already owns the rendezvous */
+int sbCommUniqueIdBytes(void);
+void sbCommGetUniqueId(void* id);
+void sbCommInitRank(Comm* c, int rank, int size, int device, const void* id);
+/* commPartition split at its two small exchanges, for launchers that move them over their own transport
+ * (commPartition itself uses NCCL; the CPU tests use torch.distributed/gloo). Pure host integer work when
+ * `m` holds host arrays; a device GMatrix is scanned and renumbered by kernels.
+ *   1. all-gather every rank's m->startRow                      -> startRows[size]        (comm.c:496)
+ *   2. plan = sbPartitionLocal(...): renumbers m->entries[].col in place, m->nc += externalCount,
+ *      fills wantCounts[owner] = number of halo entries owned by `owner`                  (comm.c:452-520, :40-114)
+ *   3. all-gather wantCounts                                    -> wantMatrix[size*size], row = requester
+ *   4. for every source s with wantMatrix[rank][s] > 0 send sbPartitionRequestSlice(plan, wantMatrix, s)
+ *      to s; concatenate what arrives by ascending requester    -> received             (comm.c:130-161)
+ *   5. sbPartitionFinish fills the Comm lists (malloc'ed, released by commFinalize) and frees the plan. */
+typedef struct SbPartitionPlan SbPartitionPlan;
+SbPartitionPlan* sbPartitionLocal(GMatrix* m, int rank, int size, const CG_UINT* startRows, int* wantCounts);
+const int* sbPartitionRequestSlice(SbPartitionPlan* plan, const int* wantMatrix, int source, int* count);
+void sbPartitionFinish(SbPartitionPlan* plan, Comm* c, const int* wantMatrix, const int* received);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPARSEBENCH_B200_H */

@@ -82,6 +82,8 @@ def load(name):
         L.getTimeStamp.restype = C.c_double
         L.waxpby.argtypes = [U, C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
         L.ddot.argtypes = [U, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+        L.spMVM.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.convertMatrix.argtypes = [C.c_void_p, C.c_void_p]
         _libs[name] = L
     return _libs[name]
 

@@ -1,0 +1,23 @@
+"""ctypes loader of libsparsebench_b200.so (the C ABI declared in include/sparsebench_b200.h)."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsparsebench_b200.so")
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "%s is missing: build it with `python -m sparsebench_b200.build` (nvcc, sm_100a). "
+                "There is no CPU fallback." % LIB_PATH)
+        _lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)   # the drop-in shims resolve against it
+    return _lib
+
+
+def load_dropin(fmt):
+    load()
+    return C.CDLL(os.path.join(HERE, "libsparsebench_b200_%s.so" % fmt))

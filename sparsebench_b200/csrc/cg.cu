@@ -1,0 +1,327 @@
+// Conjugate-gradient driver (replaces solveCG / initVectors / solverCheckResidual, CGSolver.c:19-141).
+//
+// The operation order, the lagging `normr > eps` test and the returned loop counter are the reference's.
+// What is B200-native is how an iteration runs: three kernels on one stream --
+//   p = r + beta p                                   (beta from device scalars rho[k-1]/rho[k-2])
+//   Ap = A p  fused with  pAp[k] = p.Ap
+//   x += alpha p ; r -= alpha Ap  fused with  rho[k] = r.r      (alpha = rho[k-1]/pAp[k] on the device)
+// -- with every scalar resident in HBM. The host only needs rho[k-2] to decide whether iteration k runs
+// (that IS the reference's lagging test), so it always has one full iteration queued while it waits: no
+// per-iteration pipeline drain.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "sb_internal.h"
+
+namespace sb {
+
+namespace {
+
+constexpr int kEventRing = 8;
+enum Region { R_UPDATE_P = 0, R_EXCHANGE, R_SPMV, R_ALLREDUCE, R_UPDATE_XR, R_COUNT };
+
+bool commActive(const Comm* c) { return c && c->size > 1; }
+
+struct CgSolver {
+  Comm* comm = nullptr;
+  Operator A;
+  cudaStream_t s = nullptr;
+  double eps = 0.0;
+  int itermax = 0, flags = 0, printFreq = 1;
+  bool fused = true, print = false, generated = false, profile = false;
+  uint32_t n = 0;
+  size_t rowSlots = 0, colSlots = 0;
+  // vectors (CGSolver.c:69-79), solver order (SELL: permuted)
+  double *r = nullptr, *p = nullptr, *Ap = nullptr, *x = nullptr, *b = nullptr, *tmp = nullptr;
+  double *rho = nullptr, *pAp = nullptr;   // device scalars indexed by iteration: rho[j] = r_j.r_j, pAp[k] = p_k.Ap_k
+  double* hRho = nullptr;                  // pinned mirror of rho
+  cudaEvent_t ring[kEventRing];
+  std::vector<double> hist;
+  double normr = 0.0, rtrans = 0.0, oldrtrans = 0.0;
+  int k = 1;
+  bool stopped = false;
+  // optional per-kernel event timing
+  std::vector<cudaEvent_t> evPool;
+  std::vector<int> evRegion;
+  double regionMs[R_COUNT] = { 0, 0, 0, 0, 0 };
+
+  void mark(int region)
+  {
+    if (!profile) return;
+    cudaEvent_t e;
+    SB_CUDA(cudaEventCreate(&e));
+    SB_CUDA(cudaEventRecord(e, s));
+    evPool.push_back(e);
+    evRegion.push_back(region);
+  }
+
+  void allreduce(double* d, int op)
+  {
+    if (!commActive(comm)) return;
+    commAllreduceDevice(comm, d, 1, op, s);
+    mark(R_ALLREDUCE);
+  }
+
+  void spmvWithHalo(const DotArgs* dot)
+  {
+    if (commActive(comm)) {
+      commExchangeOnStream(comm, A.nr, p, s);                 // CGSolver.c:95,122
+      mark(R_EXCHANGE);
+    }
+    launchSpmv(A, p, Ap, 0, spmvUnits(A), dot, s);            // CGSolver.c:96,123
+    mark(R_SPMV);
+  }
+
+  // caller vector (host or device, original row order) -> device vector in solver order
+  void importVector(const double* src, double* dst)
+  {
+    const size_t bytes = sizeof(double) * n;
+    const bool dev = isDevicePointer(src);
+    if (!A.oldToNew) {
+      SB_CUDA(cudaMemcpyAsync(dst, src, bytes, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    } else {
+      const double* staged = src;
+      if (!dev) {
+        SB_CUDA(cudaMemcpyAsync(tmp, src, bytes, cudaMemcpyHostToDevice, s));
+        staged = tmp;
+      }
+      launchScatter(n, A.oldToNew, staged, dst, s);           // dst[oldToNew[i]] = src[i]
+    }
+  }
+
+  void exportVector(const double* src, double* dst)
+  {
+    const size_t bytes = sizeof(double) * n;
+    const bool dev = isDevicePointer(dst);
+    if (!A.oldToNew) {
+      SB_CUDA(cudaMemcpyAsync(dst, src, bytes, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+    } else if (dev) {
+      launchGather(n, A.oldToNew, src, dst, s);               // dst[i] = src[oldToNew[i]]
+    } else {
+      launchGather(n, A.oldToNew, src, tmp, s);
+      SB_CUDA(cudaMemcpyAsync(dst, tmp, bytes, cudaMemcpyDeviceToHost, s));
+    }
+  }
+
+  void printIteration(int iter, double value)
+  {
+    if (print && (iter % printFreq == 0 || iter + 1 == itermax)) printf("Iteration = %d Residual = %E\n", iter, value);   // :118-120
+  }
+
+  void setup(Comm* comm_, Parameter* param, const Operator& A_, const SbCGInfo* info)
+  {
+    Context& c = ctx();
+    comm = comm_;
+    A = A_;
+    s = c.stream;
+    eps = param->eps;
+    itermax = param->itermax;
+    flags = info ? info->flags : (SB_CG_FUSED | SB_CG_PRINT);
+    fused = (flags & SB_CG_FUSED) != 0;
+    profile = (flags & SB_CG_PROFILE) != 0;
+    print = (flags & SB_CG_PRINT) != 0 && (!comm || comm->rank == 0);
+    generated = param->filename && (strcmp(param->filename, "generate") == 0 || strcmp(param->filename, "generate7P") == 0);
+    n = A.nr;
+    rowSlots = (size_t)(A.nrPadded > n ? A.nrPadded : n) + 2;
+    colSlots = (A.nc > rowSlots ? (size_t)A.nc : rowSlots) + 2;
+    const int nScal = (itermax > 0 ? itermax : 0) + 4;
+    r = (double*)allocate(64, sizeof(double) * rowSlots);
+    p = (double*)allocate(64, sizeof(double) * colSlots);
+    Ap = (double*)allocate(64, sizeof(double) * rowSlots);
+    x = (double*)allocate(64, sizeof(double) * rowSlots);
+    b = (double*)allocate(64, sizeof(double) * rowSlots);
+    tmp = (double*)allocate(64, sizeof(double) * rowSlots);
+    rho = (double*)allocate(64, sizeof(double) * nScal);
+    pAp = (double*)allocate(64, sizeof(double) * nScal);
+    hRho = (double*)sbAllocateHost(sizeof(double) * nScal);
+    SB_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * colSlots, s));
+    SB_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * rowSlots, s));
+    SB_CUDA(cudaMemsetAsync(rho, 0, sizeof(double) * nScal, s));
+    SB_CUDA(cudaMemsetAsync(pAp, 0, sizeof(double) * nScal, s));
+    for (int i = 0; i < kEventRing; i++) SB_CUDA(cudaEventCreateWithFlags(&ring[i], cudaEventDisableTiming));
+    hist.reserve((size_t)nScal);
+
+    // initVectors (CGSolver.c:19-38), or caller-supplied b / x0
+    launchInitVectors(n, A.rowPtr, A.rowLen, generated, x, b, s);
+    if (info && info->b) importVector(info->b, b);
+    if (info && info->x) importVector(info->x, x);
+
+    // pre-loop (CGSolver.c:94-100)
+    launchWaxpby(n, 1.0, x, 0.0, x, p, s);
+    spmvWithHalo(nullptr);
+    launchWaxpby(n, 1.0, b, -1.0, Ap, r, s);
+    launchDot(n, r, r, rho, 0, s);
+    allreduce(rho, SB_SUM);
+    SB_CUDA(cudaMemcpyAsync(hRho, rho, sizeof(double), cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    rtrans = hRho[0];
+    normr = sqrt(rtrans);
+    hist.push_back(normr);
+    if (print) printf("Initial Residual = %E\n", normr);      // :102
+    printFreq = itermax / 10;                                 // :85-91
+    if (printFreq > 50) printFreq = 50;
+    if (printFreq < 1) printFreq = 1;
+    k = 1;
+    if (profile) {   // drop the pre-loop marks, start the clock here
+      for (cudaEvent_t e : evPool) cudaEventDestroy(e);
+      evPool.clear();
+      evRegion.clear();
+      mark(-1);
+    }
+  }
+
+  // Runs iterations while k < min(untilK, itermax) and the lagging test passes. Asynchronous: returns with up to
+  // two iterations still in flight.
+  int iterate(int untilK)
+  {
+    const int stopK = untilK < itermax ? untilK : itermax;
+    if (stopped) return k;
+    if (fused) {
+      // the normr tested before iteration k is sqrt(rho[max(k-2,0)]) -- the reference's lagging test (:107,:116)
+      for (; k < stopK; k++) {
+        if ((int)hist.size() < k) {                            // hist[k-1] = normr of iteration k-1 = sqrt(rho[k-2])
+          if (k >= 3) {
+            SB_CUDA(cudaEventSynchronize(ring[(k - 2) % kEventRing]));
+            normr = sqrt(hRho[k - 2]);
+          }
+          hist.push_back(normr);
+          printIteration(k - 1, normr);
+        }
+        if (!(normr > eps)) {
+          stopped = true;
+          break;
+        }
+        launchCgUpdateP(n, k, rho, r, p, s);                   // :109 / :111-114
+        mark(R_UPDATE_P);
+        DotArgs d { pAp + k, false, 1 };
+        spmvWithHalo(&d);                                      // :122-125
+        allreduce(pAp + k, SB_SUM);
+        launchCgUpdateXR(n, k, rho, pAp, x, r, p, Ap, 2, s);   // :126-128 (+ :112 of iteration k+1)
+        mark(R_UPDATE_XR);
+        allreduce(rho + k, SB_SUM);
+        SB_CUDA(cudaMemcpyAsync(hRho + k, rho + k, sizeof(double), cudaMemcpyDeviceToHost, s));
+        SB_CUDA(cudaEventRecord(ring[k % kEventRing], s));
+      }
+    } else {
+      // the reference's call sequence through the drop-in entry points (host scalars, 5 kernels + 2 syncs / iteration)
+      for (; k < stopK; k++) {
+        if (!(normr > eps)) {
+          stopped = true;
+          break;
+        }
+        if (k == 1) {
+          launchWaxpby(n, 1.0, r, 0.0, r, p, s);
+        } else {
+          oldrtrans = rtrans;
+          ddot(n, r, r, &rtrans);
+          const double beta = rtrans / oldrtrans;
+          launchWaxpby(n, 1.0, r, beta, p, p, s);
+        }
+        normr = sqrt(rtrans);
+        hist.push_back(normr);
+        printIteration(k, normr);
+        spmvWithHalo(nullptr);
+        double alpha = 0.0;
+        ddot(n, p, Ap, &alpha);
+        alpha = rtrans / alpha;
+        launchWaxpby(n, 1.0, x, alpha, p, x, s);
+        launchWaxpby(n, 1.0, r, -alpha, Ap, r, s);
+      }
+    }
+    return k;
+  }
+
+  int finish(SbCGInfo* info, float loopMs)
+  {
+    Context& c = ctx();
+    SB_CUDA(cudaStreamSynchronize(s));
+    if (fused && (int)hist.size() < k) {
+      // iteration k-1 was the last one executed; record its normr = sqrt(rho[k-2])
+      const double last = k >= 3 ? sqrt(hRho[k - 2]) : normr;
+      hist.push_back(last);
+      printIteration(k - 1, last);
+    }
+    if (print) printf("Solution performed %d iterations and took %.2fs\n", k, loopMs * 1e-3);   // :133
+    double maxErr = -1.0;
+    if (generated) {                                           // solverCheckResidual, :40-60
+      launchMaxErr(n, x, c.dScalar + 8, s);
+      SB_CUDA(cudaMemcpyAsync(c.hScalar + 8, c.dScalar + 8, sizeof(double), cudaMemcpyDeviceToHost, s));
+      SB_CUDA(cudaStreamSynchronize(s));
+      maxErr = c.hScalar[8];
+      commReduction(&maxErr, SB_MAX);
+      if (print) printf("Difference between computed and exact  = %f\n", maxErr);
+    }
+    if (info) {
+      if (info->x) exportVector(x, info->x);
+      SB_CUDA(cudaStreamSynchronize(s));
+      info->nhist = (int)hist.size();
+      if (info->history)
+        for (int i = 0; i < info->nhist && i < info->historyCap; i++) info->history[i] = hist[(size_t)i];
+      info->solveMs = loopMs;
+      info->maxError = maxErr;
+      for (int i = 0; i < R_COUNT; i++) info->regionMs[i] = 0.0;
+      if (profile) {
+        for (size_t i = 1; i < evPool.size(); i++) {
+          float ms = 0.f;
+          SB_CUDA(cudaEventElapsedTime(&ms, evPool[i - 1], evPool[i]));
+          if (evRegion[i] >= 0) info->regionMs[evRegion[i]] += ms;
+        }
+      }
+    }
+    for (cudaEvent_t e : evPool) cudaEventDestroy(e);
+    for (int i = 0; i < kEventRing; i++) SB_CUDA(cudaEventDestroy(ring[i]));
+    sbFree(r); sbFree(p); sbFree(Ap); sbFree(x); sbFree(b); sbFree(tmp); sbFree(rho); sbFree(pAp);
+    sbFreeHost(hRho);
+    return k;
+  }
+};
+
+} // namespace
+
+} // namespace sb
+
+using namespace sb;
+
+extern "C" {
+
+void* sbCGCreate(Comm* comm, Parameter* param, void* matrix, int fmt, SbCGInfo* info)
+{
+  CgSolver* S = new CgSolver();
+  S->setup(comm, param, makeOperator(matrix, fmt), info);
+  return S;
+}
+
+int sbCGIterate(void* solver, int untilK) { return ((CgSolver*)solver)->iterate(untilK); }
+
+int sbCGFinish(void* solver, SbCGInfo* info, double loopMs)
+{
+  CgSolver* S = (CgSolver*)solver;
+  const int k = S->finish(info, (float)loopMs);
+  delete S;
+  return k;
+}
+
+int sbSolveCG(Comm* comm, Parameter* param, void* matrix, int fmt, SbCGInfo* info)
+{
+  CgSolver* S = (CgSolver*)sbCGCreate(comm, param, matrix, fmt, info);
+  cudaEvent_t a, b;
+  SB_CUDA(cudaEventCreate(&a));
+  SB_CUDA(cudaEventCreate(&b));
+  SB_CUDA(cudaEventRecord(a, S->s));                           // timeStart, CGSolver.c:106
+  S->iterate(param->itermax);
+  SB_CUDA(cudaEventRecord(b, S->s));                           // timeStop, :130
+  SB_CUDA(cudaEventSynchronize(b));
+  float ms = 0.f;
+  SB_CUDA(cudaEventElapsedTime(&ms, a, b));
+  SB_CUDA(cudaEventDestroy(a));
+  SB_CUDA(cudaEventDestroy(b));
+  return sbCGFinish(S, info, ms);
+}
+
+int sbCRS_solveCG(Comm* comm, Parameter* param, SbCRSMatrix* m) { return sbSolveCG(comm, param, m, SB_FMT_CRS, nullptr); }
+int sbSCS_solveCG(Comm* comm, Parameter* param, SbSCSMatrix* m) { return sbSolveCG(comm, param, m, SB_FMT_SCS, nullptr); }
+int sbCCRS_solveCG(Comm* comm, Parameter* param, SbCCRSMatrix* m) { return sbSolveCG(comm, param, m, SB_FMT_CCRS, nullptr); }
+
+} // extern "C"

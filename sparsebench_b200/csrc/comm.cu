@@ -1,0 +1,444 @@
+// Communication layer of the hot path (replaces commInit/commFinalize/commPartition/commExchange/
+// commReduction of comm.c). One process per GPU; the MPI-3 neighbourhood collective and the scalar
+// MPI_Allreduce of the reference become NCCL operations enqueued on CUDA streams (NVLink 5 / NVSwitch
+// inside one B200 box). Row-block partitioning and the halo index lists are the reference's own
+// (partition.cpp), bit for bit.
+#include <arpa/inet.h>
+#include <cub/device/device_select.cuh>
+#include <nccl.h>
+#include <netdb.h>
+#include <netinet/in.h>
+#include <sys/socket.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "sb_internal.h"
+#include "sb_partition.h"
+
+#define SB_NCCL(call)                                                                            \
+  do {                                                                                           \
+    ncclResult_t r_ = (call);                                                                    \
+    if (r_ != ncclSuccess) {                                                                     \
+      fprintf(stderr, "sparsebench_b200: NCCL error at %s:%d: %s\n", __FILE__, __LINE__,         \
+          ncclGetErrorString(r_));                                                               \
+      exit(EXIT_FAILURE);                                                                        \
+    }                                                                                            \
+  } while (0)
+
+struct SbPartitionPlan {
+  sb::PartitionPlan plan;
+};
+
+namespace sb {
+
+struct CommExt {
+  ncclComm_t nccl = nullptr;
+  int rank = 0, size = 1;
+  int* dElementsToSend = nullptr;
+  int dElementsCount = 0;
+  double* dScalar = nullptr;      // staging for host-scalar reductions
+  double* hScalar = nullptr;
+};
+
+static CommExt* g_world = nullptr;   // commReduction has no Comm* argument (it used MPI_COMM_WORLD, comm.c:653-662)
+
+static CommExt* ext(const Comm* c) { return c ? (CommExt*)c->communicator : nullptr; }
+
+static void resetLists(Comm* c)
+{
+  c->externalCount = 0; c->totalSendCount = 0; c->elementsToSend = nullptr;
+  c->indegree = 0; c->outdegree = 0;
+  c->sources = c->recvCounts = c->rdispls = nullptr;
+  c->destinations = c->sendCounts = c->sdispls = nullptr;
+  c->sendBuffer = nullptr;
+}
+
+static void attach(Comm* c, int rank, int size, int device, const ncclUniqueId* id)
+{
+  c->rank = rank;
+  c->size = size;
+  c->logFile = nullptr;
+  resetLists(c);
+  c->communicator = nullptr;
+  if (size <= 1) return;
+  sbSetDevice(device);
+  CommExt* e = new CommExt();
+  e->rank = rank;
+  e->size = size;
+  SB_NCCL(ncclCommInitRank(&e->nccl, size, *id, rank));
+  e->dScalar = (double*)allocate(64, sizeof(double) * 8);
+  e->hScalar = (double*)sbAllocateHost(sizeof(double) * 8);
+  c->communicator = e;
+  g_world = e;
+}
+
+// ---- unique-id rendezvous for launchers that only export RANK/WORLD_SIZE/MASTER_ADDR/MASTER_PORT
+static void tcpBroadcastId(int rank, int size, ncclUniqueId* id)
+{
+  const char* addr = getenv("MASTER_ADDR");
+  const char* portEnv = getenv("SB_BOOTSTRAP_PORT");
+  int port = portEnv ? atoi(portEnv) : (getenv("MASTER_PORT") ? atoi(getenv("MASTER_PORT")) + 1 : 29511);
+  if (!addr) addr = "127.0.0.1";
+  if (rank == 0) {
+    int ls = socket(AF_INET, SOCK_STREAM, 0);
+    int one = 1;
+    setsockopt(ls, SOL_SOCKET, SO_REUSEADDR, &one, sizeof(one));
+    sockaddr_in sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.sin_family = AF_INET;
+    sa.sin_addr.s_addr = htonl(INADDR_ANY);
+    sa.sin_port = htons((uint16_t)port);
+    if (bind(ls, (sockaddr*)&sa, sizeof(sa)) != 0 || listen(ls, size) != 0) SB_FATAL("commInit: cannot listen on port %d", port);
+    for (int i = 1; i < size; i++) {
+      int cs = accept(ls, nullptr, nullptr);
+      if (cs < 0 || write(cs, id, sizeof(*id)) != (ssize_t)sizeof(*id)) SB_FATAL("commInit: rendezvous send failed");
+      close(cs);
+    }
+    close(ls);
+  } else {
+    addrinfo hints, *res = nullptr;
+    memset(&hints, 0, sizeof(hints));
+    hints.ai_family = AF_INET;
+    hints.ai_socktype = SOCK_STREAM;
+    char portStr[16];
+    snprintf(portStr, sizeof(portStr), "%d", port);
+    if (getaddrinfo(addr, portStr, &hints, &res) != 0 || !res) SB_FATAL("commInit: cannot resolve %s", addr);
+    int fd = -1;
+    for (int attempt = 0; attempt < 600; attempt++) {   // rank 0 may not be listening yet
+      fd = socket(AF_INET, SOCK_STREAM, 0);
+      if (connect(fd, res->ai_addr, res->ai_addrlen) == 0) break;
+      close(fd);
+      fd = -1;
+      usleep(100000);
+    }
+    if (fd < 0) SB_FATAL("commInit: cannot reach rank 0 at %s:%d", addr, port);
+    size_t got = 0;
+    while (got < sizeof(*id)) {
+      ssize_t r = read(fd, (char*)id + got, sizeof(*id) - got);
+      if (r <= 0) SB_FATAL("commInit: rendezvous receive failed");
+      got += (size_t)r;
+    }
+    close(fd);
+    freeaddrinfo(res);
+  }
+}
+
+// ---- kernels
+__global__ void packKernel(int n, const int* __restrict__ elements, const double* __restrict__ x, double* __restrict__ out)
+{
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = x[elements[i]];   // comm.c:635-638
+}
+
+__global__ void flagExternalKernel(uint64_t n, const Entry* __restrict__ e, uint32_t startRow, uint32_t stopRow,
+    unsigned char* __restrict__ flag, uint32_t* __restrict__ col)
+{
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t c = e[i].col;
+    col[i] = c;
+    flag[i] = (c < startRow || c > stopRow) ? 1 : 0;       // comm.c:457 (stopRow inclusive)
+  }
+}
+
+__global__ void renumberKernel(uint64_t n, Entry* __restrict__ e, uint32_t startRow, uint32_t stopRow, int nExt,
+    const uint32_t* __restrict__ sortedGlobal, const uint32_t* __restrict__ sortedLocal)
+{
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t c = e[i].col;
+    if (c >= startRow && c <= stopRow) {
+      e[i].col = c - startRow;                             // comm.c:100-101
+    } else {
+      int lo = 0, hi = nExt - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (sortedGlobal[mid] < c) lo = mid + 1; else hi = mid;
+      }
+      e[i].col = sortedLocal[lo];                          // comm.c:102-104
+    }
+  }
+}
+
+static void ensureDeviceLists(Comm* c)
+{
+  CommExt* e = ext(c);
+  if (!e || c->totalSendCount == 0) return;
+  if (e->dElementsToSend && e->dElementsCount == c->totalSendCount) return;
+  sbFree(e->dElementsToSend);
+  e->dElementsToSend = (int*)allocate(64, sizeof(int) * (size_t)c->totalSendCount);
+  e->dElementsCount = c->totalSendCount;
+  sbCopyToDevice(e->dElementsToSend, c->elementsToSend, sizeof(int) * (size_t)c->totalSendCount);
+  if (!c->sendBuffer) c->sendBuffer = (CG_FLOAT*)allocate(64, sizeof(CG_FLOAT) * (size_t)c->totalSendCount);   // comm.c:124-125
+}
+
+void commExchangeOnStream(Comm* c, uint32_t numRows, double* x, cudaStream_t s)
+{
+  CommExt* e = ext(c);
+  if (!e || (c->indegree == 0 && c->outdegree == 0)) return;
+  ensureDeviceLists(c);
+  if (c->totalSendCount > 0) {
+    const int threads = 256;
+    int blocks = (c->totalSendCount + threads - 1) / threads;
+    if (blocks > ctx().numSMs * 4) blocks = ctx().numSMs * 4;
+    packKernel<<<blocks, threads, 0, s>>>(c->totalSendCount, e->dElementsToSend, x, c->sendBuffer);
+    SB_CUDA(cudaGetLastError());
+    countLaunch();
+  }
+  // MPI_Neighbor_alltoallv (comm.c:640-648): straight into the halo part of x, no receive staging
+  SB_NCCL(ncclGroupStart());
+  for (int i = 0; i < c->outdegree; i++)
+    SB_NCCL(ncclSend(c->sendBuffer + c->sdispls[i], (size_t)c->sendCounts[i], ncclDouble, c->destinations[i], e->nccl, s));
+  for (int i = 0; i < c->indegree; i++)
+    SB_NCCL(ncclRecv(x + numRows + c->rdispls[i], (size_t)c->recvCounts[i], ncclDouble, c->sources[i], e->nccl, s));
+  SB_NCCL(ncclGroupEnd());
+}
+
+void commAllreduceDevice(Comm* c, double* d, int count, int op, cudaStream_t s)
+{
+  CommExt* e = ext(c);
+  if (!e) return;
+  SB_NCCL(ncclAllReduce(d, d, (size_t)count, ncclDouble, op == SB_MAX ? ncclMax : ncclSum, e->nccl, s));
+}
+
+// all-gather of `count` ints per rank through NCCL (setup-time, tiny)
+static void allGatherInts(CommExt* e, const int* mine, int count, int* all)
+{
+  Context& c = ctx();
+  int* d = (int*)allocate(64, sizeof(int) * (size_t)count * (size_t)(e->size + 1));
+  SB_CUDA(cudaMemcpyAsync(d, mine, sizeof(int) * (size_t)count, cudaMemcpyHostToDevice, c.stream));
+  SB_NCCL(ncclAllGather(d, d + count, (size_t)count, ncclInt32, e->nccl, c.stream));
+  SB_CUDA(cudaMemcpyAsync(all, d + count, sizeof(int) * (size_t)count * (size_t)e->size, cudaMemcpyDeviceToHost, c.stream));
+  SB_CUDA(cudaStreamSynchronize(c.stream));
+  sbFree(d);
+}
+
+} // namespace sb
+
+using namespace sb;
+
+extern "C" {
+
+int sbCommUniqueIdBytes(void) { return (int)sizeof(ncclUniqueId); }
+
+void sbCommGetUniqueId(void* id) { SB_NCCL(ncclGetUniqueId((ncclUniqueId*)id)); }
+
+void sbCommInitRank(Comm* c, int rank, int size, int device, const void* id)
+{
+  attach(c, rank, size, device, (const ncclUniqueId*)id);
+}
+
+void commInit(Comm* c, int argc, char** argv)
+{
+  (void)argc; (void)argv;
+  const char* ws = getenv("WORLD_SIZE");
+  const int size = ws ? atoi(ws) : 1;
+  const int rank = getenv("RANK") ? atoi(getenv("RANK")) : 0;
+  if (size <= 1) {                        // comm.c:869-872
+    attach(c, 0, 1, 0, nullptr);
+    return;
+  }
+  const int ndev = sbDeviceCount();
+  if (ndev == 0) SB_FATAL("commInit: no CUDA device");
+  const int local = getenv("LOCAL_RANK") ? atoi(getenv("LOCAL_RANK")) : rank;
+  ncclUniqueId id;
+  if (rank == 0) SB_NCCL(ncclGetUniqueId(&id));
+  tcpBroadcastId(rank, size, &id);
+  attach(c, rank, size, local % ndev, &id);
+}
+
+void commFinalize(Comm* c)
+{
+  free(c->sources); free(c->recvCounts); free(c->rdispls);          // comm.c:896-903
+  free(c->destinations); free(c->sendCounts); free(c->sdispls);
+  free(c->elementsToSend);
+  if (c->sendBuffer) sbFree(c->sendBuffer);
+  CommExt* e = ext(c);
+  if (e) {
+    SB_CUDA(cudaDeviceSynchronize());
+    sbFree(e->dElementsToSend);
+    sbFree(e->dScalar);
+    sbFreeHost(e->hScalar);
+    ncclCommDestroy(e->nccl);
+    if (g_world == e) g_world = nullptr;
+    delete e;
+  }
+  resetLists(c);
+  c->communicator = nullptr;
+}
+
+void commReduction(CG_FLOAT* v, int op)
+{
+  CommExt* e = g_world;
+  if (!e) return;                          // single rank: no-op (comm.c:655,661)
+  Context& c = ctx();
+  e->hScalar[0] = *v;
+  SB_CUDA(cudaMemcpyAsync(e->dScalar, e->hScalar, sizeof(double), cudaMemcpyHostToDevice, c.stream));
+  SB_NCCL(ncclAllReduce(e->dScalar, e->dScalar, 1, ncclDouble, op == SB_MAX ? ncclMax : ncclSum, e->nccl, c.stream));
+  SB_CUDA(cudaMemcpyAsync(e->hScalar, e->dScalar, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  SB_CUDA(cudaStreamSynchronize(c.stream));
+  *v = e->hScalar[0];
+}
+
+void commExchange(Comm* c, CG_UINT numRows, CG_FLOAT* x) { commExchangeOnStream(c, numRows, x, ctx().stream); }
+
+void commDistributeMatrix(Comm* c, MMMatrix* m, MMMatrix* mLocal)
+{
+  if (c->size > 1) SB_FATAL("commDistributeMatrix: MatrixMarket scatter over ranks is outside this package's hot path (SURVEY 8f row 2)");
+  mLocal->startRow = 0;                    // comm.c:404-410
+  mLocal->stopRow = m->nr - 1;
+  mLocal->count = m->count;
+  mLocal->nr = m->nr;
+  mLocal->nnz = m->nnz;
+  mLocal->entries = m->entries;
+  mLocal->totalNr = m->nr;                 // left unset by the reference's single-rank branch
+  mLocal->totalNnz = m->nnz;
+}
+
+SbPartitionPlan* sbPartitionLocal(GMatrix* m, int rank, int size, const CG_UINT* startRows, int* wantCounts)
+{
+  SbPartitionPlan* P = new SbPartitionPlan();
+  const uint32_t startRow = m->startRow, stopRow = m->stopRow, nr = m->nr;
+  if (isDevicePointer(m->entries)) {
+    // device GMatrix: compact the external references in entry order, number them on the host, rewrite on the device
+    Context& c = ctx();
+    cudaStream_t s = c.stream;
+    uint32_t stored = 0;
+    SB_CUDA(cudaMemcpyAsync(&stored, m->rowPtr + nr, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    const uint64_t n = stored;
+    unsigned char* flag = (unsigned char*)allocate(64, n ? n : 1);
+    uint32_t* col = (uint32_t*)allocate(64, sizeof(uint32_t) * (n ? n : 1));
+    uint32_t* sel = (uint32_t*)allocate(64, sizeof(uint32_t) * (n ? n : 1));
+    int* dCount = (int*)allocate(64, sizeof(int));
+    const int threads = 256;
+    const int blocks = (int)std::min<uint64_t>((n + threads - 1) / threads + 1, (uint64_t)c.numSMs * 16);
+    flagExternalKernel<<<blocks, threads, 0, s>>>(n, m->entries, startRow, stopRow, flag, col);
+    SB_CUDA(cudaGetLastError());
+    size_t tmpBytes = 0;
+    SB_CUDA(cub::DeviceSelect::Flagged(nullptr, tmpBytes, col, flag, sel, dCount, (long long)n, s));
+    void* tmp = allocate(64, tmpBytes);
+    SB_CUDA(cub::DeviceSelect::Flagged(tmp, tmpBytes, col, flag, sel, dCount, (long long)n, s));   // stable: entry order kept
+    int nRefs = 0;
+    SB_CUDA(cudaMemcpyAsync(&nRefs, dCount, sizeof(int), cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    std::vector<uint32_t> refs((size_t)nRefs);
+    if (nRefs) sbCopyToHost(refs.data(), sel, sizeof(uint32_t) * (size_t)nRefs);
+    P->plan.build(refs.data(), refs.size(), rank, size, nr, startRow, startRows);
+    const int nExt = (int)P->plan.extGlobal.size();
+    std::vector<std::pair<uint32_t, uint32_t>> table((size_t)nExt);
+    for (int i = 0; i < nExt; i++) table[(size_t)i] = { P->plan.extGlobal[(size_t)i], P->plan.localId[(size_t)i] };
+    std::sort(table.begin(), table.end());
+    std::vector<uint32_t> g((size_t)nExt), l((size_t)nExt);
+    for (int i = 0; i < nExt; i++) { g[(size_t)i] = table[(size_t)i].first; l[(size_t)i] = table[(size_t)i].second; }
+    uint32_t* dg = (uint32_t*)allocate(64, sizeof(uint32_t) * (size_t)(nExt ? nExt : 1));
+    uint32_t* dl = (uint32_t*)allocate(64, sizeof(uint32_t) * (size_t)(nExt ? nExt : 1));
+    if (nExt) {
+      sbCopyToDevice(dg, g.data(), sizeof(uint32_t) * (size_t)nExt);
+      sbCopyToDevice(dl, l.data(), sizeof(uint32_t) * (size_t)nExt);
+    }
+    renumberKernel<<<blocks, threads, 0, s>>>(n, m->entries, startRow, stopRow, nExt, dg, dl);
+    SB_CUDA(cudaGetLastError());
+    SB_CUDA(cudaStreamSynchronize(s));
+    sbFree(flag); sbFree(col); sbFree(sel); sbFree(dCount); sbFree(tmp); sbFree(dg); sbFree(dl);
+  } else {
+    const uint32_t stored = m->rowPtr[nr];
+    std::vector<uint32_t> refs;
+    for (uint32_t j = 0; j < stored; j++) {
+      const uint32_t col = m->entries[j].col;
+      if (col < startRow || col > stopRow) refs.push_back(col);
+    }
+    P->plan.build(refs.data(), refs.size(), rank, size, nr, startRow, startRows);
+    for (uint32_t j = 0; j < stored; j++) m->entries[j].col = P->plan.renumber(m->entries[j].col, stopRow);
+  }
+  m->nc = m->nc + (CG_UINT)P->plan.extGlobal.size();        // comm.c:616
+  for (int o = 0; o < size; o++) wantCounts[o] = P->plan.want[(size_t)o];
+  return P;
+}
+
+const int* sbPartitionRequestSlice(SbPartitionPlan* P, const int* wantMatrix, int source, int* count)
+{
+  const int* ptr = nullptr;
+  P->plan.requestSlice(wantMatrix, source, &ptr, count);
+  return ptr;
+}
+
+static int* dupInts(const std::vector<int>& v)
+{
+  int* p = (int*)malloc(sizeof(int) * (v.size() ? v.size() : 1));
+  if (!v.empty()) memcpy(p, v.data(), sizeof(int) * v.size());
+  return p;
+}
+
+void sbPartitionFinish(SbPartitionPlan* P, Comm* c, const int* wantMatrix, const int* received)
+{
+  CommLists L;
+  P->plan.finish(L, wantMatrix, received);
+  c->externalCount = L.externalCount;
+  c->totalSendCount = L.totalSendCount;
+  c->indegree = (int)L.sources.size();
+  c->outdegree = (int)L.destinations.size();
+  c->sources = dupInts(L.sources); c->recvCounts = dupInts(L.recvCounts); c->rdispls = dupInts(L.rdispls);
+  c->destinations = dupInts(L.destinations); c->sendCounts = dupInts(L.sendCounts); c->sdispls = dupInts(L.sdispls);
+  c->elementsToSend = dupInts(L.elementsToSend);
+  c->sendBuffer = nullptr;                                   // device buffer, created with the device lists
+  delete P;
+}
+
+void commPartition(Comm* c, GMatrix* m)
+{
+  const int size = c->size, rank = c->rank;
+  CommExt* e = ext(c);
+  if (size <= 1) {   // one row block: every column is local already, all lists stay empty (startRow is 0)
+    resetLists(c);
+    c->sources = dupInts({}); c->recvCounts = dupInts({}); c->rdispls = dupInts({});
+    c->destinations = dupInts({}); c->sendCounts = dupInts({}); c->sdispls = dupInts({});
+    c->elementsToSend = dupInts({});
+    return;
+  }
+  if (size > 1 && !e) SB_FATAL("commPartition: Comm has %d ranks but no communicator (call commInit first)", size);
+  std::vector<CG_UINT> startRows((size_t)size);
+  std::vector<int> wantMatrix((size_t)size * size), mine((size_t)size);
+  if (size > 1) {
+    int my = (int)m->startRow;
+    std::vector<int> all((size_t)size);
+    allGatherInts(e, &my, 1, all.data());                   // comm.c:496-502
+    for (int i = 0; i < size; i++) startRows[(size_t)i] = (CG_UINT)all[(size_t)i];
+  } else {
+    startRows[0] = m->startRow;
+  }
+  SbPartitionPlan* P = sbPartitionLocal(m, rank, size, startRows.data(), mine.data());
+  if (size > 1) allGatherInts(e, mine.data(), size, wantMatrix.data());
+  else wantMatrix[0] = mine[0];
+  // request lists: requester -> owner (comm.c:130-161)
+  int total = 0;
+  std::vector<int> recvOff((size_t)size, 0);
+  for (int s = 0; s < size; s++) {
+    recvOff[(size_t)s] = total;
+    total += wantMatrix[(size_t)s * size + rank];
+  }
+  std::vector<int> received((size_t)(total ? total : 1));
+  if (size > 1) {
+    Context& cx = ctx();
+    int nReq = 0;
+    for (int s = 0; s < size; s++) nReq += wantMatrix[(size_t)rank * size + s];
+    int* dSend = (int*)allocate(64, sizeof(int) * (size_t)(nReq ? nReq : 1));
+    int* dRecv = (int*)allocate(64, sizeof(int) * (size_t)(total ? total : 1));
+    if (nReq) sbCopyToDevice(dSend, P->plan.requests.data(), sizeof(int) * (size_t)nReq);
+    SB_NCCL(ncclGroupStart());
+    for (int s = 0; s < size; s++) {
+      int cnt = 0;
+      const int* slice = sbPartitionRequestSlice(P, wantMatrix.data(), s, &cnt);
+      if (cnt > 0) SB_NCCL(ncclSend(dSend + (slice - P->plan.requests.data()), (size_t)cnt, ncclInt32, s, e->nccl, cx.stream));
+      const int in = wantMatrix[(size_t)s * size + rank];
+      if (in > 0) SB_NCCL(ncclRecv(dRecv + recvOff[(size_t)s], (size_t)in, ncclInt32, s, e->nccl, cx.stream));
+    }
+    SB_NCCL(ncclGroupEnd());
+    if (total) sbCopyToHost(received.data(), dRecv, sizeof(int) * (size_t)total);
+    else SB_CUDA(cudaStreamSynchronize(cx.stream));
+    sbFree(dSend); sbFree(dRecv);
+  }
+  sbPartitionFinish(P, c, wantMatrix.data(), received.data());
+  if (size > 1) ensureDeviceLists(c);
+}
+
+} // extern "C"

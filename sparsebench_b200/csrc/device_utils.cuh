@@ -1,0 +1,81 @@
+// Device-side helpers shared by the hot-path kernels: streaming loads, reference-order arithmetic and the
+// deterministic one-kernel grid reduction used by every dot product.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sb {
+
+// Matrix values / indices are read exactly once per SpMV: keep them out of L1 so the cache stays with the
+// gathered x vector (B200: 256 KB L1+smem per SM, 126 MB L2).
+__device__ __forceinline__ double ldStream(const double* p)
+{
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t ldStream(const uint32_t* p)
+{
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double2 ldStream2(const double* p)
+{
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
+// The reference accumulates `sum += val * x` with a separately rounded multiply and add (strict C, no
+// contraction on baseline x86-64). Keeping that order and rounding makes row sums bit-identical to the
+// reference's; fp64 pipes are <5 % utilised by an HBM-bound SpMV, so the extra instruction is free.
+__device__ __forceinline__ double mulAdd(double acc, double a, double b) { return __dadd_rn(acc, __dmul_rn(a, b)); }
+
+__device__ __forceinline__ double warpSum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over the block in a fixed order; result valid in thread 0. `scratch` holds >= 32 doubles.
+__device__ __forceinline__ double blockSum(double v, double* scratch)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+  v = warpSum(v);
+  __syncthreads();              // scratch may still be in use by a previous call
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (warp == 0) {
+    t = lane < nwarps ? scratch[lane] : 0.0;
+    t = warpSum(t);
+  }
+  return t;
+}
+
+// One-kernel grid reduction: every block deposits its partial, the last block to arrive (atomic ticket)
+// adds all partials in a fixed order, so the result does not depend on block scheduling.
+// out = (accumulate ? *out : 0) + sum(partials). The ticket resets itself for the next launch.
+__device__ __forceinline__ void gridSum(double blockPartial, double* partials, unsigned int* ticket, double* out,
+    bool accumulate, double* scratch)
+{
+  __shared__ bool amLast;
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = blockPartial;
+    __threadfence();
+    const unsigned int t = atomicInc(ticket, gridDim.x - 1);
+    amLast = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (amLast) {
+    __threadfence();
+    double v = 0.0;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) v += __ldcg(partials + i);
+    v = blockSum(v, scratch);
+    if (threadIdx.x == 0) *out = accumulate ? (*out + v) : v;
+  }
+}
+
+} // namespace sb

@@ -1,0 +1,133 @@
+// Internal declarations shared by the translation units of libsparsebench_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "sparsebench_b200.h"
+
+// Error convention of the reference: message + exit(EXIT_FAILURE) (allocate.c:19-33).
+#define SB_CUDA(call)                                                                          \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) {                                                                   \
+      fprintf(stderr, "sparsebench_b200: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e_),  \
+          __FILE__, __LINE__, cudaGetErrorString(e_));                                         \
+      exit(EXIT_FAILURE);                                                                      \
+    }                                                                                          \
+  } while (0)
+
+#define SB_FATAL(...)                                                                          \
+  do {                                                                                         \
+    fprintf(stderr, "sparsebench_b200: " __VA_ARGS__);                                         \
+    fprintf(stderr, "\n");                                                                     \
+    exit(EXIT_FAILURE);                                                                        \
+  } while (0)
+
+namespace sb {
+
+constexpr int kMaxPartials = 4096;   // upper bound on reduction blocks of any kernel
+
+// Per-process device context: one stream, reduction scratch, launch counter.
+struct Context {
+  int device = -1;
+  int numSMs = 0;
+  cudaStream_t stream = nullptr;     // blocking stream: ordered with the legacy default stream
+  cudaStream_t commStream = nullptr; // halo exchange side stream
+  double* partials = nullptr;        // kMaxPartials doubles per reduction slot, 4 slots
+  unsigned int* tickets = nullptr;   // last-block tickets, one per reduction slot
+  double* dScalar = nullptr;         // small device scalar block (64 doubles)
+  double* hScalar = nullptr;         // pinned mirror
+  void* flushBuf = nullptr;
+  size_t flushBytes = 0;
+  size_t launches = 0;
+};
+Context& ctx();                      // lazily initialised on first use; exits if no CUDA device
+inline void countLaunch(int n = 1) { ctx().launches += (size_t)n; }
+
+bool isDevicePointer(const void* p);
+
+// ---- sparse formats: device-side views the kernels take
+struct CrsView {
+  uint32_t nr;
+  const uint32_t* rowPtr;
+  const uint32_t* col;
+  const double* val;
+};
+struct SellView {
+  uint32_t nChunks, nr, C;
+  const uint32_t* chunkPtr;
+  const uint32_t* chunkLens;
+  const uint32_t* col;
+  const double* val;
+};
+struct CcrsView {
+  uint32_t nr;
+  const uint32_t* rowPtr;
+  const Entry* entries;
+};
+
+// A sparse operator as the CG driver sees it.
+struct Operator {
+  int fmt;
+  uint32_t nr = 0, nc = 0, nrPadded = 0;   // vectors written by spmv need nrPadded slots
+  uint64_t nnzTrue = 0;
+  const uint32_t* rowPtr = nullptr;        // CRS/CCRS: device rowPtr (b = 27-(len-1) rule); SCS: original-order rowLen
+  const uint32_t* rowLen = nullptr;        // SCS: row lengths in vector (permuted) order
+  const uint32_t* oldToNew = nullptr;      // SCS with sigma>1: vectors live in permuted order
+  const uint32_t* newToOld = nullptr;
+  CrsView crs{};
+  SellView sell{};                         // col = symmetric-permuted columns when oldToNew != nullptr
+  CcrsView ccrs{};
+};
+
+// Fused dot-product epilogue: *out = (accumulate ? *out : 0) + sum, reduced through scratch slot `slot` (0..3).
+struct DotArgs {
+  double* out;
+  bool accumulate;
+  int slot;
+};
+// y = A x on units [lo,hi) (rows for CRS/CCRS, chunks for SELL); with `dot` also sum_i x[i]*y[i] over them.
+uint32_t spmvUnits(const Operator& A);
+void launchSpmv(const Operator& A, const double* x, double* y, uint32_t lo, uint32_t hi, const DotArgs* dot,
+    cudaStream_t s);
+
+// ---- vector kernels (vecops.cu)
+void launchWaxpby(uint32_t n, double alpha, const double* x, double beta, const double* y, double* w, cudaStream_t s);
+// *dResult (device) = sum x[i]*y[i], deterministic one-kernel grid reduction through scratch slot `slot`
+void launchDot(uint32_t n, const double* x, const double* y, double* dResult, int slot, cudaStream_t s);
+// fused CG passes: rho[j] = r_j.r_j, pAp[k] = p_k.Ap_k live on the device, k is the 1-based iteration
+void launchCgUpdateP(uint32_t n, int k, const double* rho, const double* r, double* p, cudaStream_t s);
+void launchCgUpdateXR(uint32_t n, int k, double* rho, const double* pAp, double* x, double* r, const double* p,
+    const double* Ap, int slot, cudaStream_t s);
+void launchInitVectors(uint32_t n, const uint32_t* rowPtr, const uint32_t* rowLen, bool generated, double* x, double* b,
+    cudaStream_t s);
+void launchScatter(uint32_t n, const uint32_t* map, const double* in, double* out, cudaStream_t s);   // out[map[i]] = in[i]
+void launchGather(uint32_t n, const uint32_t* map, const double* in, double* out, cudaStream_t s);    // out[i] = in[map[i]]
+void launchMaxErr(uint32_t n, const double* x, double* out, cudaStream_t s);
+
+// ---- communication (comm.cu)
+void commExchangeOnStream(Comm* c, uint32_t numRows, double* x, cudaStream_t s);
+void commAllreduceDevice(Comm* c, double* d, int count, int op, cudaStream_t s);
+
+// ---- side tables keyed by the device array a Matrix struct points to
+struct ScsExt {
+  uint32_t* colPerm = nullptr;   // symmetric-permuted column ids (CG keeps vectors in permuted order)
+  uint32_t* rowLenPerm = nullptr;
+  uint32_t* rowLenOrig = nullptr;
+  bool identityPerm = true;
+  uint64_t nnzTrue = 0;
+  uint32_t nc = 0;               // columns incl. halo (the reference's SCS struct drops it, matrix-SCS.c:38)
+};
+struct CrsExt {
+  uint64_t nnzTrue = 0;
+  bool ownsArrays = true;
+};
+ScsExt* scsExt(const void* key, bool create);
+CrsExt* crsExt(const void* key, bool create);
+void eraseExt(const void* key);
+
+Operator makeOperator(void* matrix, int fmt);
+
+} // namespace sb

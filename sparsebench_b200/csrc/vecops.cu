@@ -1,0 +1,317 @@
+// Krylov vector kernels (replace waxpby / ddot of solver.c:16-62) and their fused single-pass forms used by
+// the CG driver. All are pure HBM streams: grid = numSMs * 8 CTAs, 16-byte vector accesses, arithmetic in the
+// reference's rounding (separate multiply and add), dot products through the deterministic grid reduction.
+#include "device_utils.cuh"
+#include "sb_internal.h"
+
+namespace sb {
+
+constexpr int kVecThreads = 256;
+
+static inline int vecGrid(uint64_t n, int perThread)
+{
+  Context& c = ctx();
+  uint64_t blocks = (n + (uint64_t)kVecThreads * perThread - 1) / ((uint64_t)kVecThreads * perThread);
+  uint64_t cap = (uint64_t)c.numSMs * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks > (uint64_t)kMaxPartials) blocks = kMaxPartials;
+  return (int)(blocks ? blocks : 1);
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// MODE 0: w = x + beta*y   (alpha == 1, solver.c:24-27)
+// MODE 1: w = alpha*x + y  (beta == 1,  solver.c:29-32)
+// MODE 2: w = alpha*x + beta*y          (solver.c:34-37)
+template <int MODE>
+__device__ __forceinline__ double waxpbyOne(double alpha, double x, double beta, double y)
+{
+  if (MODE == 0) return __dadd_rn(x, __dmul_rn(beta, y));
+  if (MODE == 1) return __dadd_rn(__dmul_rn(alpha, x), y);
+  return __dadd_rn(__dmul_rn(alpha, x), __dmul_rn(beta, y));
+}
+
+// w may alias x or y (the CG calls it in place, CGSolver.c:114,127,128): every element is read before it is
+// written by the same thread, so no __restrict__ here.
+template <int MODE, bool VEC>
+__global__ void __launch_bounds__(kVecThreads)
+waxpbyKernel(uint32_t n, double alpha, const double* x, double beta, const double* y, double* w)
+{
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (VEC) {
+    const uint64_t n2 = n / 2;
+    const double2* x2 = reinterpret_cast<const double2*>(x);
+    const double2* y2 = reinterpret_cast<const double2*>(y);
+    double2* w2 = reinterpret_cast<double2*>(w);
+    for (uint64_t i = tid; i < n2; i += stride) {
+      const double2 a = x2[i], b = y2[i];
+      double2 r;
+      r.x = waxpbyOne<MODE>(alpha, a.x, beta, b.x);
+      r.y = waxpbyOne<MODE>(alpha, a.y, beta, b.y);
+      w2[i] = r;
+    }
+    if (tid == 0 && (n & 1u)) w[n - 1] = waxpbyOne<MODE>(alpha, x[n - 1], beta, y[n - 1]);
+  } else {
+    for (uint64_t i = tid; i < n; i += stride) w[i] = waxpbyOne<MODE>(alpha, x[i], beta, y[i]);
+  }
+}
+
+void launchWaxpby(uint32_t n, double alpha, const double* x, double beta, const double* y, double* w, cudaStream_t s)
+{
+  if (n == 0) return;
+  const bool vec = aligned16(x) && aligned16(y) && aligned16(w);
+  const int grid = vecGrid(n, vec ? 4 : 2);
+  const int mode = (alpha == 1.0) ? 0 : (beta == 1.0) ? 1 : 2;
+#define SB_LAUNCH(M)                                                                        \
+  do {                                                                                      \
+    if (vec) waxpbyKernel<M, true><<<grid, kVecThreads, 0, s>>>(n, alpha, x, beta, y, w);   \
+    else waxpbyKernel<M, false><<<grid, kVecThreads, 0, s>>>(n, alpha, x, beta, y, w);      \
+  } while (0)
+  if (mode == 0) SB_LAUNCH(0);
+  else if (mode == 1) SB_LAUNCH(1);
+  else SB_LAUNCH(2);
+#undef SB_LAUNCH
+  SB_CUDA(cudaGetLastError());
+  countLaunch();
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kVecThreads)
+dotKernel(uint32_t n, const double* __restrict__ x, const double* __restrict__ y, double* partials, unsigned int* ticket,
+    double* out)
+{
+  __shared__ double scratch[32];
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  double acc = 0.0;
+  if (VEC) {
+    const uint64_t n2 = n / 2;
+    const double2* x2 = reinterpret_cast<const double2*>(x);
+    const double2* y2 = reinterpret_cast<const double2*>(y);
+    double a0 = 0.0, a1 = 0.0;
+    for (uint64_t i = tid; i < n2; i += stride) {
+      const double2 a = x2[i], b = y2[i];
+      a0 = fma(a.x, b.x, a0);
+      a1 = fma(a.y, b.y, a1);
+    }
+    acc = a0 + a1;
+    if (tid == 0 && (n & 1u)) acc = fma(x[n - 1], y[n - 1], acc);
+  } else {
+    for (uint64_t i = tid; i < n; i += stride) acc = fma(x[i], y[i], acc);
+  }
+  const double b = blockSum(acc, scratch);
+  gridSum(b, partials, ticket, out, false, scratch);
+}
+
+void launchDot(uint32_t n, const double* x, const double* y, double* dResult, int slot, cudaStream_t s)
+{
+  Context& c = ctx();
+  if (n == 0) {
+    SB_CUDA(cudaMemsetAsync(dResult, 0, sizeof(double), s));
+    return;
+  }
+  const bool vec = aligned16(x) && aligned16(y);
+  const int grid = vecGrid(n, vec ? 4 : 2);
+  if (vec)
+    dotKernel<true><<<grid, kVecThreads, 0, s>>>(n, x, y, c.partials + (size_t)slot * kMaxPartials, c.tickets + slot, dResult);
+  else
+    dotKernel<false><<<grid, kVecThreads, 0, s>>>(n, x, y, c.partials + (size_t)slot * kMaxPartials, c.tickets + slot, dResult);
+  SB_CUDA(cudaGetLastError());
+  countLaunch();
+}
+
+// ------------------------------------------------------------------------------------------- fused CG passes
+// rho[j] = r_j . r_j (rho[0] from the initial residual), pAp[k] = p_k . A p_k. Iteration k (1-based,
+// CGSolver.c:107-129) uses rtrans = rho[k-1], oldrtrans = rho[k-2].
+
+// p = r + beta*p with beta = rho[k-1]/rho[k-2]  (CGSolver.c:111-114); k == 1: p = r + 0*r (:109).
+__global__ void __launch_bounds__(kVecThreads)
+cgUpdatePKernel(uint32_t n, int k, const double* __restrict__ rho, const double* __restrict__ r, double* __restrict__ p)
+{
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t n2 = n / 2;
+  const double2* r2 = reinterpret_cast<const double2*>(r);
+  double2* p2 = reinterpret_cast<double2*>(p);
+  if (k == 1) {
+    for (uint64_t i = tid; i < n2; i += stride) {
+      const double2 a = r2[i];
+      double2 o;
+      o.x = __dadd_rn(a.x, __dmul_rn(0.0, a.x));
+      o.y = __dadd_rn(a.y, __dmul_rn(0.0, a.y));
+      p2[i] = o;
+    }
+    if (tid == 0 && (n & 1u)) p[n - 1] = __dadd_rn(r[n - 1], __dmul_rn(0.0, r[n - 1]));
+    return;
+  }
+  const double beta = __ddiv_rn(rho[k - 1], rho[k - 2]);
+  for (uint64_t i = tid; i < n2; i += stride) {
+    const double2 a = r2[i], b = p2[i];
+    double2 o;
+    o.x = __dadd_rn(a.x, __dmul_rn(beta, b.x));
+    o.y = __dadd_rn(a.y, __dmul_rn(beta, b.y));
+    p2[i] = o;
+  }
+  if (tid == 0 && (n & 1u)) p[n - 1] = __dadd_rn(r[n - 1], __dmul_rn(beta, p[n - 1]));
+}
+
+// alpha = rho[k-1]/pAp[k]; x += alpha*p; r += (-alpha)*Ap; rho[k] = r.r   (CGSolver.c:126-128 + :112 of the
+// next iteration, which reads the same r)
+__global__ void __launch_bounds__(kVecThreads)
+cgUpdateXRKernel(uint32_t n, int k, double* __restrict__ rho, const double* __restrict__ pAp, double* __restrict__ x,
+    double* __restrict__ r, const double* __restrict__ p, const double* __restrict__ Ap, double* partials,
+    unsigned int* ticket)
+{
+  __shared__ double scratch[32];
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const double alpha = __ddiv_rn(rho[k - 1], pAp[k]);
+  const double nalpha = -alpha;
+  const uint64_t n2 = n / 2;
+  double2* x2 = reinterpret_cast<double2*>(x);
+  double2* r2 = reinterpret_cast<double2*>(r);
+  const double2* p2 = reinterpret_cast<const double2*>(p);
+  const double2* q2 = reinterpret_cast<const double2*>(Ap);
+  double a0 = 0.0, a1 = 0.0;
+  for (uint64_t i = tid; i < n2; i += stride) {
+    const double2 xv = x2[i], pv = p2[i], rv = r2[i], qv = q2[i];
+    double2 xo, ro;
+    xo.x = __dadd_rn(xv.x, __dmul_rn(alpha, pv.x));
+    xo.y = __dadd_rn(xv.y, __dmul_rn(alpha, pv.y));
+    ro.x = __dadd_rn(rv.x, __dmul_rn(nalpha, qv.x));
+    ro.y = __dadd_rn(rv.y, __dmul_rn(nalpha, qv.y));
+    x2[i] = xo;
+    r2[i] = ro;
+    a0 = fma(ro.x, ro.x, a0);
+    a1 = fma(ro.y, ro.y, a1);
+  }
+  double acc = a0 + a1;
+  if (tid == 0 && (n & 1u)) {
+    const uint32_t i = n - 1;
+    x[i] = __dadd_rn(x[i], __dmul_rn(alpha, p[i]));
+    const double ro = __dadd_rn(r[i], __dmul_rn(nalpha, Ap[i]));
+    r[i] = ro;
+    acc = fma(ro, ro, acc);
+  }
+  const double b = blockSum(acc, scratch);
+  gridSum(b, partials, ticket, rho + k, false, scratch);
+}
+
+void launchCgUpdateP(uint32_t n, int k, const double* rho, const double* r, double* p, cudaStream_t s)
+{
+  if (n == 0) return;
+  cgUpdatePKernel<<<vecGrid(n, 4), kVecThreads, 0, s>>>(n, k, rho, r, p);
+  SB_CUDA(cudaGetLastError());
+  countLaunch();
+}
+
+void launchCgUpdateXR(uint32_t n, int k, double* rho, const double* pAp, double* x, double* r, const double* p,
+    const double* Ap, int slot, cudaStream_t s)
+{
+  Context& c = ctx();
+  if (n == 0) {
+    SB_CUDA(cudaMemsetAsync(rho + k, 0, sizeof(double), s));
+    return;
+  }
+  cgUpdateXRKernel<<<vecGrid(n, 4), kVecThreads, 0, s>>>(n, k, rho, pAp, x, r, p, Ap,
+      c.partials + (size_t)slot * kMaxPartials, c.tickets + slot);
+  SB_CUDA(cudaGetLastError());
+  countLaunch();
+}
+
+// ------------------------------------------------------------------------------------------- setup helpers
+// initVectors (CGSolver.c:19-38): x = 0, b = 27 - (rowLen - 1) for generated matrices, else b = 1.
+__global__ void initVectorsKernel(uint32_t n, const uint32_t* __restrict__ rowPtr, const uint32_t* __restrict__ rowLen,
+    int generated, double* __restrict__ x, double* __restrict__ b)
+{
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int len = rowLen ? (int)rowLen[i] : (int)(rowPtr[i + 1] - rowPtr[i]);
+    x[i] = 0.0;
+    b[i] = generated ? 27.0 - (double)(len - 1) : 1.0;
+  }
+}
+
+void launchInitVectors(uint32_t n, const uint32_t* rowPtr, const uint32_t* rowLen, bool generated, double* x, double* b,
+    cudaStream_t s)
+{
+  if (n == 0) return;
+  initVectorsKernel<<<vecGrid(n, 1), kVecThreads, 0, s>>>(n, rowPtr, rowLen, generated ? 1 : 0, x, b);
+  SB_CUDA(cudaGetLastError());
+  countLaunch();
+}
+
+// out[map[i]] = in[i]  /  out[i] = in[map[i]]  (SELL row permutation of the CG vectors)
+__global__ void scatterKernel(uint32_t n, const uint32_t* __restrict__ map, const double* __restrict__ in, double* __restrict__ out)
+{
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[map[i]] = in[i];
+}
+__global__ void gatherKernel(uint32_t n, const uint32_t* __restrict__ map, const double* __restrict__ in, double* __restrict__ out)
+{
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = in[map[i]];
+}
+void launchScatter(uint32_t n, const uint32_t* map, const double* in, double* out, cudaStream_t s)
+{
+  if (n == 0) return;
+  scatterKernel<<<vecGrid(n, 1), kVecThreads, 0, s>>>(n, map, in, out);
+  SB_CUDA(cudaGetLastError());
+  countLaunch();
+}
+void launchGather(uint32_t n, const uint32_t* map, const double* in, double* out, cudaStream_t s)
+{
+  if (n == 0) return;
+  gatherKernel<<<vecGrid(n, 1), kVecThreads, 0, s>>>(n, map, in, out);
+  SB_CUDA(cudaGetLastError());
+  countLaunch();
+}
+
+// max_i |x[i] - 1| (solverCheckResidual, CGSolver.c:40-60 with xexact == 1)
+__global__ void maxErrKernel(uint32_t n, const double* __restrict__ x, double* out)
+{
+  __shared__ double sm[kVecThreads];
+  double m = 0.0;
+  bool nan = false;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double d = fabs(x[i] - 1.0);
+    if (d > m) m = d;        // NaN never compares greater, as in the reference loop (CGSolver.c:50-53)
+    (void)nan;
+  }
+  sm[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o && sm[threadIdx.x + o] > sm[threadIdx.x]) sm[threadIdx.x] = sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sm[0];
+}
+void launchMaxErr(uint32_t n, const double* x, double* out, cudaStream_t s)
+{
+  maxErrKernel<<<1, kVecThreads, 0, s>>>(n, x, out);
+  SB_CUDA(cudaGetLastError());
+  countLaunch();
+}
+
+} // namespace sb
+
+using namespace sb;
+
+extern "C" {
+
+void waxpby(const CG_UINT n, const CG_FLOAT alpha, const CG_FLOAT* x, const CG_FLOAT beta, const CG_FLOAT* y,
+    CG_FLOAT* w)
+{
+  launchWaxpby(n, alpha, x, beta, y, w, ctx().stream);
+}
+
+void ddot(const CG_UINT n, const CG_FLOAT* x, const CG_FLOAT* y, CG_FLOAT* result)
+{
+  Context& c = ctx();
+  launchDot(n, x, y, c.dScalar, 0, c.stream);
+  SB_CUDA(cudaMemcpyAsync(c.hScalar, c.dScalar, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  SB_CUDA(cudaStreamSynchronize(c.stream));
+  double sum = c.hScalar[0];
+  commReduction(&sum, SB_SUM);      // solver.c:60
+  *result = sum;
+}
+
+} // extern "C"

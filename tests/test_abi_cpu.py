@@ -1,0 +1,145 @@
+"""CPU-side checks of the product: the C-ABI library loads without a GPU, exports every symbol the header
+declares, and its host-only entry points (matrixGenerate, the commPartition halves) match the oracle / the
+reference outputs bit for bit. No compute call needs a device here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import orc
+from sparsebench_b200 import _lib, api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "sparsebench_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = text[text.index("/* ") if "/* " in text else 0:]
+    names = re.findall(r"^[A-Za-z_][\w \*]*?\b(\w+)\s*\([^;{]*\)\s*;", text, flags=re.M)
+    return sorted(set(names))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    L = _lib.load()
+    names = declared_symbols()
+    assert len(names) >= 40, names
+    for expected in ("allocate", "getTimeStamp", "waxpby", "ddot", "commPartition", "commExchange", "commReduction",
+                     "commInit", "commFinalize", "matrixGenerate", "sbCRS_spMVM", "sbSCS_convertMatrix", "sbSolveCG"):
+        assert expected in names
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+@pytest.mark.parametrize("fmt", ["CRS", "SCS", "CCRS"])
+def test_dropin_shims_export_reference_names(fmt):
+    S = _lib.load_dropin(fmt)
+    for n in ("convertMatrix", "spMVM", "solveCG"):       # matrix.h:57, solver.h:11-13
+        assert hasattr(S, n)
+
+
+def test_struct_layouts_match_reference_headers():
+    # CG_UINT = unsigned int, pointers 8 bytes: CRSMatrix.h:9-16, SCSMatrix.h:13-27, matrix.h:29-35, comm.h:27-46
+    assert C.sizeof(api.GMatrix) == 48 and C.sizeof(api.CRSMatrix) == 56 and C.sizeof(api.CCRSMatrix) == 48
+    assert C.sizeof(api.SCSMatrix) == 32 + 16 + 24 + 32 and api.SCSMatrix.C.offset == 48
+    assert C.sizeof(api.Parameter) == 32 and api.ENTRY_DTYPE.itemsize == 16
+    assert api.Comm.elementsToSend.offset == 24 and api.Comm.communicator.offset == 96
+
+
+@pytest.mark.parametrize("nx,ny,nz,rank,size,use7", [(4, 3, 2, 0, 1, False), (5, 4, 3, 1, 3, False), (3, 3, 3, 2, 3, True),
+                                                     (1, 1, 5, 0, 2, False), (16, 16, 8, 3, 4, False)])
+def test_host_matrixGenerate_bit_exact(nx, ny, nz, rank, size, use7):
+    g = api.matrixGenerate(nx, ny, nz, rank, size, use7)
+    rp, col, val = api.gmatrix_arrays(g)
+    m = orc.generate(nx, ny, nz, rank, size, use7)
+    assert np.array_equal(rp, m.rowPtr) and np.array_equal(col, m.col) and np.array_equal(val, m.val)
+    n = nx * ny * nz
+    assert (g.nr, g.nc, g.nnz, g.totalNr, g.totalNnz, g.startRow, g.stopRow) == \
+        (n, n, 27 * n, n * size, 27 * n * size, n * rank, n * rank + n - 1)      # matrix.c:114-120
+    api.lib().sbFreeGMatrix(C.byref(g))
+
+
+def partition_serial(mats):
+    """Drives sbPartitionLocal / sbPartitionRequestSlice / sbPartitionFinish for all ranks in one process."""
+    L = api.lib()
+    P = len(mats)
+    starts = np.array([g.startRow for g in mats], np.uint32)
+    want = np.zeros((P, P), np.int32)
+    plans = []
+    for r, g in enumerate(mats):
+        w = np.zeros(P, np.int32)
+        plans.append(L.sbPartitionLocal(C.byref(g), r, P, starts.ctypes.data, w.ctypes.data))
+        want[r] = w
+    comms = []
+    for r in range(P):
+        received = []
+        for s in range(P):                     # ascending requester
+            if want[s, r] > 0:
+                cnt = C.c_int(0)
+                ptr = L.sbPartitionRequestSlice(plans[s], want.ctypes.data, r, C.byref(cnt))
+                assert cnt.value == want[s, r]
+                received += [ptr[i] for i in range(cnt.value)]
+        received = np.array(received + [0], np.int32)
+        comms.append((r, received))
+    out = []
+    for r, received in comms:
+        c = api.Comm()
+        c.rank, c.size = r, P
+        L.sbPartitionFinish(plans[r], C.byref(c), want.ctypes.data, received.ctypes.data)
+        out.append(c)
+    return out
+
+
+MPI_CASES = [(3, 3, 3, 2, False), (2, 4, 3, 2, False), (4, 5, 4, 3, True), (8, 16, 16, 4, False), (1, 4, 4, 4, False)]
+
+
+@pytest.mark.parametrize("P,nx,ny,nz,use7", MPI_CASES)
+def test_partition_lists_bit_exact_vs_unmodified_comm_c(golden, P, nx, ny, nz, use7):
+    """comm.c:414-625 pinned by the shim-driven reference run (tests/golden/make_golden.py)."""
+    mats = [api.matrixGenerate(nx, ny, nz, r, P, use7) for r in range(P)]
+    comms = partition_serial(mats)
+    cfg = "mpi_P%d_%dx%dx%d_%d_" % (P, nx, ny, nz, int(use7))
+    for r in range(P):
+        d = comms[r].lists()
+        sc = golden[cfg + "r%d_scalars" % r]
+        assert [mats[r].nr, mats[r].nc, d["externalCount"], d["totalSendCount"]] == list(sc[:4])
+        for f in ("sources", "recvCounts", "rdispls", "destinations", "sendCounts", "sdispls", "elementsToSend"):
+            assert np.array_equal(golden[cfg + "r%d_%s" % (r, f)], d[f]), (r, f)
+        rp, col, _ = api.gmatrix_arrays(mats[r])
+        assert np.array_equal(golden[cfg + "r%d_cols" % r], col)
+        assert np.array_equal(golden[cfg + "r%d_rowPtr" % r], rp)
+
+
+def test_partition_matches_oracle_on_irregular_matrix():
+    """A banded + random-long-range matrix split over 5 ranks of unequal size (owners first met out of order)."""
+    rng = np.random.default_rng(11)
+    N, P = 300, 5
+    rows = []
+    for i in range(N):
+        cols = {i, max(i - 1, 0), min(i + 1, N - 1), int(rng.integers(0, N)), int(rng.integers(0, N))}
+        rows.append(sorted(cols, key=lambda c: (c * 7919) % N))      # scrambled order inside the row
+    bounds = [0, 50, 120, 130, 220, 300]
+    omats, gmats = [], []
+    for r in range(P):
+        lo, hi = bounds[r], bounds[r + 1]
+        rp = np.zeros(hi - lo + 1, np.uint32)
+        col = []
+        for i in range(lo, hi):
+            col += rows[i]
+            rp[i - lo + 1] = len(col)
+        col = np.array(col, np.uint32)
+        val = rng.standard_normal(len(col))
+        omats.append(orc.Csr(rp, col.copy(), val, startRow=lo, totalNr=N))
+        gmats.append(api.gmatrix_from_csr(rp, col.copy(), val, startRow=lo, totalNr=N))
+    part = orc.Partition(omats)
+    comms = partition_serial(gmats)
+    for r in range(P):
+        d = comms[r].lists()
+        o = part.ranks[r]
+        for f in ("externalCount", "totalSendCount"):
+            assert d[f] == o[f]
+        for f in ("sources", "recvCounts", "rdispls", "destinations", "sendCounts", "sdispls", "elementsToSend"):
+            assert np.array_equal(d[f], o[f]), (r, f)
+        assert np.array_equal(api.gmatrix_arrays(gmats[r])[1], omats[r].col)
