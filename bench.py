@@ -59,50 +59,62 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML DURING the timed region (same counters as the
+    nvidia-smi line of B200_PROFILING.md, without a subprocess whose output would be block-buffered)."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, device):
         self.device = device
-        self.proc = None
-        self.tmp = None
+        self.samples, self.bits, self.power = [], 0, []
+        self.max_mhz = None
+        self._stop = False
+        self._thread = None
+
+    def _run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            phys = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.device
+            if phys:
+                try:
+                    idx = int(phys.split(",")[self.device])
+                except Exception:
+                    idx = self.device
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            while not self._stop:
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                try:
+                    self.bits |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    self.bits |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                try:
+                    self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                except Exception:
+                    pass
+                time.sleep(0.02)
+        except Exception as e:
+            self.error = repr(e)
 
     def start(self):
-        try:
-            self.tmp = tempfile.NamedTemporaryFile(mode="w+", suffix=".csv", delete=False)
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=self.tmp, stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+        import threading
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if not self.proc:
-            return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.tmp.flush()
-        rows = [l.strip().split(", ") for l in open(self.tmp.name) if l.strip()]
-        os.unlink(self.tmp.name)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-                for i, nme in enumerate(names):
-                    if r[5 + i].strip().lower().startswith("active"):
-                        reasons.add(nme)
-            except Exception:
-                continue
-        if sm:
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                   "samples": len(sm)}
+        self._stop = True
+        if self._thread:
+            self._thread.join(timeout=5)
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
+        if self.samples:
+            out["sm_mhz"] = float(np.median(self.samples))
+            out["reasons"] = sorted(k for k, b in self.REASONS.items() if self.bits & b)
+            out["samples"] = len(self.samples)
+            if self.power:
+                out["power_w_max"] = max(self.power)
+        if getattr(self, "error", None):
+            out["error"] = self.error
         return out
 
 
@@ -236,12 +248,19 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def note(msg):
+        if os.environ.get("SB_BENCH_VERBOSE"):
+            sys.stderr.write("[bench r%d] %s\n" % (rank, msg))
+            sys.stderr.flush()
+
     # ---- setup (untimed): generate on the device, partition, convert
     t_setup = time.perf_counter()
     g = api.matrixGenerate(nx, ny, nz, rank, world, device=True)
+    note('generated')
     L.commPartition(C.byref(comm), C.byref(g))
     fmt_id = {"CRS": api.FMT_CRS, "SCS": api.FMT_SCS, "CCRS": api.FMT_CCRS}[fmt]
     A = api.convertMatrix(fmt_id, g, Cc, sigma)
+    note('converted')
     if fmt != "CCRS":
         L.sbFreeGMatrix(C.byref(g))
     barrier()
@@ -275,6 +294,7 @@ def main():
 
     # ---- timed region: W warm-up iterations, then exactly K iterations, inputs resident in HBM
     S, info, hist, _p = new_solver(api.CG_FUSED, W + K + 1)
+    note('solver created')
     L.sbCGIterate(S, W + 1)
     barrier()
     sampler.start()
@@ -290,6 +310,7 @@ def main():
     assert kdone == W + K + 1, "CG stopped early: k=%d" % kdone
     resid0, resid = float(hist[0]), float(hist[info.nhist - 1])
     value = K / (ms * 1e-3)
+    note('timed region done: %.3f ms/it' % (ms / K))
 
     # ---- per-kernel device times inside the same loop (CUDA events on the launching stream)
     S2, info2, _h2, _p2 = new_solver(api.CG_FUSED | api.CG_PROFILE, W + K + 1)
@@ -297,6 +318,7 @@ def main():
     L.sbCGFinish(S2, C.byref(info2), 0.0)
     region = {api.REGIONS[i]: info2.regionMs[i] / (W + K) for i in range(5)}
     spmv_ms = region["spmv"]
+    note('profile pass done')
     peak, peak_src = peaks()
     achieved = B_spmv / (spmv_ms * 1e-3) / 1e9
     traffic = None
@@ -309,7 +331,9 @@ def main():
 
     # ---- the reference's `-t spmv` mode (main.c:200-216): x = 1, back-to-back SpMVs, no fused dot
     xs = api.to_device(np.ones(8), slots=nc + 64)
-    L.sbCopyToDevice(xs.ptr, np.ones(N).ctypes.data, 8 * N)
+    ones = np.ones(N)
+    L.sbCopyToDevice(xs.ptr, ones.ctypes.data, 8 * N)
+    del ones
     ys = api.DeviceBuffer(8 * (N + 64 + 32))
     for _ in range(3):
         api.spMVM(A, xs, ys)
@@ -319,6 +343,7 @@ def main():
         api.spMVM(A, xs, ys)
     spmv_only_ms = max_over_ranks(timer.stop_ms()) / K
     xs.free(); ys.free()
+    note('spmv mode done')
 
     # ---- e2e: the same iterations through sbSolveCG with HOST (pinned) b and x: upload, solve, download
     e2e = None
@@ -350,6 +375,7 @@ def main():
                        "each, D2H of x; matrix resident (convertMatrix is setup, as in the reference)" % (ke - 1),
                "ms_per_step": dt * 1e3 / (ke - 1)}
         L.sbFreeHost(hb); L.sbFreeHost(hx)
+        note('e2e done')
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

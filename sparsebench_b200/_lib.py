@@ -14,7 +14,10 @@ def load():
             raise RuntimeError(
                 "%s is missing: build it with `python -m sparsebench_b200.build` (nvcc, sm_100a). "
                 "There is no CPU fallback." % LIB_PATH)
-        _lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)   # the drop-in shims resolve against it
+        # RTLD_LOCAL on purpose: the library exports the reference's own names (allocate, waxpby, ...); a global load
+        # would interpose them on any other copy of the reference in the process (the test oracle). The drop-in shims
+        # find it through their DT_NEEDED entry + $ORIGIN rpath.
+        _lib = C.CDLL(LIB_PATH)
     return _lib
 
 

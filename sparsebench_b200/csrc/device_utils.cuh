@@ -11,19 +11,19 @@ namespace sb {
 __device__ __forceinline__ double ldStream(const double* p)
 {
   double v;
-  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
 __device__ __forceinline__ uint32_t ldStream(const uint32_t* p)
 {
   uint32_t v;
-  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
 __device__ __forceinline__ double2 ldStream2(const double* p)
 {
   double2 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
   return v;
 }
 
@@ -76,6 +76,40 @@ __device__ __forceinline__ void gridSum(double blockPartial, double* partials, u
     v = blockSum(v, scratch);
     if (threadIdx.x == 0) *out = accumulate ? (*out + v) : v;
   }
+}
+
+// ---- mbarrier + 1-D bulk copy (TMA, SASS UBLKCP): asynchronous global -> shared streaming of the matrix
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t arrivals)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void mbarFenceInit() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "SB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra SB_DONE;\n"
+      "bra SB_WAIT;\n"
+      "SB_DONE:\n"
+      "}\n" ::"r"(smemAddr(bar)),
+      "r"(parity)
+      : "memory");
+}
+// size and both addresses must be multiples of 16 bytes
+__device__ __forceinline__ void bulkLoad(void* smemDst, const void* gmemSrc, uint32_t bytes, uint64_t* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smemAddr(smemDst)),
+               "l"(gmemSrc), "r"(bytes), "r"(smemAddr(bar))
+               : "memory");
 }
 
 } // namespace sb

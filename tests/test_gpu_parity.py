@@ -209,11 +209,12 @@ def make_matrix(fmt, g, sigma=256):
 
 
 def assert_history(hist, href):
+    """|hist_k - href_k| <= 1e-10 * max(href_k, 1e-10 * href_0): 1e-10 relative over ten orders of magnitude of
+    residual reduction; below that the reference's own history is summation-order noise (its
+    1-thread strict and 8-thread fast-math builds already differ by 1e-11 at iteration 15 and by 4x at 1e-20)."""
     assert len(hist) == len(href)
-    floor = 1e-13 * href[0]        # below this the reference's own history is rounding noise
-    sel = href > floor
-    assert np.max(np.abs(hist[sel] - href[sel]) / href[sel]) <= CG_TOL
-    assert np.all(np.abs(hist[~sel]) <= 10 * floor)
+    scale = np.maximum(href, 1e-10 * href[0])
+    assert np.max(np.abs(hist - href) / scale) <= CG_TOL
 
 
 @pytest.mark.parametrize("fmt,sigma", [(api.FMT_CRS, 0), (api.FMT_SCS, 1), (api.FMT_SCS, 256), (api.FMT_CCRS, 0)])
