@@ -232,8 +232,11 @@ void sbCRS_convertMatrix(SbCRSMatrix* m, GMatrix* im)
   DeviceInput in = stageInput(im);
   const size_t nr = im->nr;
   m->rowPtr = (CG_UINT*)allocate(64, sizeof(CG_UINT) * (nr + 1));
-  m->colInd = (CG_UINT*)allocate(64, sizeof(CG_UINT) * (in.stored ? in.stored : 1));
-  m->val = (CG_FLOAT*)allocate(64, sizeof(CG_FLOAT) * (in.stored ? in.stored : 1));
+  // +8: the staged SpMV kernel widens its bulk copies to 16-byte granularity (up to 3 elements past the end)
+  m->colInd = (CG_UINT*)allocate(64, sizeof(CG_UINT) * (in.stored + 8));
+  m->val = (CG_FLOAT*)allocate(64, sizeof(CG_FLOAT) * (in.stored + 8));
+  SB_CUDA(cudaMemsetAsync(m->colInd + in.stored, 0, sizeof(CG_UINT) * 8, c.stream));
+  SB_CUDA(cudaMemsetAsync(m->val + in.stored, 0, sizeof(CG_FLOAT) * 8, c.stream));
   SB_CUDA(cudaMemcpyAsync(m->rowPtr, in.rowPtr, sizeof(CG_UINT) * (nr + 1), cudaMemcpyDeviceToDevice, c.stream));
   if (in.stored) {
     splitEntriesKernel<<<gridFor(in.stored, 256), 256, 0, c.stream>>>(in.stored, in.entries, m->colInd, m->val);

@@ -2,19 +2,205 @@
 // matrix-SCS.c:198-228, matrix-CCRS.c:14-31). HBM-bound, no tensor cores: 12 B (16 B for CCRS) of matrix
 // stream per non-zero against 2 flops; x is gathered through L1/L2, y written once.
 //
-// Common shape: persistent grids of numSMs * residentBlocks CTAs walk the row/chunk range in a
-// round-robin so that, at any instant, the whole chip works on one contiguous window of the matrix (and
-// of x). An optional fused epilogue accumulates sum_i x[i]*y[i] (the CG's p.Ap, CGSolver.c:125) with the
+// Common shape: one persistent CTA per SM walks the row/chunk range round-robin, so that at any instant the
+// whole chip works on one contiguous window of the matrix (and of x: the window's x stays in L2 and is
+// read from HBM once). The matrix stream -- values and column ids, read exactly once -- is moved
+// global -> shared memory by the bulk-copy engine (cp.async.bulk, SASS UBLKCP) with mbarrier completion
+// instead of through registers: ~200 KB of matrix are in flight per SM (Little's law needs ~45 KB per SM at
+// 6.5 TB/s) independent of register allocation, warps only spend instructions on LDS + the x gather + the
+// fp64 accumulate, and L1 holds nothing but the gathered x vector because the stream never passes through
+// it. An optional fused epilogue accumulates sum_i x[i]*y[i] (the CG's p.Ap, CGSolver.c:125) with the
 // deterministic one-kernel grid reduction from device_utils.cuh.
 #include "device_utils.cuh"
 #include "sb_internal.h"
 
 namespace sb {
 
+template <typename K>
+static void allowLargeSmem(K kernel, size_t bytes)
+{
+  SB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+static int envInt(const char* name, int dflt)
+{
+  const char* e = getenv(name);
+  return e && *e ? atoi(e) : dflt;
+}
+
+// SB_SPMV_LEGACY=1 selects the register-staged kernels (kept as the measured baseline of profiles/)
+static bool useLegacyKernels()
+{
+  static const int v = envInt("SB_SPMV_LEGACY", 0);
+  return v != 0;
+}
+
 // ------------------------------------------------------------------------------------------- SELL-32-sigma
-// One warp per chunk, lane = row of the chunk: the j-th column of a chunk is 32 consecutive values
-// (256 B) and 32 consecutive column ids (128 B), i.e. perfectly coalesced. Each lane sums its row in
-// stored order, exactly like tmp[k] += val*x of matrix-SCS.c:216-222.
+// One warp per chunk, lane = row of the chunk: the j-th column of a chunk is 32 consecutive values (256 B) and
+// 32 consecutive column ids (128 B). Every warp owns a private ring of S stages of J chunk columns
+// (J x 32 x 12 bytes) with one mbarrier each; producer and consumer of a ring are the same warp: a stage is
+// refilled right after the warp has consumed it (__syncwarp orders the lanes' shared-memory reads before lane 0
+// issues the overwrite), so no "empty" barriers are needed. A stage is consumed in batches of U columns: U
+// independent x gathers in flight per lane, then the U accumulations in stored order, exactly like
+// tmp[k] += val*x of matrix-SCS.c:216-222 (bit-identical row sums).
+// Chunk lengths / offsets of a warp's next 32 chunks live one per lane and are broadcast by shuffle, so the
+// metadata loads are off the critical path.
+template <bool DOT, int WARPS, int J, int S, int U, bool LOCKSTEP>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+spmvSell32TmaKernel(SellView A, const double* __restrict__ x, double* __restrict__ y, uint32_t lo, uint32_t hi,
+    double* partials, unsigned int* ticket, double* dotOut, bool accumulate)
+{
+  extern __shared__ __align__(128) unsigned char ring[];
+  __shared__ double scratch[32];
+  __shared__ uint64_t bars[WARPS * S];
+  constexpr uint32_t kStageBytes = J * 32 * 12;
+  constexpr uint32_t kFull = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* mine = ring + (size_t)warp * S * kStageBytes;
+  uint64_t* bar = bars + warp * S;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < S; s++) mbarInit(bar + s, 1);
+    mbarFenceInit();
+  }
+  __syncwarp();
+
+  const uint64_t stride = (uint64_t)gridDim.x * WARPS;
+  const uint64_t first = (uint64_t)lo + (uint64_t)blockIdx.x * WARPS + warp;
+  // this warp's t-th chunk is first + t*stride; lane l of a metadata block B holds chunk t = 32*B + l
+  auto loadMeta = [&](uint32_t block, uint32_t& lenL, uint32_t& ptrL) {
+    const uint64_t ch = first + ((uint64_t)block * 32 + lane) * stride;
+    lenL = ch < hi ? __ldg(A.chunkLens + ch) : 0u;
+    ptrL = ch < hi ? __ldg(A.chunkPtr + ch) : 0u;
+  };
+
+  // producer cursor: next slab to request = columns [pj, pj+J) of chunk pc (empty chunks have no slab)
+  uint32_t pLenL, pPtrL, pT = 0;
+  loadMeta(0, pLenL, pPtrL);
+  uint32_t cLenL = pLenL, cT = 0;
+  uint64_t pc = first;
+  uint32_t pj = 0, plen = __shfl_sync(kFull, pLenL, 0), pptr = __shfl_sync(kFull, pPtrL, 0);
+  auto produce = [&](int s) {
+    while (pc < hi && pj >= plen) {
+      pc += stride;
+      pj = 0;
+      pT++;
+      if ((pT & 31u) == 0) loadMeta(pT >> 5, pLenL, pPtrL);
+      plen = __shfl_sync(kFull, pLenL, pT & 31u);
+      pptr = __shfl_sync(kFull, pPtrL, pT & 31u);
+    }
+    if (pc >= hi) return;
+    const uint32_t cols = min((uint32_t)J, plen - pj);
+    if (lane == 0) {
+      const uint64_t off = (uint64_t)pptr + (uint64_t)pj * 32;
+      unsigned char* dst = mine + (size_t)s * kStageBytes;
+      mbarExpectTx(bar + s, cols * 32 * 12);
+      bulkLoad(dst, A.val + off, cols * 256, bar + s);
+      bulkLoad(dst + J * 256, A.col + off, cols * 128, bar + s);
+    }
+    pj += cols;
+  };
+#pragma unroll
+  for (int s = 0; s < S; s++) produce(s);
+
+  int cs = 0;
+  uint32_t phases = 0;
+  double dotAcc = 0.0;
+  // LOCKSTEP: the CTA's warps advance one chunk each per step and meet at a barrier, so that they keep working on
+  // 32*WARPS consecutive rows (one shared window of x in L1) instead of drifting apart
+  const uint64_t ctaFirst = (uint64_t)lo + (uint64_t)blockIdx.x * WARPS;
+  const uint64_t nSteps = ctaFirst < hi ? (hi - ctaFirst + stride - 1) / stride : 0;
+  for (uint64_t step = 0; step < nSteps; step++, cT++) {
+    const uint64_t chunk = first + step * stride;
+    if (chunk >= hi) {                               // only in the CTA's last step
+      if (LOCKSTEP) __syncthreads();
+      continue;
+    }
+    if (cT != 0 && (cT & 31u) == 0) {
+      uint32_t unused;
+      loadMeta(cT >> 5, cLenL, unused);
+    }
+    const uint32_t len = __shfl_sync(kFull, cLenL, cT & 31u);
+    const uint64_t row = chunk * 32 + lane;
+    double xr = 0.0;
+    if (DOT && row < A.nr) xr = __ldg(x + row);
+    double sum = 0.0;
+    for (uint32_t j0 = 0; j0 < len; j0 += J) {
+      const uint32_t cols = min((uint32_t)J, len - j0);
+      mbarWait(bar + cs, (phases >> cs) & 1u);
+      phases ^= 1u << cs;
+      const double* v = reinterpret_cast<const double*>(mine + (size_t)cs * kStageBytes) + lane;
+      const uint32_t* c = reinterpret_cast<const uint32_t*>(mine + (size_t)cs * kStageBytes + J * 256) + lane;
+#pragma unroll
+      for (uint32_t j = 0; j < (uint32_t)J; j += U) {
+        if (j < cols) {                              // warp-uniform
+          double xx[U], vv[U];
+#pragma unroll
+          for (int u = 0; u < U; u++)
+            if (j + u < cols) xx[u] = __ldg(x + c[(j + u) * 32]);
+#pragma unroll
+          for (int u = 0; u < U; u++)
+            if (j + u < cols) vv[u] = v[(j + u) * 32];
+#pragma unroll
+          for (int u = 0; u < U; u++)
+            if (j + u < cols) sum = mulAdd(sum, vv[u], xx[u]);
+        }
+      }
+      __syncwarp();
+      produce(cs);
+      cs = (cs + 1 == S) ? 0 : cs + 1;
+    }
+    y[row] = sum;                                  // padded rows are stored too (matrix-SCS.c:224-226)
+    if (DOT && row < A.nr) dotAcc = fma(sum, xr, dotAcc);
+    if (LOCKSTEP) __syncthreads();
+  }
+  if (DOT) {
+    const double b = blockSum(dotAcc, scratch);
+    gridSum(b, partials, ticket, dotOut, accumulate, scratch);
+  }
+}
+
+template <int WARPS, int J, int S, int U, bool LOCKSTEP = true>
+static void launchSell32TmaCfg(const SellView& A, const double* x, double* y, uint32_t lo, uint32_t hi, const DotArgs* dot,
+    cudaStream_t s)
+{
+  Context& c = ctx();
+  const size_t smem = (size_t)WARPS * S * J * 32 * 12;
+  static bool configured = false;
+  if (!configured) {
+    allowLargeSmem(spmvSell32TmaKernel<true, WARPS, J, S, U, LOCKSTEP>, smem);
+    allowLargeSmem(spmvSell32TmaKernel<false, WARPS, J, S, U, LOCKSTEP>, smem);
+    configured = true;
+  }
+  uint64_t blocks = ((uint64_t)(hi - lo) + WARPS - 1) / WARPS;
+  if (blocks > (uint64_t)c.numSMs) blocks = c.numSMs;
+  if (dot)
+    spmvSell32TmaKernel<true, WARPS, J, S, U, LOCKSTEP><<<(int)blocks, WARPS * 32, smem, s>>>(A, x, y, lo, hi,
+        c.partials + (size_t)dot->slot * kMaxPartials, c.tickets + dot->slot, dot->out, dot->accumulate);
+  else
+    spmvSell32TmaKernel<false, WARPS, J, S, U, LOCKSTEP><<<(int)blocks, WARPS * 32, smem, s>>>(A, x, y, lo, hi, nullptr, nullptr,
+        nullptr, false);
+  SB_CUDA(cudaGetLastError());
+  countLaunch();
+}
+
+static void launchSell32Tma(const SellView& A, const double* x, double* y, uint32_t lo, uint32_t hi, const DotArgs* dot,
+    cudaStream_t s)
+{
+  static const int cfg = envInt("SB_SELL_CFG", 0);   // tuning knob, measured in profiles/
+  switch (cfg) {
+  case 1: launchSell32TmaCfg<32, 4, 3, 4, false>(A, x, y, lo, hi, dot, s); break;
+  case 2: launchSell32TmaCfg<32, 4, 4, 4>(A, x, y, lo, hi, dot, s); break;
+  case 3: launchSell32TmaCfg<24, 4, 6, 4>(A, x, y, lo, hi, dot, s); break;
+  case 4: launchSell32TmaCfg<28, 8, 2, 8>(A, x, y, lo, hi, dot, s); break;
+  case 5: launchSell32TmaCfg<16, 16, 2, 16>(A, x, y, lo, hi, dot, s); break;
+  case 6: launchSell32TmaCfg<8, 32, 2, 8>(A, x, y, lo, hi, dot, s); break;
+  case 7: launchSell32TmaCfg<24, 8, 3, 8>(A, x, y, lo, hi, dot, s); break;
+  default: launchSell32TmaCfg<32, 4, 3, 4>(A, x, y, lo, hi, dot, s); break;
+  }
+}
+
+// Register-staged SELL-32 kernel (baseline): loads through LDG with an 8-deep unroll.
 constexpr int kSellUnroll = 8;
 
 template <bool DOT>
@@ -64,7 +250,7 @@ spmvSell32Kernel(SellView A, const double* __restrict__ x, double* __restrict__ 
         if (j + u < len) sum = mulAdd(sum, vv[u], xx[u]);
     }
     const uint64_t row = chunk * 32 + lane;
-    y[row] = sum;                                  // padded rows are stored too (matrix-SCS.c:224-226)
+    y[row] = sum;
     if (DOT && row < A.nr) dotAcc = fma(sum, __ldg(x + row), dotAcc);
   }
   if (DOT) {
@@ -103,12 +289,209 @@ spmvSellAnyCKernel(SellView A, const double* __restrict__ x, double* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------- CRS / CCRS
-// LANES consecutive lanes share a row (27-point rows: 8 lanes x 4 strided elements), partial sums are
-// combined with xor-shuffles. Row-length independent; coalescing comes from neighbouring rows being
-// neighbouring in memory.
+// Warp-specialised CTA pipeline ("CSR-stream"): the non-zeros of R consecutive rows are one contiguous range
+// of the arrays, so one producer thread bulk-copies that range -- plus the R+1 row pointers -- into a ring of S
+// shared-memory stages (full/empty mbarriers), and W consumer warps work the tile off: LPR consecutive lanes
+// share a row (4 lanes x 7 strided elements for the 27-point rows), gather x, and combine their partial sums
+// with xor-shuffles. The global stream is perfectly coalesced whatever the row lengths are, consumers never
+// touch rowPtr/col/val in global memory, and the number of consumer warps is independent of the bytes in
+// flight. Tiles whose non-zeros do not fit a stage are read straight from global memory by the same lanes.
+constexpr uint32_t kPipeMaxRows = 768;                  // row pointers per stage
+
+template <int WARPS, uint32_t CAP, uint32_t STAGES>
+struct CrsPipe {                                        // stage: val[CAP+8] | col[CAP+8] | rowPtr[kPipeMaxRows+8]
+  static constexpr int kWarps = WARPS;                  // consumer warps (+1 producer warp)
+  static constexpr uint32_t kCap = CAP, kStages = STAGES;
+  static constexpr uint32_t kColOff = (CAP + 8) * 8, kRpOff = (CAP + 8) * 12, kBytes = kRpOff + (kPipeMaxRows + 8) * 4;
+  const uint32_t* col;
+  const double* val;
+  // elements [s, e) -> shared; bulk copies need 16-byte granularity, so the range is widened to multiples of 4
+  __device__ __forceinline__ static uint64_t origin(uint64_t s) { return s & ~3ull; }
+  __device__ __forceinline__ static uint32_t bytes(uint64_t s, uint64_t e) { return (uint32_t)(((e + 3) & ~3ull) - (s & ~3ull)) * 12; }
+  __device__ __forceinline__ void request(unsigned char* dst, uint64_t s, uint64_t e, uint64_t* bar) const
+  {
+    const uint64_t a = s & ~3ull;
+    const uint32_t n = (uint32_t)(((e + 3) & ~3ull) - a);
+    bulkLoad(dst, val + a, n * 8, bar);
+    bulkLoad(dst + kColOff, col + a, n * 4, bar);
+  }
+  __device__ __forceinline__ static void fetch(const unsigned char* st, uint32_t i, uint32_t& c, double& v)
+  {
+    v = reinterpret_cast<const double*>(st)[i];
+    c = reinterpret_cast<const uint32_t*>(st + kColOff)[i];
+  }
+  __device__ __forceinline__ void fetchGlobal(uint64_t j, uint32_t& c, double& v) const
+  {
+    c = ldStream(col + j);
+    v = ldStream(val + j);
+  }
+};
+
+template <int WARPS, uint32_t CAP, uint32_t STAGES>
+struct CcrsPipe {                                       // stage: {col, pad, val}[CAP] | rowPtr[kPipeMaxRows+8]
+  static constexpr int kWarps = WARPS;
+  static constexpr uint32_t kCap = CAP, kStages = STAGES;
+  static constexpr uint32_t kRpOff = CAP * 16, kBytes = kRpOff + (kPipeMaxRows + 8) * 4;
+  const Entry* entries;
+  __device__ __forceinline__ static uint64_t origin(uint64_t s) { return s; }
+  __device__ __forceinline__ static uint32_t bytes(uint64_t s, uint64_t e) { return (uint32_t)(e - s) * 16; }
+  __device__ __forceinline__ void request(unsigned char* dst, uint64_t s, uint64_t e, uint64_t* bar) const
+  {
+    bulkLoad(dst, entries + s, (uint32_t)(e - s) * 16, bar);
+  }
+  __device__ __forceinline__ static void fetch(const unsigned char* st, uint32_t i, uint32_t& c, double& v)
+  {
+    const double2 e = reinterpret_cast<const double2*>(st)[i];   // one 16-byte record
+    c = (uint32_t)__double_as_longlong(e.x);
+    v = e.y;
+  }
+  __device__ __forceinline__ void fetchGlobal(uint64_t j, uint32_t& c, double& v) const
+  {
+    const double2 e = ldStream2(reinterpret_cast<const double*>(entries + j));
+    c = (uint32_t)__double_as_longlong(e.x);
+    v = e.y;
+  }
+};
+
+template <bool DOT, int LPR, typename L>
+__global__ void __launch_bounds__((L::kWarps + 1) * 32, 1)
+spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __restrict__ x, double* __restrict__ y,
+    uint32_t lo, uint32_t hi, uint32_t tileRows, double* partials, unsigned int* ticket, double* dotOut, bool accumulate)
+{
+  extern __shared__ __align__(128) unsigned char ring[];
+  __shared__ double scratch[32];
+  __shared__ uint64_t fullBar[L::kStages], emptyBar[L::kStages];
+  constexpr uint32_t S = L::kStages;
+  constexpr int kPipeWarps = L::kWarps;
+  constexpr int UN = 8;                                  // elements per lane per batch
+  constexpr int GPW = 32 / LPR;                          // rows per warp per pass
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (uint32_t s = 0; s < S; s++) {
+      mbarInit(fullBar + s, 1);
+      mbarInit(emptyBar + s, kPipeWarps);
+    }
+    mbarFenceInit();
+  }
+  __syncthreads();
+
+  const uint64_t nTiles = ((uint64_t)(hi - lo) + tileRows - 1) / tileRows;
+  double dotAcc = 0.0;
+  if (warp == kPipeWarps) {
+    // ---- producer: one thread keeps the ring full
+    if (lane == 0) {
+      uint32_t i = 0;
+      for (uint64_t t = blockIdx.x; t < nTiles; t += gridDim.x, i++) {
+        const uint32_t s = i % S, k = i / S;
+        const uint64_t r0 = (uint64_t)lo + t * tileRows;
+        const uint64_t r1 = r0 + tileRows < (uint64_t)hi ? r0 + tileRows : (uint64_t)hi;
+        const uint64_t bs = __ldg(rowPtr + r0), be = __ldg(rowPtr + r1);
+        const uint64_t a = r0 & ~3ull;
+        const uint32_t nrp = (uint32_t)((r1 + 1 - a + 3) & ~3ull);
+        const bool fits = be > bs && be - L::origin(bs) <= L::kCap;
+        if (k > 0) mbarWait(emptyBar + s, (k - 1) & 1u);
+        unsigned char* dst = ring + (size_t)s * L::kBytes;
+        mbarExpectTx(fullBar + s, nrp * 4 + (fits ? L::bytes(bs, be) : 0u));
+        bulkLoad(dst + L::kRpOff, rowPtr + a, nrp * 4, fullBar + s);
+        if (fits) acc.request(dst, bs, be, fullBar + s);
+      }
+    }
+  } else {
+    // ---- consumers
+    const int sub = lane % LPR, grp = lane / LPR;
+    uint32_t i = 0;
+    for (uint64_t t = blockIdx.x; t < nTiles; t += gridDim.x, i++) {
+      const uint32_t s = i % S, k = i / S;
+      const uint64_t r0 = (uint64_t)lo + t * tileRows;
+      const uint64_t r1 = r0 + tileRows < (uint64_t)hi ? r0 + tileRows : (uint64_t)hi;
+      const uint32_t nrows = (uint32_t)(r1 - r0);
+      mbarWait(fullBar + s, k & 1u);
+      const unsigned char* st = ring + (size_t)s * L::kBytes;
+      const uint32_t* rp = reinterpret_cast<const uint32_t*>(st + L::kRpOff) + (uint32_t)(r0 & 3ull);
+      const uint64_t bs = rp[0], be = rp[nrows];
+      const uint64_t org = L::origin(bs);
+      const bool fits = be > bs && be - org <= L::kCap;
+      for (uint32_t g0 = warp * GPW; g0 < nrows; g0 += kPipeWarps * GPW) {
+        const uint32_t g = g0 + grp;
+        const bool live = g < nrows;
+        const uint32_t rs = live ? rp[g] : 0u, re = live ? rp[g + 1] : 0u;
+        double sum = 0.0;
+        if (fits) {
+          uint32_t idx = rs - (uint32_t)org + sub;
+          const uint32_t end = re - (uint32_t)org;
+          while (__any_sync(0xffffffffu, idx < end)) {
+            uint32_t cc[UN];
+            double vv[UN], xx[UN];
+#pragma unroll
+            for (int u = 0; u < UN; u++)
+              if (idx + u * LPR < end) L::fetch(st, idx + u * LPR, cc[u], vv[u]);
+#pragma unroll
+            for (int u = 0; u < UN; u++)
+              if (idx + u * LPR < end) xx[u] = __ldg(x + cc[u]);
+#pragma unroll
+            for (int u = 0; u < UN; u++)
+              if (idx + u * LPR < end) sum = mulAdd(sum, vv[u], xx[u]);
+            idx += UN * LPR;
+          }
+        } else {
+          for (uint64_t j = (uint64_t)rs + sub; j < re; j += LPR) {   // oversized tile: straight from global memory
+            uint32_t c;
+            double v;
+            acc.fetchGlobal(j, c, v);
+            sum = mulAdd(sum, v, __ldg(x + c));
+          }
+        }
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (live && sub == 0) {
+          y[r0 + g] = sum;
+          if (DOT) dotAcc = fma(sum, __ldg(x + r0 + g), dotAcc);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbarArrive(emptyBar + s);
+    }
+  }
+  if (DOT) {
+    const double b = blockSum(dotAcc, scratch);
+    gridSum(b, partials, ticket, dotOut, accumulate, scratch);
+  }
+}
+
+template <int LPR, typename L>
+static void launchRowsPipe(L acc, const uint32_t* rowPtr, const double* x, double* y, uint32_t lo, uint32_t hi,
+    uint32_t tileRows, const DotArgs* dot, cudaStream_t s)
+{
+  Context& c = ctx();
+  const size_t smem = (size_t)L::kStages * L::kBytes;
+  static bool configured = false;
+  if (!configured) {
+    allowLargeSmem(spmvRowsPipeKernel<true, LPR, L>, smem);
+    allowLargeSmem(spmvRowsPipeKernel<false, LPR, L>, smem);
+    configured = true;
+  }
+  uint64_t blocks = ((uint64_t)(hi - lo) + tileRows - 1) / tileRows;
+  if (blocks > (uint64_t)c.numSMs) blocks = c.numSMs;
+  const int threads = (L::kWarps + 1) * 32;
+  if (dot)
+    spmvRowsPipeKernel<true, LPR, L><<<(int)blocks, threads, smem, s>>>(acc, rowPtr, x, y, lo, hi, tileRows,
+        c.partials + (size_t)dot->slot * kMaxPartials, c.tickets + dot->slot, dot->out, dot->accumulate);
+  else
+    spmvRowsPipeKernel<false, LPR, L><<<(int)blocks, threads, smem, s>>>(acc, rowPtr, x, y, lo, hi, tileRows, nullptr,
+        nullptr, nullptr, false);
+  SB_CUDA(cudaGetLastError());
+  countLaunch();
+}
+
+// Register-staged sub-warp kernel (long rows, and the measured baseline): LANES consecutive lanes share a row,
+// partial sums are combined with xor-shuffles.
 struct CrsAccess {
   const uint32_t* col;
   const double* val;
+  template <int W, uint32_t CAP, uint32_t S> using Pipe = CrsPipe<W, CAP, S>;
+  template <typename P> P pipe() const { return P { col, val }; }
+  static constexpr uint32_t kStagesFor3584 = 5, kStagesFor5376 = 3;
+  static constexpr int kDefaultCfg = 0;                 // 23 consumer warps (+1 producer = 6 warps per scheduler, 80 registers), 3 stages of 66 KB
   __device__ __forceinline__ void load(uint64_t j, uint32_t& c, double& v) const
   {
     c = ldStream(col + j);
@@ -117,6 +500,10 @@ struct CrsAccess {
 };
 struct CcrsAccess {
   const Entry* entries;
+  template <int W, uint32_t CAP, uint32_t S> using Pipe = CcrsPipe<W, CAP, S>;
+  template <typename P> P pipe() const { return P { entries }; }
+  static constexpr uint32_t kStagesFor3584 = 3, kStagesFor5376 = 2;
+  static constexpr int kDefaultCfg = 1;                 // 16 consumer warps, 3 stages of 59 KB (16-byte records)
   __device__ __forceinline__ void load(uint64_t j, uint32_t& c, double& v) const
   {
     const double2 e = ldStream2(reinterpret_cast<const double*>(entries + j));   // one 16-byte record
@@ -193,11 +580,44 @@ static void launchRows(Access acc, const uint32_t* rowPtr, uint32_t nr, const do
   countLaunch();
 }
 
+// lanes per row ~ avg/7 (one 8-deep batch per row); tile = as many passes of the consumer warps as fit a stage.
+// CRS and CCRS take the same decisions (same CAP), so their row sums are bit-identical to each other.
+template <typename Access, typename P>
+static bool tryRowsPipe(Access acc, const uint32_t* rowPtr, double avg, const double* x, double* y, uint32_t lo, uint32_t hi,
+    const DotArgs* dot, cudaStream_t s)
+{
+  // every pipe layout has CAP / WARPS = 224 non-zeros per consumer warp and pass: lanes per row = avg / 7
+  const int lpr = avg <= 7.0 ? 1 : avg <= 14.0 ? 2 : avg <= 28.0 ? 4 : avg <= 56.0 ? 8 : avg <= 112.0 ? 16 : 32;
+  const uint32_t rowsPerPass = (uint32_t)P::kWarps * (32u / (uint32_t)lpr);
+  const uint32_t fitRows = (uint32_t)((double)P::kCap / (avg > 1.0 ? avg : 1.0));
+  uint32_t tileRows = (fitRows / rowsPerPass) * rowsPerPass;
+  if (tileRows > kPipeMaxRows) tileRows = (kPipeMaxRows / rowsPerPass) * rowsPerPass;
+  if (tileRows < rowsPerPass) return false;
+  switch (lpr) {
+  case 1: launchRowsPipe<1>(acc.template pipe<P>(), rowPtr, x, y, lo, hi, tileRows, dot, s); break;
+  case 2: launchRowsPipe<2>(acc.template pipe<P>(), rowPtr, x, y, lo, hi, tileRows, dot, s); break;
+  case 4: launchRowsPipe<4>(acc.template pipe<P>(), rowPtr, x, y, lo, hi, tileRows, dot, s); break;
+  case 8: launchRowsPipe<8>(acc.template pipe<P>(), rowPtr, x, y, lo, hi, tileRows, dot, s); break;
+  case 16: launchRowsPipe<16>(acc.template pipe<P>(), rowPtr, x, y, lo, hi, tileRows, dot, s); break;
+  default: launchRowsPipe<32>(acc.template pipe<P>(), rowPtr, x, y, lo, hi, tileRows, dot, s); break;
+  }
+  return true;
+}
+
 template <typename Access>
 static void launchRowsAuto(Access acc, const uint32_t* rowPtr, uint32_t nr, uint64_t nnz, const double* x, double* y,
     uint32_t lo, uint32_t hi, const DotArgs* dot, cudaStream_t s)
 {
   const double avg = nr ? (double)nnz / (double)nr : 0.0;
+  if (!useLegacyKernels()) {
+    static const int cfg = envInt("SB_ROWS_CFG", Access::kDefaultCfg);   // tuning knob, measured in profiles/
+    bool done;
+    if (cfg == 1)
+      done = tryRowsPipe<Access, typename Access::template Pipe<16, 3584, Access::kStagesFor3584>>(acc, rowPtr, avg, x, y, lo, hi, dot, s);
+    else
+      done = tryRowsPipe<Access, typename Access::template Pipe<23, 5376, Access::kStagesFor5376>>(acc, rowPtr, avg, x, y, lo, hi, dot, s);
+    if (done) return;
+  }
   if (avg <= 6.0) launchRows<2, Access>(acc, rowPtr, nr, x, y, lo, hi, dot, s);
   else if (avg <= 12.0) launchRows<4, Access>(acc, rowPtr, nr, x, y, lo, hi, dot, s);
   else if (avg <= 40.0) launchRows<8, Access>(acc, rowPtr, nr, x, y, lo, hi, dot, s);
@@ -226,6 +646,8 @@ void launchSpmv(const Operator& A, const double* x, double* y, uint32_t lo, uint
       spmvSellAnyCKernel<false><<<(int)blocks, 256, 0, s>>>(A.sell, x, y, lo, hi, nullptr, nullptr, nullptr, false);
     SB_CUDA(cudaGetLastError());
     countLaunch();
+  } else if (A.fmt == SB_FMT_SCS && !useLegacyKernels()) {
+    launchSell32Tma(A.sell, x, y, lo, hi, dot, s);
   } else if (A.fmt == SB_FMT_SCS) {
     uint64_t blocks = ((uint64_t)(hi - lo) + 7) / 8;
     const uint64_t cap = (uint64_t)c.numSMs * 4;
