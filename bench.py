@@ -1,12 +1,16 @@
 #!/usr/bin/env python
-"""bench.py -- CG iterations/s (+ SpMV GFLOP/s and HBM GB/s against the roofline) of the SparseBench hot path.
+"""bench.py -- CG throughput (GFLOP/s over all GPUs, with CG iterations/s, SpMV GFLOP/s and HBM GB/s against the
+roofline beside it) of the SparseBench hot path.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload sell256|crs128|ccrs128|...] [--impl reference]
 
 A step is ONE CG iteration (CGSolver.c:107-129: p-update, halo exchange, SpMV, two dot products, x/r update)
 over the synthetic HPCG 27-point stencil matrix named by the workload; the default workload is BASELINE.json
 configs[2]/[3]: 256^3 rows per GPU, SELL-C-sigma (C=32, sigma=256), fp64, z-stacked row blocks over N GPUs (weak
-scaling). One JSON line is printed by rank 0. See DESIGN.md section "Measurement" for every field.
+scaling). `value` is the whole-job aggregate: floating-point operations of one CG iteration summed over all ranks
+(2 nnz + 10 N per rank; the reference's own accounting, profiler.c:19-22) times iterations per second,
+so it grows with N under weak scaling while `cg.iterations_per_sec` stays flat. One JSON line is printed by rank 0.
+See DESIGN.md section "Measurement" for every field.
 """
 import argparse
 import ctypes as C
@@ -193,7 +197,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     nx, ny, nz, fmt, Cc, sigma, desc = WORKLOADS[args.workload]
     K, W = args.steps, args.warmup
-    metric, unit = "cg_iterations_per_sec", "it/s"
+    metric, unit = "cg_gflops", "GFLOP/s"
+    # flops of one CG iteration over the whole job (all ranks): 2 per stored non-zero + 10 per row
+    flops_it_job = sum(2 * local_nnz(nx, ny, nz, r, world) + 10 * nx * ny * nz for r in range(world))
 
     if args.impl == "reference":
         if rank != 0:
@@ -202,12 +208,15 @@ def main():
         if r is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_CRS_fast.so was not built"}))
             return 0
-        line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": unit, "n_gpus": args.gpus, "steps": K,
+        gf = r["value"] * flops_it_job / 1e9
+        line = {"impl": "reference", "metric": metric, "value": gf, "unit": unit, "n_gpus": args.gpus, "steps": K,
                 "warmup": W, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": desc, "nx": nx, "ny": ny, "nz_per_gpu": nz, "format": "CRS (reference CPU build)"},
-                "cpu_baseline": {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
-                "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "cpu_baseline": {"value": gf, "unit": unit, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                                 "iterations_per_sec": r["value"]},
+                "e2e": {"value": gf, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "cg": {"iterations_per_sec": r["value"]},
                 "gpu_launches": 0}
         print(json.dumps(line))
         return 0
@@ -309,7 +318,8 @@ def main():
     L.sbCGFinish(S, C.byref(info), ms)
     assert kdone == W + K + 1, "CG stopped early: k=%d" % kdone
     resid0, resid = float(hist[0]), float(hist[info.nhist - 1])
-    value = K / (ms * 1e-3)
+    its = K / (ms * 1e-3)
+    value = its * flops_it_job / 1e9
     note('timed region done: %.3f ms/it' % (ms / K))
 
     # ---- per-kernel device times inside the same loop (CUDA events on the launching stream)
@@ -369,7 +379,8 @@ def main():
         L.sbDeviceSynchronize()
         dt = time.perf_counter() - t0
         dt = max_over_ranks(dt)
-        e2e = {"value": (ke - 1) / dt, "unit": unit, "h2d_bytes_per_step": 2 * 8 * N / (ke - 1),
+        e2e = {"value": (ke - 1) / dt * flops_it_job / 1e9, "unit": unit, "iterations_per_sec": (ke - 1) / dt,
+               "h2d_bytes_per_step": 2 * 8 * N / (ke - 1),
                "d2h_bytes_per_step": (8 * N + 8 * ke) / (ke - 1),
                "what": "sbSolveCG(host b, host x0 -> host x): H2D of b and x0, %d iterations with a D2H residual scalar "
                        "each, D2H of x; matrix resident (convertMatrix is setup, as in the reference)" % (ke - 1),
@@ -384,7 +395,8 @@ def main():
             sub.steps, sub.warmup = min(K, 20), 3
             r = reference_arm(sub, nx, ny, nz, desc, 1)
             if r:
-                cpu = {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+                cpu = {"value": r["value"] * flops_it_job / 1e9, "unit": unit, "cores": r["cores"], "kind": r["kind"],
+                       "sample": r["sample"], "iterations_per_sec": r["value"]}
         except Exception as e:  # the CPU leg must never take the GPU numbers down with it
             cpu = {"value": None, "unit": unit, "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % (e,)}
 
@@ -408,7 +420,7 @@ def main():
             "spmv": {"gflops": F_spmv / (spmv_only_ms * 1e-3) / 1e9, "gbs": B_spmv / (spmv_only_ms * 1e-3) / 1e9,
                      "gbs_format_bytes": B_spmv_fmt / (spmv_only_ms * 1e-3) / 1e9, "ms": spmv_only_ms,
                      "frac_of_peak": B_spmv / (spmv_only_ms * 1e-3) / 1e9 / peak, "mode": "x=1, back-to-back (main.c:200-216)"},
-            "cg": {"gbs_per_gpu": B_it / (ms / K * 1e-3) / 1e9, "gflops_per_gpu": F_it / (ms / K * 1e-3) / 1e9,
+            "cg": {"iterations_per_sec": its, "gbs_per_gpu": B_it / (ms / K * 1e-3) / 1e9, "gflops_per_gpu": F_it / (ms / K * 1e-3) / 1e9,
                    "frac_of_peak": B_it / (ms / K * 1e-3) / 1e9 / peak, "kernel_ms_per_iteration": region,
                    "residual_initial": resid0, "residual_final": resid, "max_error_vs_xexact": info.maxError},
         }

@@ -305,7 +305,10 @@ int sbCGFinish(void* solver, SbCGInfo* info, double loopMs)
 
 int sbSolveCG(Comm* comm, Parameter* param, void* matrix, int fmt, SbCGInfo* info)
 {
+  const bool trace = getenv("SB_CG_TRACE") != nullptr;
+  const double t0 = trace ? getTimeStamp() : 0.0;
   CgSolver* S = (CgSolver*)sbCGCreate(comm, param, matrix, fmt, info);
+  const double t1 = trace ? getTimeStamp() : 0.0;
   cudaEvent_t a, b;
   SB_CUDA(cudaEventCreate(&a));
   SB_CUDA(cudaEventCreate(&b));
@@ -317,7 +320,10 @@ int sbSolveCG(Comm* comm, Parameter* param, void* matrix, int fmt, SbCGInfo* inf
   SB_CUDA(cudaEventElapsedTime(&ms, a, b));
   SB_CUDA(cudaEventDestroy(a));
   SB_CUDA(cudaEventDestroy(b));
-  return sbCGFinish(S, info, ms);
+  const double t2 = trace ? getTimeStamp() : 0.0;
+  const int k = sbCGFinish(S, info, ms);
+  if (trace) fprintf(stderr, "[sbSolveCG] create %.2f ms, loop %.2f ms (device %.2f), finish %.2f ms\n", (t1 - t0) * 1e3, (t2 - t1) * 1e3, ms, (getTimeStamp() - t2) * 1e3);
+  return k;
 }
 
 int sbCRS_solveCG(Comm* comm, Parameter* param, SbCRSMatrix* m) { return sbSolveCG(comm, param, m, SB_FMT_CRS, nullptr); }

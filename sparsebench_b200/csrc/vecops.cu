@@ -265,28 +265,36 @@ void launchGather(uint32_t n, const uint32_t* map, const double* in, double* out
   countLaunch();
 }
 
-// max_i |x[i] - 1| (solverCheckResidual, CGSolver.c:40-60 with xexact == 1)
-__global__ void maxErrKernel(uint32_t n, const double* __restrict__ x, double* out)
+// max_i |x[i] - 1| (solverCheckResidual, CGSolver.c:40-60 with xexact == 1). NaN never compares greater, as in the
+// reference loop (CGSolver.c:50-53). Non-negative doubles order like their bit patterns, so the grid maximum is an
+// integer atomicMax.
+__global__ void __launch_bounds__(kVecThreads)
+maxErrKernel(uint32_t n, const double* __restrict__ x, unsigned long long* out)
 {
-  __shared__ double sm[kVecThreads];
+  __shared__ double sm[kVecThreads / 32];
   double m = 0.0;
-  bool nan = false;
-  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     const double d = fabs(x[i] - 1.0);
-    if (d > m) m = d;        // NaN never compares greater, as in the reference loop (CGSolver.c:50-53)
-    (void)nan;
+    if (d > m) m = d;
   }
-  sm[threadIdx.x] = m;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double t = __shfl_xor_sync(0xffffffffu, m, o);
+    if (t > m) m = t;
+  }
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
   __syncthreads();
-  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o && sm[threadIdx.x + o] > sm[threadIdx.x]) sm[threadIdx.x] = sm[threadIdx.x + o];
-    __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kVecThreads / 32; w++)
+      if (sm[w] > m) m = sm[w];
+    atomicMax(out, (unsigned long long)__double_as_longlong(m));
   }
-  if (threadIdx.x == 0) *out = sm[0];
 }
 void launchMaxErr(uint32_t n, const double* x, double* out, cudaStream_t s)
 {
-  maxErrKernel<<<1, kVecThreads, 0, s>>>(n, x, out);
+  SB_CUDA(cudaMemsetAsync(out, 0, sizeof(double), s));
+  if (n == 0) return;
+  maxErrKernel<<<vecGrid(n, 4), kVecThreads, 0, s>>>(n, x, reinterpret_cast<unsigned long long*>(out));
   SB_CUDA(cudaGetLastError());
   countLaunch();
 }

@@ -1,6 +1,10 @@
 #!/bin/bash
 set -u
-run() { echo "== $N $FMT $*"; env "$@" timeout 200 python tools/spmv_probe.py --n $N --fmt $FMT --reps 5 --cg 60 2>&1 | tail -2; }
-N=256
-FMT=CRS; run SB_DOT_MODE=0; run SB_DOT_MODE=1; run SB_DOT_MODE=2; run SB_DOT_MODE=3; run SB_CG_SPLIT_DOT=1
-FMT=SCS; run A=1; run SB_CG_SPLIT_DOT=1
+mkdir -p gpurun_out
+SB_CG_TRACE=1 timeout 900 python bench.py --no-cpu-baseline --steps 100 > gpurun_out/bench_sell256.json 2> gpurun_out/bench_sell256.err; echo "rc=$?"
+grep sbSolveCG gpurun_out/bench_sell256.err
+python -c "
+import json
+d=json.loads(open('gpurun_out/bench_sell256.json').read().strip().splitlines()[-1])
+for k in ('metric','value','unit','ms_per_step','e2e','roofline','cg'): print(k, d[k])
+"
