@@ -194,7 +194,8 @@ enum {
   SB_CG_NO_OVERLAP = 8,   /* multi-GPU: do not overlap the halo exchange with interior rows */
   SB_CG_PROFILE = 16      /* CUDA events around every kernel of the loop -> regionMs (measurement runs only) */
 };
-enum { SB_REGION_UPDATE_P = 0, SB_REGION_EXCHANGE, SB_REGION_SPMV, SB_REGION_ALLREDUCE, SB_REGION_UPDATE_XR, SB_REGION_COUNT };
+enum { SB_REGION_UPDATE_P = 0, SB_REGION_EXCHANGE, SB_REGION_SPMV, SB_REGION_ALLREDUCE, SB_REGION_UPDATE_XR,
+       SB_REGION_HALO_WAIT, SB_REGION_SPMV_BOUNDARY, SB_REGION_COUNT };
 typedef struct {
   int flags;
   const CG_FLOAT* b;      /* right-hand side, nr entries; NULL -> initVectors rule (CGSolver.c:19-38) */

@@ -16,7 +16,7 @@ ENTRY_DTYPE = np.dtype([("col", np.uint32), ("pad", np.uint32), ("val", np.float
 FMT_CRS, FMT_SCS, FMT_CCRS = 0, 1, 2
 FMT_NAMES = {FMT_CRS: "CRS", FMT_SCS: "SCS", FMT_CCRS: "CCRS"}
 CG_FUSED, CG_PRINT, CG_HOST_VECTORS, CG_NO_OVERLAP, CG_PROFILE = 1, 2, 4, 8, 16
-REGIONS = ("update_p", "exchange", "spmv", "allreduce", "update_xr")
+REGIONS = ("update_p", "exchange", "spmv", "allreduce", "update_xr", "halo_wait", "spmv_boundary")
 OP_MAX, OP_SUM = 0, 1
 
 
@@ -68,7 +68,7 @@ class Comm(C.Structure):
 class CGInfo(C.Structure):
     _fields_ = [("flags", C.c_int), ("b", C.c_void_p), ("x", C.c_void_p), ("history", C.POINTER(C.c_double)),
                 ("historyCap", C.c_int), ("nhist", C.c_int), ("solveMs", C.c_double), ("maxError", C.c_double),
-                ("regionMs", C.c_double * 5)]
+                ("regionMs", C.c_double * 7)]
 
 
 _configured = False

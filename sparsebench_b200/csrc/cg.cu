@@ -20,7 +20,7 @@ namespace sb {
 namespace {
 
 constexpr int kEventRing = 8;
-enum Region { R_UPDATE_P = 0, R_EXCHANGE, R_SPMV, R_ALLREDUCE, R_UPDATE_XR, R_COUNT };
+enum Region { R_UPDATE_P = 0, R_EXCHANGE, R_SPMV, R_ALLREDUCE, R_UPDATE_XR, R_HALO_WAIT, R_SPMV_BOUNDARY, R_COUNT };
 
 bool commActive(const Comm* c) { return c && c->size > 1; }
 
@@ -30,7 +30,9 @@ struct CgSolver {
   cudaStream_t s = nullptr;
   double eps = 0.0;
   int itermax = 0, flags = 0, printFreq = 1;
-  bool fused = true, print = false, generated = false, profile = false;
+  bool fused = true, print = false, generated = false, profile = false, overlap = true;
+  int* elemsPerm = nullptr;                // SELL with a row permutation: elementsToSend in solver (permuted) numbering
+  uint32_t intLo = 0, intHi = 0;           // SpMV units [intLo, intHi) reference no halo column
   uint32_t n = 0;
   size_t rowSlots = 0, colSlots = 0;
   // vectors (CGSolver.c:69-79), solver order (SELL: permuted)
@@ -45,7 +47,7 @@ struct CgSolver {
   // optional per-kernel event timing
   std::vector<cudaEvent_t> evPool;
   std::vector<int> evRegion;
-  double regionMs[R_COUNT] = { 0, 0, 0, 0, 0 };
+  double regionMs[R_COUNT] = { 0, 0, 0, 0, 0, 0, 0 };
 
   void mark(int region)
   {
@@ -64,13 +66,34 @@ struct CgSolver {
     mark(R_ALLREDUCE);
   }
 
+  // commExchange + spMVM (CGSolver.c:95-96,122-123). With the peer-window transport the exchange is split: my
+  // boundary values leave first, the rows that reference no halo column are multiplied while the neighbours'
+  // values arrive, the boundary rows follow once they are there.
   void spmvWithHalo(const DotArgs* dot)
   {
+    const uint32_t units = spmvUnits(A);
     if (commActive(comm)) {
-      commExchangeOnStream(comm, A.nr, p, s);                 // CGSolver.c:95,122
+      if (commPeerMode(comm)) {
+        commHaloPut(comm, p, elemsPerm, s);
+        mark(R_EXCHANGE);
+        if (overlap && intLo < intHi) {
+          launchSpmv(A, p, Ap, intLo, intHi, dot, s);
+          mark(R_SPMV);
+          commHaloWait(comm, A.nr, p, s);
+          mark(R_HALO_WAIT);
+          DotArgs more { dot ? dot->out : nullptr, true, dot ? dot->slot : 0 };
+          launchSpmv(A, p, Ap, 0, intLo, dot ? &more : nullptr, s);
+          launchSpmv(A, p, Ap, intHi, units, dot ? &more : nullptr, s);
+          mark(R_SPMV_BOUNDARY);
+          return;
+        }
+        commHaloWait(comm, A.nr, p, s);
+      } else {
+        commExchangeOnStream(comm, A.nr, p, elemsPerm, s);
+      }
       mark(R_EXCHANGE);
     }
-    launchSpmv(A, p, Ap, 0, spmvUnits(A), dot, s);            // CGSolver.c:96,123
+    launchSpmv(A, p, Ap, 0, units, dot, s);
     mark(R_SPMV);
   }
 
@@ -122,6 +145,7 @@ struct CgSolver {
     fused = (flags & SB_CG_FUSED) != 0;
     profile = (flags & SB_CG_PROFILE) != 0;
     print = (flags & SB_CG_PRINT) != 0 && (!comm || comm->rank == 0);
+    overlap = (flags & SB_CG_NO_OVERLAP) == 0;
     generated = param->filename && (strcmp(param->filename, "generate") == 0 || strcmp(param->filename, "generate7P") == 0);
     n = A.nr;
     rowSlots = (size_t)(A.nrPadded > n ? A.nrPadded : n) + 2;
@@ -142,6 +166,14 @@ struct CgSolver {
     SB_CUDA(cudaMemsetAsync(pAp, 0, sizeof(double) * nScal, s));
     for (int i = 0; i < kEventRing; i++) SB_CUDA(cudaEventCreateWithFlags(&ring[i], cudaEventDisableTiming));
     hist.reserve((size_t)nScal);
+
+    if (commActive(comm)) {
+      if (A.oldToNew && comm->totalSendCount > 0) {           // vectors are row-permuted: send p[oldToNew[element]]
+        elemsPerm = (int*)allocate(64, sizeof(int) * (size_t)comm->totalSendCount);
+        launchPermuteIndices((uint32_t)comm->totalSendCount, A.oldToNew, commDeviceElements(comm), elemsPerm, s);
+      }
+      spmvInteriorUnits(A, &intLo, &intHi, s);
+    }
 
     // initVectors (CGSolver.c:19-38), or caller-supplied b / x0
     launchInitVectors(n, A.rowPtr, A.rowLen, generated, x, b, s);
@@ -272,7 +304,7 @@ struct CgSolver {
     }
     for (cudaEvent_t e : evPool) cudaEventDestroy(e);
     for (int i = 0; i < kEventRing; i++) SB_CUDA(cudaEventDestroy(ring[i]));
-    sbFree(r); sbFree(p); sbFree(Ap); sbFree(x); sbFree(b); sbFree(tmp); sbFree(rho); sbFree(pAp);
+    sbFree(r); sbFree(p); sbFree(Ap); sbFree(x); sbFree(b); sbFree(tmp); sbFree(rho); sbFree(pAp); sbFree(elemsPerm);
     sbFreeHost(hRho);
     return k;
   }

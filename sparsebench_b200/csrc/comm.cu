@@ -33,13 +33,67 @@ struct SbPartitionPlan {
 
 namespace sb {
 
+// ------------------------------------------------------------------------------------------- peer windows
+// Inside one NVSwitch box every GPU can store straight into every other GPU's memory. Each rank owns two
+// windows that its peers map through CUDA IPC:
+//   control window : halo arrival / acknowledge counters and the slots of the scalar all-reduce
+//   halo window    : two receive slots (double buffering by exchange parity) of externalCount doubles, laid
+//                    out like the halo part of x (grouped by source in rdispls order)
+// Halo exchange = the SENDER's kernel gathers x[elementsToSend[i]] and stores the values directly into the
+// receivers' slots over NVLink, then publishes the exchange number (release, system scope); the receiver's
+// kernel spins on its own counters (acquire), copies the slot behind its x vector and acknowledges. No
+// host involvement, no staging buffer, no receive-side collective: the pack kernel (K6) and the
+// MPI_Neighbor_alltoallv (C1) of comm.c:627-651 are one launch. The all-reduce of a dot product is one
+// single-CTA kernel: every rank stores its partial into slot [rank] of every peer and sums the slots of its
+// own window in rank order, so all ranks obtain bit-identical results.
+constexpr int kMaxRanks = 64;
+constexpr int kRedDepth = 4;
+constexpr long long kSpinTimeoutCycles = 40000000000ll;   // ~20 s: a dead peer must not hang the GPU forever
+
+struct CtrlWindow {
+  unsigned long long haloFlag[kMaxRanks];              // [source rank] newest exchange completely stored by that source
+  unsigned long long haloAck[kMaxRanks];               // [dest rank]   newest exchange that dest has copied out of its slot
+  unsigned long long redFlag[kRedDepth][kMaxRanks];    // [epoch % depth][rank] epoch of the value below
+  double redVal[kRedDepth][kMaxRanks];
+};
+
+struct PutPlan {
+  int ndest;
+  int sdispl[kMaxRanks + 1];                           // element offsets per destination (comm.c:150)
+  double* remote[2][kMaxRanks];                        // destination slot (per parity), already offset to my segment
+  unsigned long long* remoteFlag[kMaxRanks];           // &destCtrl->haloFlag[myRank]
+  const unsigned long long* ack[kMaxRanks];            // &myCtrl->haloAck[destRank]
+};
+
+struct WaitPlan {
+  int nsrc;
+  int externalCount;
+  const unsigned long long* flag[kMaxRanks];           // &myCtrl->haloFlag[sourceRank]
+  unsigned long long* remoteAck[kMaxRanks];            // &sourceCtrl->haloAck[myRank]
+  const double* slot[2];
+};
+
+enum { COMM_NCCL = 0, COMM_PEER = 1 };
+
 struct CommExt {
   ncclComm_t nccl = nullptr;
   int rank = 0, size = 1;
+  int mode = COMM_NCCL;
   int* dElementsToSend = nullptr;
-  int dElementsCount = 0;
   double* dScalar = nullptr;      // staging for host-scalar reductions
   double* hScalar = nullptr;
+  std::vector<int> wantMatrix;    // [requester][owner] halo counts of the current partition
+  bool installed = false;         // device lists / windows match the Comm lists
+  // peer mode
+  CtrlWindow* ctrl = nullptr;
+  std::vector<CtrlWindow*> peerCtrl;
+  CtrlWindow** dPeerCtrl = nullptr;
+  double* halo = nullptr;
+  std::vector<double*> peerHalo;
+  PutPlan* dPut = nullptr;
+  WaitPlan* dWait = nullptr;
+  unsigned int* dTickets = nullptr;
+  unsigned long long haloSeq = 0, redEpoch = 0;
 };
 
 static CommExt* g_world = nullptr;   // commReduction has no Comm* argument (it used MPI_COMM_WORLD, comm.c:653-662)
@@ -55,6 +109,74 @@ static void resetLists(Comm* c)
   c->sendBuffer = nullptr;
 }
 
+// all-gather of `bytes` bytes per rank through NCCL (setup-time, tiny)
+static void allGatherBytes(CommExt* e, const void* mine, size_t bytes, void* all)
+{
+  Context& c = ctx();
+  char* d = (char*)allocate(64, bytes * (size_t)(e->size + 1));
+  SB_CUDA(cudaMemcpyAsync(d, mine, bytes, cudaMemcpyHostToDevice, c.stream));
+  SB_NCCL(ncclAllGather(d, d + bytes, bytes, ncclChar, e->nccl, c.stream));
+  SB_CUDA(cudaMemcpyAsync(all, d + bytes, bytes * (size_t)e->size, cudaMemcpyDeviceToHost, c.stream));
+  SB_CUDA(cudaStreamSynchronize(c.stream));
+  sbFree(d);
+}
+
+static void allGatherInts(CommExt* e, const int* mine, int count, int* all)
+{
+  allGatherBytes(e, mine, sizeof(int) * (size_t)count, all);
+}
+
+static void ncclBarrier(CommExt* e)
+{
+  Context& c = ctx();
+  SB_CUDA(cudaMemsetAsync(e->dScalar + 4, 0, sizeof(double), c.stream));
+  SB_NCCL(ncclAllReduce(e->dScalar + 4, e->dScalar + 4, 1, ncclDouble, ncclSum, e->nccl, c.stream));
+  SB_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+// Maps every peer's copy of a window; returns false (on every rank) if any rank could not map any peer.
+static bool mapPeers(CommExt* e, void* mine, std::vector<void*>& peers)
+{
+  cudaIpcMemHandle_t h;
+  memset(&h, 0, sizeof(h));
+  int ok = cudaIpcGetMemHandle(&h, mine) == cudaSuccess ? 1 : 0;
+  if (!ok) cudaGetLastError();
+  std::vector<cudaIpcMemHandle_t> all((size_t)e->size);
+  allGatherBytes(e, &h, sizeof(h), all.data());
+  std::vector<int> oks((size_t)e->size);
+  allGatherInts(e, &ok, 1, oks.data());
+  for (int r = 0; r < e->size; r++) ok &= oks[(size_t)r];
+  peers.assign((size_t)e->size, nullptr);
+  if (ok) {
+    for (int r = 0; r < e->size; r++) {
+      if (r == e->rank) { peers[(size_t)r] = mine; continue; }
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+        break;
+      }
+      peers[(size_t)r] = p;
+    }
+  }
+  allGatherInts(e, &ok, 1, oks.data());
+  int allOk = 1;
+  for (int r = 0; r < e->size; r++) allOk &= oks[(size_t)r];
+  if (!allOk) {
+    for (int r = 0; r < e->size; r++)
+      if (r != e->rank && peers[(size_t)r]) cudaIpcCloseMemHandle(peers[(size_t)r]);
+    peers.assign((size_t)e->size, nullptr);
+  }
+  return allOk != 0;
+}
+
+static void unmapPeers(CommExt* e, std::vector<void*>& peers)
+{
+  for (int r = 0; r < (int)peers.size(); r++)
+    if (r != e->rank && peers[(size_t)r]) cudaIpcCloseMemHandle(peers[(size_t)r]);
+  peers.clear();
+}
+
 static void attach(Comm* c, int rank, int size, int device, const ncclUniqueId* id)
 {
   c->rank = rank;
@@ -63,6 +185,7 @@ static void attach(Comm* c, int rank, int size, int device, const ncclUniqueId* 
   resetLists(c);
   c->communicator = nullptr;
   if (size <= 1) return;
+  if (size > kMaxRanks) SB_FATAL("commInit: %d ranks exceed the supported maximum of %d", size, kMaxRanks);
   sbSetDevice(device);
   CommExt* e = new CommExt();
   e->rank = rank;
@@ -70,8 +193,30 @@ static void attach(Comm* c, int rank, int size, int device, const ncclUniqueId* 
   SB_NCCL(ncclCommInitRank(&e->nccl, size, *id, rank));
   e->dScalar = (double*)allocate(64, sizeof(double) * 8);
   e->hScalar = (double*)sbAllocateHost(sizeof(double) * 8);
+  e->dTickets = (unsigned int*)allocate(64, sizeof(unsigned int) * 4);
+  SB_CUDA(cudaMemset(e->dTickets, 0, sizeof(unsigned int) * 4));
   c->communicator = e;
   g_world = e;
+  // SB_COMM=nccl keeps every exchange on NCCL (the measured baseline); default: NVLink peer windows
+  const char* modeEnv = getenv("SB_COMM");
+  const bool wantPeer = !(modeEnv && strcmp(modeEnv, "nccl") == 0);
+  if (wantPeer) {
+    e->ctrl = (CtrlWindow*)allocate(256, sizeof(CtrlWindow));
+    SB_CUDA(cudaMemset(e->ctrl, 0, sizeof(CtrlWindow)));
+    SB_CUDA(cudaDeviceSynchronize());
+    std::vector<void*> peers;
+    if (mapPeers(e, e->ctrl, peers)) {
+      e->peerCtrl.resize((size_t)size);
+      for (int r = 0; r < size; r++) e->peerCtrl[(size_t)r] = (CtrlWindow*)peers[(size_t)r];
+      e->dPeerCtrl = (CtrlWindow**)allocate(64, sizeof(CtrlWindow*) * (size_t)size);
+      sbCopyToDevice(e->dPeerCtrl, e->peerCtrl.data(), sizeof(CtrlWindow*) * (size_t)size);
+      e->mode = COMM_PEER;
+    } else {
+      if (rank == 0) fprintf(stderr, "sparsebench_b200: CUDA IPC peer mapping unavailable, using NCCL for halo exchange and reductions\n");
+      sbFree(e->ctrl);
+      e->ctrl = nullptr;
+    }
+  }
 }
 
 // ---- unique-id rendezvous for launchers that only export RANK/WORLD_SIZE/MASTER_ADDR/MASTER_PORT
@@ -131,6 +276,107 @@ __global__ void packKernel(int n, const int* __restrict__ elements, const double
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = x[elements[i]];   // comm.c:635-638
 }
 
+__device__ __forceinline__ unsigned long long ldAcquireSys(const unsigned long long* p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void stReleaseSys(unsigned long long* p, unsigned long long v)
+{
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void spinUntilAtLeast(const unsigned long long* p, unsigned long long target, const char* what)
+{
+  const long long start = clock64();
+  while (ldAcquireSys(p) < target) {
+    __nanosleep(100);
+    if (clock64() - start > kSpinTimeoutCycles) {
+      printf("sparsebench_b200: timed out waiting for a peer (%s, target %llu)\n", what, target);
+      __trap();
+    }
+  }
+}
+
+// Sender side of the halo exchange: gather + direct stores into the receivers' slots, then publish `seq`.
+__global__ void __launch_bounds__(256)
+haloPutKernel(const PutPlan* __restrict__ plan, const int* __restrict__ elements, const double* __restrict__ x,
+    unsigned long long seq, unsigned int* ticket)
+{
+  __shared__ bool amLast;
+  const int nd = plan->ndest;
+  // the slot of parity seq&1 was last filled by exchange seq-2: wait until every receiver has drained that one
+  if ((int)threadIdx.x < nd && seq > 2) spinUntilAtLeast(plan->ack[threadIdx.x], seq - 2, "halo acknowledge");
+  __syncthreads();
+  const int total = plan->sdispl[nd];
+  const int par = (int)(seq & 1ull);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int d = 0;
+    while (i >= plan->sdispl[d + 1]) d++;
+    plan->remote[par][d][i - plan->sdispl[d]] = x[elements[i]];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicInc(ticket, gridDim.x - 1);
+    amLast = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (amLast && (int)threadIdx.x < nd) {
+    __threadfence_system();
+    stReleaseSys(plan->remoteFlag[threadIdx.x], seq);
+  }
+}
+
+// Receiver side: wait for every source's `seq`, copy the slot behind the local part of x, acknowledge.
+__global__ void __launch_bounds__(256)
+haloWaitKernel(const WaitPlan* __restrict__ plan, double* __restrict__ xHalo, unsigned long long seq, unsigned int* ticket)
+{
+  __shared__ bool amLast;
+  const int ns = plan->nsrc;
+  if ((int)threadIdx.x < ns) spinUntilAtLeast(plan->flag[threadIdx.x], seq, "halo arrival");
+  __syncthreads();
+  const double* src = plan->slot[seq & 1ull];
+  const int n = plan->externalCount;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) xHalo[i] = __ldcg(src + i);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicInc(ticket, gridDim.x - 1);
+    amLast = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (amLast && (int)threadIdx.x < ns) {
+    __threadfence_system();
+    stReleaseSys(plan->remoteAck[threadIdx.x], seq);
+  }
+}
+
+// All-reduce of one double over the peer windows (replaces MPI_Allreduce of comm.c:657,659).
+__global__ void __launch_bounds__(kMaxRanks)
+peerAllreduceKernel(CtrlWindow* mine, CtrlWindow* const* __restrict__ peers, int rank, int size, unsigned long long epoch,
+    double* d, int op)
+{
+  __shared__ double vals[kMaxRanks];
+  const int t = threadIdx.x;
+  const int slot = (int)(epoch % kRedDepth);
+  if (t < size) {
+    const double v = *d;
+    CtrlWindow* w = peers[t];
+    *(volatile double*)&w->redVal[slot][rank] = v;
+    __threadfence_system();
+    stReleaseSys(&w->redFlag[slot][rank], epoch);
+    spinUntilAtLeast(&mine->redFlag[slot][t], epoch, "all-reduce");
+    vals[t] = *(volatile double*)&mine->redVal[slot][t];
+  }
+  __syncthreads();
+  if (t == 0) {
+    double acc = vals[0];
+    for (int r = 1; r < size; r++) acc = (op == SB_MAX) ? (vals[r] > acc ? vals[r] : acc) : acc + vals[r];   // rank order: same bits on every rank
+    *d = acc;
+  }
+}
+
 __global__ void flagExternalKernel(uint64_t n, const Entry* __restrict__ e, uint32_t startRow, uint32_t stopRow,
     unsigned char* __restrict__ flag, uint32_t* __restrict__ col)
 {
@@ -159,28 +405,142 @@ __global__ void renumberKernel(uint64_t n, Entry* __restrict__ e, uint32_t start
   }
 }
 
-static void ensureDeviceLists(Comm* c)
+// Releases the device-side state of the current partition (collective in peer mode: peers may still store into
+// the halo window until everybody has reached this point).
+static void uninstallPartition(Comm* c)
 {
   CommExt* e = ext(c);
-  if (!e || c->totalSendCount == 0) return;
-  if (e->dElementsToSend && e->dElementsCount == c->totalSendCount) return;
-  sbFree(e->dElementsToSend);
-  e->dElementsToSend = (int*)allocate(64, sizeof(int) * (size_t)c->totalSendCount);
-  e->dElementsCount = c->totalSendCount;
-  sbCopyToDevice(e->dElementsToSend, c->elementsToSend, sizeof(int) * (size_t)c->totalSendCount);
-  if (!c->sendBuffer) c->sendBuffer = (CG_FLOAT*)allocate(64, sizeof(CG_FLOAT) * (size_t)c->totalSendCount);   // comm.c:124-125
+  if (!e || !e->installed) return;
+  SB_CUDA(cudaDeviceSynchronize());
+  if (e->mode == COMM_PEER) {
+    ncclBarrier(e);
+    std::vector<void*> peers(e->peerHalo.begin(), e->peerHalo.end());
+    unmapPeers(e, peers);
+    e->peerHalo.clear();
+    ncclBarrier(e);
+    sbFree(e->halo); e->halo = nullptr;
+    sbFree(e->dPut); e->dPut = nullptr;
+    sbFree(e->dWait); e->dWait = nullptr;
+  }
+  sbFree(e->dElementsToSend); e->dElementsToSend = nullptr;
+  if (c->sendBuffer) { sbFree(c->sendBuffer); c->sendBuffer = nullptr; }
+  e->installed = false;
 }
 
-void commExchangeOnStream(Comm* c, uint32_t numRows, double* x, cudaStream_t s)
+// Device-side state for the Comm lists of the current partition. Collective.
+static void installPartition(Comm* c)
+{
+  CommExt* e = ext(c);
+  if (!e || e->installed) return;
+  const int size = e->size, rank = e->rank;
+  if (c->totalSendCount > 0) {
+    e->dElementsToSend = (int*)allocate(64, sizeof(int) * (size_t)c->totalSendCount);
+    sbCopyToDevice(e->dElementsToSend, c->elementsToSend, sizeof(int) * (size_t)c->totalSendCount);
+    c->sendBuffer = (CG_FLOAT*)allocate(64, sizeof(CG_FLOAT) * (size_t)c->totalSendCount);   // comm.c:124-125
+  }
+  if (e->mode == COMM_PEER) {
+    if ((int)e->wantMatrix.size() != size * size) SB_FATAL("commPartition: missing halo count matrix");
+    const int* W = e->wantMatrix.data();
+    const size_t ext0 = (size_t)c->externalCount;
+    e->halo = (double*)allocate(256, sizeof(double) * (2 * ext0 + 2));
+    SB_CUDA(cudaMemset(e->halo, 0, sizeof(double) * (2 * ext0 + 2)));
+    SB_CUDA(cudaDeviceSynchronize());
+    std::vector<void*> peers;
+    if (!mapPeers(e, e->halo, peers)) SB_FATAL("commPartition: CUDA IPC mapping of the halo windows failed");
+    e->peerHalo.resize((size_t)size);
+    for (int r = 0; r < size; r++) e->peerHalo[(size_t)r] = (double*)peers[(size_t)r];
+    PutPlan put;
+    memset(&put, 0, sizeof(put));
+    put.ndest = c->outdegree;
+    for (int i = 0; i < c->outdegree; i++) {
+      const int d = c->destinations[i];
+      put.sdispl[i] = c->sdispls[i];
+      // my segment inside d's halo: after everything d receives from lower-ranked sources (its rdispls, comm.c:135)
+      size_t off = 0, extD = 0;
+      for (int s2 = 0; s2 < size; s2++) {
+        if (s2 < rank) off += (size_t)W[(size_t)d * size + s2];
+        extD += (size_t)W[(size_t)d * size + s2];
+      }
+      put.remote[0][i] = e->peerHalo[(size_t)d] + off;
+      put.remote[1][i] = e->peerHalo[(size_t)d] + extD + off;
+      put.remoteFlag[i] = &e->peerCtrl[(size_t)d]->haloFlag[rank];
+      put.ack[i] = &e->ctrl->haloAck[d];
+    }
+    put.sdispl[c->outdegree] = c->totalSendCount;
+    WaitPlan wait;
+    memset(&wait, 0, sizeof(wait));
+    wait.nsrc = c->indegree;
+    wait.externalCount = c->externalCount;
+    for (int i = 0; i < c->indegree; i++) {
+      const int s2 = c->sources[i];
+      wait.flag[i] = &e->ctrl->haloFlag[s2];
+      wait.remoteAck[i] = &e->peerCtrl[(size_t)s2]->haloAck[rank];
+    }
+    wait.slot[0] = e->halo;
+    wait.slot[1] = e->halo + ext0;
+    e->dPut = (PutPlan*)allocate(64, sizeof(PutPlan));
+    e->dWait = (WaitPlan*)allocate(64, sizeof(WaitPlan));
+    sbCopyToDevice(e->dPut, &put, sizeof(put));
+    sbCopyToDevice(e->dWait, &wait, sizeof(wait));
+    ncclBarrier(e);
+  }
+  e->installed = true;
+}
+
+bool commPeerMode(const Comm* c)
+{
+  CommExt* e = ext(c);
+  return e && e->mode == COMM_PEER;
+}
+
+// First half of an exchange: after this call the neighbours' copies of my boundary values are on their way.
+void commHaloPut(Comm* c, const double* x, const int* elements, cudaStream_t s)
 {
   CommExt* e = ext(c);
   if (!e || (c->indegree == 0 && c->outdegree == 0)) return;
-  ensureDeviceLists(c);
+  installPartition(c);
+  if (e->mode != COMM_PEER) SB_FATAL("commHaloPut needs the peer-window transport");
+  e->haloSeq++;
+  if (c->outdegree > 0) {
+    int blocks = (c->totalSendCount + 255) / 256;
+    if (blocks > 32) blocks = 32;
+    if (blocks < 1) blocks = 1;
+    haloPutKernel<<<blocks, 256, 0, s>>>(e->dPut, elements ? elements : e->dElementsToSend, x, e->haloSeq, e->dTickets);
+    SB_CUDA(cudaGetLastError());
+    countLaunch();
+  }
+}
+
+// Second half: x[numRows .. numRows+externalCount) holds the neighbours' values when this kernel has run.
+void commHaloWait(Comm* c, uint32_t numRows, double* x, cudaStream_t s)
+{
+  CommExt* e = ext(c);
+  if (!e || (c->indegree == 0 && c->outdegree == 0)) return;
+  if (c->indegree > 0) {
+    int blocks = (c->externalCount + 255) / 256;
+    if (blocks > 32) blocks = 32;
+    if (blocks < 1) blocks = 1;
+    haloWaitKernel<<<blocks, 256, 0, s>>>(e->dWait, x + numRows, e->haloSeq, e->dTickets + 1);
+    SB_CUDA(cudaGetLastError());
+    countLaunch();
+  }
+}
+
+void commExchangeOnStream(Comm* c, uint32_t numRows, double* x, const int* elements, cudaStream_t s)
+{
+  CommExt* e = ext(c);
+  if (!e || (c->indegree == 0 && c->outdegree == 0)) return;
+  installPartition(c);
+  if (e->mode == COMM_PEER) {
+    commHaloPut(c, x, elements, s);
+    commHaloWait(c, numRows, x, s);
+    return;
+  }
   if (c->totalSendCount > 0) {
     const int threads = 256;
     int blocks = (c->totalSendCount + threads - 1) / threads;
     if (blocks > ctx().numSMs * 4) blocks = ctx().numSMs * 4;
-    packKernel<<<blocks, threads, 0, s>>>(c->totalSendCount, e->dElementsToSend, x, c->sendBuffer);
+    packKernel<<<blocks, threads, 0, s>>>(c->totalSendCount, elements ? elements : e->dElementsToSend, x, c->sendBuffer);
     SB_CUDA(cudaGetLastError());
     countLaunch();
   }
@@ -197,19 +557,24 @@ void commAllreduceDevice(Comm* c, double* d, int count, int op, cudaStream_t s)
 {
   CommExt* e = ext(c);
   if (!e) return;
+  if (e->mode == COMM_PEER) {
+    for (int i = 0; i < count; i++) {
+      e->redEpoch++;
+      peerAllreduceKernel<<<1, kMaxRanks, 0, s>>>(e->ctrl, e->dPeerCtrl, e->rank, e->size, e->redEpoch, d + i, op);
+      SB_CUDA(cudaGetLastError());
+      countLaunch();
+    }
+    return;
+  }
   SB_NCCL(ncclAllReduce(d, d, (size_t)count, ncclDouble, op == SB_MAX ? ncclMax : ncclSum, e->nccl, s));
 }
 
-// all-gather of `count` ints per rank through NCCL (setup-time, tiny)
-static void allGatherInts(CommExt* e, const int* mine, int count, int* all)
+const int* commDeviceElements(Comm* c)
 {
-  Context& c = ctx();
-  int* d = (int*)allocate(64, sizeof(int) * (size_t)count * (size_t)(e->size + 1));
-  SB_CUDA(cudaMemcpyAsync(d, mine, sizeof(int) * (size_t)count, cudaMemcpyHostToDevice, c.stream));
-  SB_NCCL(ncclAllGather(d, d + count, (size_t)count, ncclInt32, e->nccl, c.stream));
-  SB_CUDA(cudaMemcpyAsync(all, d + count, sizeof(int) * (size_t)count * (size_t)e->size, cudaMemcpyDeviceToHost, c.stream));
-  SB_CUDA(cudaStreamSynchronize(c.stream));
-  sbFree(d);
+  CommExt* e = ext(c);
+  if (!e) return nullptr;
+  installPartition(c);
+  return e->dElementsToSend;
 }
 
 } // namespace sb
@@ -251,11 +616,19 @@ void commFinalize(Comm* c)
   free(c->sources); free(c->recvCounts); free(c->rdispls);          // comm.c:896-903
   free(c->destinations); free(c->sendCounts); free(c->sdispls);
   free(c->elementsToSend);
-  if (c->sendBuffer) sbFree(c->sendBuffer);
   CommExt* e = ext(c);
   if (e) {
     SB_CUDA(cudaDeviceSynchronize());
-    sbFree(e->dElementsToSend);
+    uninstallPartition(c);
+    if (e->mode == COMM_PEER) {
+      ncclBarrier(e);                                                // nobody stores into a window that is about to go
+      std::vector<void*> peers(e->peerCtrl.begin(), e->peerCtrl.end());
+      unmapPeers(e, peers);
+      ncclBarrier(e);
+      sbFree(e->ctrl);
+      sbFree(e->dPeerCtrl);
+    }
+    sbFree(e->dTickets);
     sbFree(e->dScalar);
     sbFreeHost(e->hScalar);
     ncclCommDestroy(e->nccl);
@@ -273,13 +646,15 @@ void commReduction(CG_FLOAT* v, int op)
   Context& c = ctx();
   e->hScalar[0] = *v;
   SB_CUDA(cudaMemcpyAsync(e->dScalar, e->hScalar, sizeof(double), cudaMemcpyHostToDevice, c.stream));
-  SB_NCCL(ncclAllReduce(e->dScalar, e->dScalar, 1, ncclDouble, op == SB_MAX ? ncclMax : ncclSum, e->nccl, c.stream));
+  Comm tmp;
+  tmp.communicator = e;
+  commAllreduceDevice(&tmp, e->dScalar, 1, op, c.stream);
   SB_CUDA(cudaMemcpyAsync(e->hScalar, e->dScalar, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
   SB_CUDA(cudaStreamSynchronize(c.stream));
   *v = e->hScalar[0];
 }
 
-void commExchange(Comm* c, CG_UINT numRows, CG_FLOAT* x) { commExchangeOnStream(c, numRows, x, ctx().stream); }
+void commExchange(Comm* c, CG_UINT numRows, CG_FLOAT* x) { commExchangeOnStream(c, numRows, x, nullptr, ctx().stream); }
 
 void commDistributeMatrix(Comm* c, MMMatrix* m, MMMatrix* mLocal)
 {
@@ -373,6 +748,10 @@ void sbPartitionFinish(SbPartitionPlan* P, Comm* c, const int* wantMatrix, const
 {
   CommLists L;
   P->plan.finish(L, wantMatrix, received);
+  if (CommExt* e = ext(c)) {
+    uninstallPartition(c);                                   // device state of a previous partition (collective)
+    e->wantMatrix.assign(wantMatrix, wantMatrix + (size_t)c->size * c->size);
+  }
   c->externalCount = L.externalCount;
   c->totalSendCount = L.totalSendCount;
   c->indegree = (int)L.sources.size();
@@ -438,7 +817,7 @@ void commPartition(Comm* c, GMatrix* m)
     sbFree(dSend); sbFree(dRecv);
   }
   sbPartitionFinish(P, c, wantMatrix.data(), received.data());
-  if (size > 1) ensureDeviceLists(c);
+  if (size > 1) installPartition(c);
 }
 
 } // extern "C"

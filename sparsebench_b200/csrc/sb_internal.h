@@ -90,6 +90,8 @@ struct DotArgs {
 };
 // y = A x on units [lo,hi) (rows for CRS/CCRS, chunks for SELL); with `dot` also sum_i x[i]*y[i] over them.
 uint32_t spmvUnits(const Operator& A);
+// largest unit range [lo, hi) around the middle whose rows reference no halo column (col >= nr); blocks the stream
+void spmvInteriorUnits(const Operator& A, uint32_t* lo, uint32_t* hi, cudaStream_t s);
 void launchSpmv(const Operator& A, const double* x, double* y, uint32_t lo, uint32_t hi, const DotArgs* dot,
     cudaStream_t s);
 
@@ -106,10 +108,17 @@ void launchInitVectors(uint32_t n, const uint32_t* rowPtr, const uint32_t* rowLe
 void launchScatter(uint32_t n, const uint32_t* map, const double* in, double* out, cudaStream_t s);   // out[map[i]] = in[i]
 void launchGather(uint32_t n, const uint32_t* map, const double* in, double* out, cudaStream_t s);    // out[i] = in[map[i]]
 void launchMaxErr(uint32_t n, const double* x, double* out, cudaStream_t s);
+void launchPermuteIndices(uint32_t n, const uint32_t* map, const int* in, int* out, cudaStream_t s);   // out[i] = map[in[i]]
 
 // ---- communication (comm.cu)
-void commExchangeOnStream(Comm* c, uint32_t numRows, double* x, cudaStream_t s);
+// `elements` overrides the device copy of Comm.elementsToSend (the CG passes row-permuted indices for SELL)
+void commExchangeOnStream(Comm* c, uint32_t numRows, double* x, const int* elements, cudaStream_t s);
 void commAllreduceDevice(Comm* c, double* d, int count, int op, cudaStream_t s);
+// NVLink peer-window transport: the exchange split in its two halves, so that interior rows run in between
+bool commPeerMode(const Comm* c);
+void commHaloPut(Comm* c, const double* x, const int* elements, cudaStream_t s);
+void commHaloWait(Comm* c, uint32_t numRows, double* x, cudaStream_t s);
+const int* commDeviceElements(Comm* c);                    // device copy of Comm.elementsToSend
 
 // ---- side tables keyed by the device array a Matrix struct points to
 struct ScsExt {

@@ -627,6 +627,47 @@ static void launchRowsAuto(Access acc, const uint32_t* rowPtr, uint32_t nr, uint
 
 uint32_t spmvUnits(const Operator& A) { return A.fmt == SB_FMT_SCS ? A.sell.nChunks : A.nr; }
 
+// ---- interior / boundary split for the overlapped halo exchange (setup, once per solver)
+// bounds[0] = max(u+1) over halo-touching units u below the middle, bounds[1] = min(u) over those at or above it
+__global__ void haloTouchKernel(Operator A, uint32_t units, uint32_t* bounds)
+{
+  const uint32_t mid = units / 2;
+  for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < units; u += gridDim.x * blockDim.x) {
+    bool touch = false;
+    if (A.fmt == SB_FMT_SCS) {
+      const uint64_t b = A.sell.chunkPtr[u], e = b + (uint64_t)A.sell.chunkLens[u] * A.sell.C;
+      for (uint64_t j = b; j < e && !touch; j++) touch = A.sell.col[j] >= A.nr;
+    } else if (A.fmt == SB_FMT_CRS) {
+      for (uint32_t j = A.crs.rowPtr[u]; j < A.crs.rowPtr[u + 1] && !touch; j++) touch = A.crs.col[j] >= A.nr;
+    } else {
+      for (uint32_t j = A.ccrs.rowPtr[u]; j < A.ccrs.rowPtr[u + 1] && !touch; j++) touch = A.ccrs.entries[j].col >= A.nr;
+    }
+    if (touch) {
+      if (u < mid) atomicMax(bounds, u + 1);
+      else atomicMin(bounds + 1, u);
+    }
+  }
+}
+
+void spmvInteriorUnits(const Operator& A, uint32_t* lo, uint32_t* hi, cudaStream_t s)
+{
+  const uint32_t units = spmvUnits(A);
+  uint32_t h[2] = { 0u, units };
+  if (units > 0) {
+    uint32_t* d = (uint32_t*)allocate(64, 2 * sizeof(uint32_t));
+    SB_CUDA(cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, s));
+    const int blocks = (int)(((uint64_t)units + 127) / 128 < (uint64_t)ctx().numSMs * 16 ? ((uint64_t)units + 127) / 128 : (uint64_t)ctx().numSMs * 16);
+    haloTouchKernel<<<blocks, 128, 0, s>>>(A, units, d);
+    SB_CUDA(cudaGetLastError());
+    countLaunch();
+    SB_CUDA(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    sbFree(d);
+  }
+  *lo = h[0];
+  *hi = h[1] > h[0] ? h[1] : h[0];
+}
+
 void launchSpmv(const Operator& A, const double* x, double* y, uint32_t lo, uint32_t hi, const DotArgs* dot,
     cudaStream_t s)
 {

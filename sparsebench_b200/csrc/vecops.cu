@@ -265,6 +265,18 @@ void launchGather(uint32_t n, const uint32_t* map, const double* in, double* out
   countLaunch();
 }
 
+__global__ void permuteIndicesKernel(uint32_t n, const uint32_t* __restrict__ map, const int* __restrict__ in, int* __restrict__ out)
+{
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = (int)map[in[i]];
+}
+void launchPermuteIndices(uint32_t n, const uint32_t* map, const int* in, int* out, cudaStream_t s)
+{
+  if (n == 0) return;
+  permuteIndicesKernel<<<vecGrid(n, 1), kVecThreads, 0, s>>>(n, map, in, out);
+  SB_CUDA(cudaGetLastError());
+  countLaunch();
+}
+
 // max_i |x[i] - 1| (solverCheckResidual, CGSolver.c:40-60 with xexact == 1). NaN never compares greater, as in the
 // reference loop (CGSolver.c:50-53). Non-negative doubles order like their bit patterns, so the grid maximum is an
 // integer atomicMax.

@@ -1,0 +1,100 @@
+"""Multi-GPU parity check (run under torchrun, one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 tests/mgpu_check.py
+
+Every rank builds its z-slab on its GPU through the C ABI (matrixGenerate -> commPartition -> convertMatrix ->
+solveCG) and compares with the CPU oracle: halo index lists bit-exact against the oracle's restatement of
+comm.c:414-625, halo exchange values exact, CG residual history within 1e-10 of the single-rank oracle run on the
+global problem with an identical iteration count, solution slab within 1e-9. Exits non-zero on any mismatch.
+Also imported by tests/test_gpu_multi.py, which launches it when at least two GPUs are visible.
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import orc  # noqa: E402
+from sparsebench_b200 import api  # noqa: E402
+
+CG_TOL = 1e-10
+
+
+def check(cond, msg, failures):
+    if not cond:
+        failures.append(msg)
+
+
+def main():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    L = api.lib()
+    comm = api.Comm()
+    L.commInit(C.byref(comm), 0, None)           # reads RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* (comm.h:48)
+    assert (comm.rank, comm.size) == (rank, world)
+    failures = []
+    cases = [(8, 8, 4, 10, 0.0), (16, 16, 6, 60, 1e-6), (12, 10, 3, 30, 1e-3), (32, 32, 8, 40, 0.0)]
+    fmts = [(api.FMT_CRS, 0), (api.FMT_SCS, 1), (api.FMT_SCS, 256), (api.FMT_CCRS, 0)]
+    for (nx, ny, nz, itermax, eps) in cases:
+        # oracle: global problem on one rank + the reference's partition lists for every rank
+        mg = orc.generate(nx, ny, nz * world)
+        x0, b, _ = orc.init_vectors(mg)
+        kref, href, xref = orc.cg_crs(mg, b, x0, itermax, eps)
+        omats = [orc.generate(nx, ny, nz, r, world) for r in range(world)]
+        part = orc.Partition(omats)
+        n = nx * ny * nz
+        for fmt, sigma in fmts:
+            tag = "%dx%dx%d fmt=%s sigma=%d" % (nx, ny, nz, api.FMT_NAMES[fmt], sigma)
+            g = api.matrixGenerate(nx, ny, nz, rank, world, device=True)
+            L.commPartition(C.byref(comm), C.byref(g))
+            d, o = comm.lists(), part.ranks[rank]
+            for f in ("externalCount", "totalSendCount"):
+                check(d[f] == o[f], "%s: %s %r != %r" % (tag, f, d[f], o[f]), failures)
+            for f in ("sources", "recvCounts", "rdispls", "destinations", "sendCounts", "sdispls", "elementsToSend"):
+                check(np.array_equal(d[f], o[f]), "%s: list %s differs" % (tag, f), failures)
+            check(np.array_equal(api.gmatrix_arrays(g)[1], omats[rank].col), "%s: renumbered columns differ" % tag, failures)
+            # halo exchange through the drop-in entry point (comm.c:627-651): x = global row id
+            nc = n + comm.externalCount
+            xs = np.zeros(nc)
+            xs[:n] = rank * n + np.arange(n)
+            xd = api.to_device(xs)
+            L.commExchange(C.byref(comm), n, xd.ptr)
+            got = api.to_host(xd, np.float64, nc)
+            want = np.array(part.ranks[rank]["externalsReordered"], np.float64) if "externalsReordered" in part.ranks[rank] else None
+            if want is not None:
+                check(np.array_equal(got[n:], want), "%s: halo values differ" % tag, failures)
+            A = api.convertMatrix(fmt, g, 32, sigma)
+            for flags in (api.CG_FUSED, api.CG_FUSED | api.CG_NO_OVERLAP, 0):
+                k, hist, x, info = api.solveCG(A, itermax, eps, comm=comm, flags=flags, want_x=True)
+                check(k == kref, "%s flags=%d: k %d != %d" % (tag, flags, k, kref), failures)
+                if len(hist) == len(href):
+                    scale = np.maximum(href, 1e-10 * href[0])
+                    err = float(np.max(np.abs(hist - href) / scale))
+                    check(err <= CG_TOL, "%s flags=%d: history error %.3e" % (tag, flags, err), failures)
+                else:
+                    check(False, "%s flags=%d: history length %d != %d" % (tag, flags, len(hist), len(href)), failures)
+                xe = float(np.max(np.abs(x - xref[rank * n:(rank + 1) * n])))
+                check(xe <= 1e-9 * max(1.0, float(np.max(np.abs(xref)))), "%s flags=%d: solution error %.3e" % (tag, flags, xe), failures)
+            api.destroyMatrix(A)
+            if fmt != api.FMT_CCRS:
+                L.sbFreeGMatrix(C.byref(g))
+    # global reductions (comm.c:653-662)
+    v = C.c_double(float(rank + 1))
+    L.commReduction(C.byref(v), api.OP_SUM)
+    check(v.value == world * (world + 1) / 2.0, "commReduction SUM %r" % v.value, failures)
+    v = C.c_double(float(rank + 1))
+    L.commReduction(C.byref(v), api.OP_MAX)
+    check(v.value == float(world), "commReduction MAX %r" % v.value, failures)
+    L.commFinalize(C.byref(comm))
+    for f in failures[:20]:
+        print("[rank %d] FAIL %s" % (rank, f), flush=True)
+    print("[rank %d] mgpu_check: %s (%d failures, mode %s)" % (rank, "PASS" if not failures else "FAIL", len(failures),
+                                                              os.environ.get("SB_COMM", "default")), flush=True)
+    return 1 if failures else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
