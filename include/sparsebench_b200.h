@@ -222,6 +222,7 @@ void commFinalize(Comm* c);                                                   /*
 void commPartition(Comm* c, GMatrix* m);                                      /* comm.h:51, comm.c:414-625 */
 void commExchange(Comm* c, CG_UINT numRows, CG_FLOAT* x);                     /* comm.h:57, comm.c:627-651 */
 void commReduction(CG_FLOAT* v, int op);                                      /* comm.h:58, comm.c:653-662 (host scalar) */
+void sbCommAllreduceDevice(Comm* c, CG_FLOAT* dev, int count, int op);        /* the same reduction on device scalars, asynchronous */
 void commDistributeMatrix(Comm* c, MMMatrix* m, MMMatrix* mLocal);            /* comm.h:50, comm.c:311-412 (single rank) */
 /* bootstrap pieces used when another launcher (torchrun) already owns the rendezvous */
 int sbCommUniqueIdBytes(void);

@@ -30,7 +30,7 @@ struct CgSolver {
   cudaStream_t s = nullptr;
   double eps = 0.0;
   int itermax = 0, flags = 0, printFreq = 1;
-  bool fused = true, print = false, generated = false, profile = false, overlap = true;
+  bool fused = true, print = false, generated = false, profile = false, overlap = true, gated = false;
   int* elemsPerm = nullptr;                // SELL with a row permutation: elementsToSend in solver (permuted) numbering
   uint32_t intLo = 0, intHi = 0;           // SpMV units [intLo, intHi) reference no halo column
   uint32_t n = 0;
@@ -66,31 +66,21 @@ struct CgSolver {
     mark(R_ALLREDUCE);
   }
 
-  // commExchange + spMVM (CGSolver.c:95-96,122-123). With the peer-window transport the exchange is split: my
-  // boundary values leave first, the rows that reference no halo column are multiplied while the neighbours'
-  // values arrive, the boundary rows follow once they are there.
+  // commExchange + spMVM (CGSolver.c:95-96,122-123). With the peer-window transport my boundary values are stored
+  // straight behind the neighbours' copy of p, and ONE SpMV launch multiplies the rows that reference no halo
+  // column while those stores are in flight, waits on the arrival counters, and finishes with the boundary rows.
   void spmvWithHalo(const DotArgs* dot)
   {
     const uint32_t units = spmvUnits(A);
     if (commActive(comm)) {
-      if (commPeerMode(comm)) {
-        commHaloPut(comm, p, elemsPerm, s);
+      if (gated) {
+        const HaloGate gate = commHaloPutDirect(comm, p, elemsPerm, s);
         mark(R_EXCHANGE);
-        if (overlap && intLo < intHi) {
-          launchSpmv(A, p, Ap, intLo, intHi, dot, s);
-          mark(R_SPMV);
-          commHaloWait(comm, A.nr, p, s);
-          mark(R_HALO_WAIT);
-          DotArgs more { dot ? dot->out : nullptr, true, dot ? dot->slot : 0 };
-          launchSpmv(A, p, Ap, 0, intLo, dot ? &more : nullptr, s);
-          launchSpmv(A, p, Ap, intHi, units, dot ? &more : nullptr, s);
-          mark(R_SPMV_BOUNDARY);
-          return;
-        }
-        commHaloWait(comm, A.nr, p, s);
-      } else {
-        commExchangeOnStream(comm, A.nr, p, elemsPerm, s);
+        launchSpmvGated(A, p, Ap, intLo, intHi, gate, dot, s);
+        mark(R_SPMV);
+        return;
       }
+      commExchangeOnStream(comm, A.nr, p, elemsPerm, s);
       mark(R_EXCHANGE);
     }
     launchSpmv(A, p, Ap, 0, units, dot, s);
@@ -172,7 +162,12 @@ struct CgSolver {
         elemsPerm = (int*)allocate(64, sizeof(int) * (size_t)comm->totalSendCount);
         launchPermuteIndices((uint32_t)comm->totalSendCount, A.oldToNew, commDeviceElements(comm), elemsPerm, s);
       }
-      spmvInteriorUnits(A, &intLo, &intHi, s);
+      // direct halo delivery into p + gated single-launch SpMV (collective decision inside commAttachHaloVector)
+      if (commPeerMode(comm)) {
+        const bool can = overlap && spmvGatedAvailable(A);
+        if (can) spmvInteriorUnits(A, &intLo, &intHi, s);
+        gated = commAttachHaloVector(comm, p, A.nr, can);
+      }
     }
 
     // initVectors (CGSolver.c:19-38), or caller-supplied b / x0
@@ -269,6 +264,7 @@ struct CgSolver {
   {
     Context& c = ctx();
     SB_CUDA(cudaStreamSynchronize(s));
+    if (gated) commDetachHaloVector(comm);
     if (fused && (int)hist.size() < k) {
       // iteration k-1 was the last one executed; record its normr = sqrt(rho[k-2])
       const double last = k >= 3 ? sqrt(hRho[k - 2]) : normr;

@@ -53,6 +53,7 @@ constexpr long long kSpinTimeoutCycles = 40000000000ll;   // ~20 s: a dead peer 
 struct CtrlWindow {
   unsigned long long haloFlag[kMaxRanks];              // [source rank] newest exchange completely stored by that source
   unsigned long long haloAck[kMaxRanks];               // [dest rank]   newest exchange that dest has copied out of its slot
+  unsigned long long directFlag[kMaxRanks];            // [source rank] arrival counter of direct (registered-vector) exchanges
   unsigned long long redFlag[kRedDepth][kMaxRanks];    // [epoch % depth][rank] epoch of the value below
   double redVal[kRedDepth][kMaxRanks];
 };
@@ -94,6 +95,11 @@ struct CommExt {
   WaitPlan* dWait = nullptr;
   unsigned int* dTickets = nullptr;
   unsigned long long haloSeq = 0, redEpoch = 0;
+  // registered halo vector (direct delivery)
+  std::vector<double*> peerVec;
+  PutPlan* dPutDirect = nullptr;
+  unsigned long long directSeq = 0;
+  bool attached = false;
 };
 
 static CommExt* g_world = nullptr;   // commReduction has no Comm* argument (it used MPI_COMM_WORLD, comm.c:653-662)
@@ -286,70 +292,83 @@ __device__ __forceinline__ void stReleaseSys(unsigned long long* p, unsigned lon
 {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ void spinUntilAtLeast(const unsigned long long* p, unsigned long long target, const char* what)
+// A dead peer must not hang the GPU: give up (trap -> the host sees a launch failure and exits) after ~20 s.
+__device__ __forceinline__ void spinUntilAtLeast(const unsigned long long* p, unsigned long long target)
 {
+  if (ldAcquireSys(p) >= target) return;
   const long long start = clock64();
   while (ldAcquireSys(p) < target) {
-    __nanosleep(100);
-    if (clock64() - start > kSpinTimeoutCycles) {
-      printf("sparsebench_b200: timed out waiting for a peer (%s, target %llu)\n", what, target);
-      __trap();
-    }
+    __nanosleep(40);
+    if (clock64() - start > kSpinTimeoutCycles) __trap();
   }
 }
 
-// Sender side of the halo exchange: gather + direct stores into the receivers' slots, then publish `seq`.
-__global__ void __launch_bounds__(256)
-haloPutKernel(const PutPlan* __restrict__ plan, const int* __restrict__ elements, const double* __restrict__ x,
-    unsigned long long seq, unsigned int* ticket)
+// Sender side of the halo exchange: gather + direct stores into the receivers' slots. Every block publishes its
+// part with one system-scope reduction on the receiver's arrival counter (no grid-wide rendezvous): exchange
+// number `seq` is complete at a receiver when its counter for this source has reached seq * kPutBlocks.
+constexpr int kPutBlocks = 32, kWaitBlocks = 32, kHaloThreads = 512;
+
+__device__ __forceinline__ void signalAddSys(unsigned long long* p)
 {
-  __shared__ bool amLast;
+  asm volatile("red.release.sys.global.add.u64 [%0], 1;" ::"l"(p) : "memory");
+}
+
+__global__ void __launch_bounds__(kHaloThreads)
+haloPutKernel(const PutPlan* __restrict__ plan, const int* __restrict__ elements, const double* __restrict__ x,
+    unsigned long long seq, bool direct)
+{
   const int nd = plan->ndest;
   // the slot of parity seq&1 was last filled by exchange seq-2: wait until every receiver has drained that one
-  if ((int)threadIdx.x < nd && seq > 2) spinUntilAtLeast(plan->ack[threadIdx.x], seq - 2, "halo acknowledge");
+  if (!direct && (int)threadIdx.x < nd && seq > 2) spinUntilAtLeast(plan->ack[threadIdx.x], (seq - 2) * kWaitBlocks);
   __syncthreads();
   const int total = plan->sdispl[nd];
-  const int par = (int)(seq & 1ull);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    int d = 0;
-    while (i >= plan->sdispl[d + 1]) d++;
-    plan->remote[par][d][i - plan->sdispl[d]] = x[elements[i]];
+  const int par = direct ? 0 : (int)(seq & 1ull);
+  const int stride = gridDim.x * blockDim.x;
+  for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {   // 4 independent gathers in flight
+    int idx[4];
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (i0 + u * stride < total) idx[u] = elements[i0 + u * stride];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (i0 + u * stride < total) v[u] = x[idx[u]];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u * stride;
+      if (i < total) {
+        int d = 0;
+        while (i >= plan->sdispl[d + 1]) d++;
+        plan->remote[par][d][i - plan->sdispl[d]] = v[u];
+      }
+    }
   }
-  __threadfence_system();
+  // the barrier orders every thread's stores before the signalling threads' release (cumulative, system scope)
   __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int t = atomicInc(ticket, gridDim.x - 1);
-    amLast = (t == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (amLast && (int)threadIdx.x < nd) {
-    __threadfence_system();
-    stReleaseSys(plan->remoteFlag[threadIdx.x], seq);
-  }
+  if ((int)threadIdx.x < nd) signalAddSys(plan->remoteFlag[threadIdx.x]);
 }
 
 // Receiver side: wait for every source's `seq`, copy the slot behind the local part of x, acknowledge.
-__global__ void __launch_bounds__(256)
-haloWaitKernel(const WaitPlan* __restrict__ plan, double* __restrict__ xHalo, unsigned long long seq, unsigned int* ticket)
+__global__ void __launch_bounds__(kHaloThreads)
+haloWaitKernel(const WaitPlan* __restrict__ plan, double* __restrict__ xHalo, unsigned long long seq)
 {
-  __shared__ bool amLast;
   const int ns = plan->nsrc;
-  if ((int)threadIdx.x < ns) spinUntilAtLeast(plan->flag[threadIdx.x], seq, "halo arrival");
+  if ((int)threadIdx.x < ns) spinUntilAtLeast(plan->flag[threadIdx.x], seq * kPutBlocks);
   __syncthreads();
   const double* src = plan->slot[seq & 1ull];
   const int n = plan->externalCount;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) xHalo[i] = __ldcg(src + i);
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int t = atomicInc(ticket, gridDim.x - 1);
-    amLast = (t == gridDim.x - 1);
+  const int stride = gridDim.x * blockDim.x;
+  for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (i0 + u * stride < n) v[u] = __ldcg(src + i0 + u * stride);
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (i0 + u * stride < n) xHalo[i0 + u * stride] = v[u];
   }
   __syncthreads();
-  if (amLast && (int)threadIdx.x < ns) {
-    __threadfence_system();
-    stReleaseSys(plan->remoteAck[threadIdx.x], seq);
-  }
+  if ((int)threadIdx.x < ns) signalAddSys(plan->remoteAck[threadIdx.x]);   // release: ordered after this block's reads
 }
 
 // All-reduce of one double over the peer windows (replaces MPI_Allreduce of comm.c:657,659).
@@ -366,7 +385,7 @@ peerAllreduceKernel(CtrlWindow* mine, CtrlWindow* const* __restrict__ peers, int
     *(volatile double*)&w->redVal[slot][rank] = v;
     __threadfence_system();
     stReleaseSys(&w->redFlag[slot][rank], epoch);
-    spinUntilAtLeast(&mine->redFlag[slot][t], epoch, "all-reduce");
+    spinUntilAtLeast(&mine->redFlag[slot][t], epoch);
     vals[t] = *(volatile double*)&mine->redVal[slot][t];
   }
   __syncthreads();
@@ -412,6 +431,7 @@ static void uninstallPartition(Comm* c)
   CommExt* e = ext(c);
   if (!e || !e->installed) return;
   SB_CUDA(cudaDeviceSynchronize());
+  commDetachHaloVector(c);
   if (e->mode == COMM_PEER) {
     ncclBarrier(e);
     std::vector<void*> peers(e->peerHalo.begin(), e->peerHalo.end());
@@ -478,6 +498,12 @@ static void installPartition(Comm* c)
     }
     wait.slot[0] = e->halo;
     wait.slot[1] = e->halo + ext0;
+    // arrival / acknowledge counters restart with every partition (the neighbour sets may have changed)
+    e->haloSeq = 0;
+    ncclBarrier(e);
+    SB_CUDA(cudaMemset(e->ctrl->haloFlag, 0, sizeof(e->ctrl->haloFlag)));
+    SB_CUDA(cudaMemset(e->ctrl->haloAck, 0, sizeof(e->ctrl->haloAck)));
+    SB_CUDA(cudaDeviceSynchronize());
     e->dPut = (PutPlan*)allocate(64, sizeof(PutPlan));
     e->dWait = (WaitPlan*)allocate(64, sizeof(WaitPlan));
     sbCopyToDevice(e->dPut, &put, sizeof(put));
@@ -502,10 +528,7 @@ void commHaloPut(Comm* c, const double* x, const int* elements, cudaStream_t s)
   if (e->mode != COMM_PEER) SB_FATAL("commHaloPut needs the peer-window transport");
   e->haloSeq++;
   if (c->outdegree > 0) {
-    int blocks = (c->totalSendCount + 255) / 256;
-    if (blocks > 32) blocks = 32;
-    if (blocks < 1) blocks = 1;
-    haloPutKernel<<<blocks, 256, 0, s>>>(e->dPut, elements ? elements : e->dElementsToSend, x, e->haloSeq, e->dTickets);
+    haloPutKernel<<<kPutBlocks, kHaloThreads, 0, s>>>(e->dPut, elements ? elements : e->dElementsToSend, x, e->haloSeq, false);
     SB_CUDA(cudaGetLastError());
     countLaunch();
   }
@@ -517,13 +540,86 @@ void commHaloWait(Comm* c, uint32_t numRows, double* x, cudaStream_t s)
   CommExt* e = ext(c);
   if (!e || (c->indegree == 0 && c->outdegree == 0)) return;
   if (c->indegree > 0) {
-    int blocks = (c->externalCount + 255) / 256;
-    if (blocks > 32) blocks = 32;
-    if (blocks < 1) blocks = 1;
-    haloWaitKernel<<<blocks, 256, 0, s>>>(e->dWait, x + numRows, e->haloSeq, e->dTickets + 1);
+    haloWaitKernel<<<kWaitBlocks, kHaloThreads, 0, s>>>(e->dWait, x + numRows, e->haloSeq);
     SB_CUDA(cudaGetLastError());
     countLaunch();
   }
+}
+
+bool commAttachHaloVector(Comm* c, double* x, uint32_t numRows, bool localOk)
+{
+  CommExt* e = ext(c);
+  if (!e || e->mode != COMM_PEER) return false;
+  installPartition(c);
+  if (e->attached) commDetachHaloVector(c);
+  const int size = e->size, rank = e->rank;
+  int ok = (localOk && c->indegree <= kMaxGateSources) ? 1 : 0;   // collective decision: every rank must agree
+  std::vector<int> oks((size_t)size);
+  allGatherInts(e, &ok, 1, oks.data());
+  for (int r = 0; r < size; r++) ok &= oks[(size_t)r];
+  if (!ok) return false;
+  SB_CUDA(cudaDeviceSynchronize());
+  std::vector<void*> peers;
+  if (!mapPeers(e, x, peers)) return false;
+  e->peerVec.resize((size_t)size);
+  for (int r = 0; r < size; r++) e->peerVec[(size_t)r] = (double*)peers[(size_t)r];
+  std::vector<int> rows((size_t)size);
+  int mine = (int)numRows;
+  allGatherInts(e, &mine, 1, rows.data());
+  const int* W = e->wantMatrix.data();
+  PutPlan put;
+  memset(&put, 0, sizeof(put));
+  put.ndest = c->outdegree;
+  for (int i = 0; i < c->outdegree; i++) {
+    const int d = c->destinations[i];
+    put.sdispl[i] = c->sdispls[i];
+    size_t off = 0;
+    for (int s2 = 0; s2 < rank; s2++) off += (size_t)W[(size_t)d * size + s2];
+    put.remote[0][i] = put.remote[1][i] = e->peerVec[(size_t)d] + (size_t)rows[(size_t)d] + off;   // x_d + nr_d + rdispl
+    put.remoteFlag[i] = &e->peerCtrl[(size_t)d]->directFlag[rank];
+    put.ack[i] = nullptr;
+  }
+  put.sdispl[c->outdegree] = c->totalSendCount;
+  e->dPutDirect = (PutPlan*)allocate(64, sizeof(PutPlan));
+  sbCopyToDevice(e->dPutDirect, &put, sizeof(put));
+  e->directSeq = 0;
+  SB_CUDA(cudaMemset(e->ctrl->directFlag, 0, sizeof(e->ctrl->directFlag)));
+  SB_CUDA(cudaDeviceSynchronize());
+  ncclBarrier(e);
+  e->attached = true;
+  return true;
+}
+
+void commDetachHaloVector(Comm* c)
+{
+  CommExt* e = ext(c);
+  if (!e || !e->attached) return;
+  SB_CUDA(cudaDeviceSynchronize());
+  ncclBarrier(e);                                           // nobody stores into a vector that is about to go
+  std::vector<void*> peers(e->peerVec.begin(), e->peerVec.end());
+  unmapPeers(e, peers);
+  e->peerVec.clear();
+  sbFree(e->dPutDirect);
+  e->dPutDirect = nullptr;
+  ncclBarrier(e);
+  e->attached = false;
+}
+
+HaloGate commHaloPutDirect(Comm* c, const double* x, const int* elements, cudaStream_t s)
+{
+  CommExt* e = ext(c);
+  HaloGate g;
+  if (!e || !e->attached) SB_FATAL("commHaloPutDirect: no registered halo vector");
+  e->directSeq++;
+  if (c->outdegree > 0) {
+    haloPutKernel<<<kPutBlocks, kHaloThreads, 0, s>>>(e->dPutDirect, elements ? elements : e->dElementsToSend, x, e->directSeq, true);
+    SB_CUDA(cudaGetLastError());
+    countLaunch();
+  }
+  g.nsrc = c->indegree;
+  g.target = e->directSeq * kPutBlocks;
+  for (int i = 0; i < c->indegree; i++) g.flag[i] = &e->ctrl->directFlag[c->sources[i]];
+  return g;
 }
 
 void commExchangeOnStream(Comm* c, uint32_t numRows, double* x, const int* elements, cudaStream_t s)
@@ -653,6 +749,8 @@ void commReduction(CG_FLOAT* v, int op)
   SB_CUDA(cudaStreamSynchronize(c.stream));
   *v = e->hScalar[0];
 }
+
+void sbCommAllreduceDevice(Comm* c, CG_FLOAT* dev, int count, int op) { commAllreduceDevice(c, dev, count, op, ctx().stream); }
 
 void commExchange(Comm* c, CG_UINT numRows, CG_FLOAT* x) { commExchangeOnStream(c, numRows, x, nullptr, ctx().stream); }
 

@@ -190,6 +190,7 @@ Operator makeOperator(void* matrix, int fmt)
     A.crs = CrsView { m->nr, m->rowPtr, m->colInd, m->val };
     CrsExt* e = crsExt(m->val, false);
     A.nnzTrue = e ? e->nnzTrue : 0;
+    A.split = e ? &e->split : nullptr;
   } else if (fmt == SB_FMT_CCRS) {
     SbCCRSMatrix* m = (SbCCRSMatrix*)matrix;
     A.nr = m->nr; A.nc = m->nc; A.nrPadded = m->nr;
@@ -197,6 +198,7 @@ Operator makeOperator(void* matrix, int fmt)
     A.ccrs = CcrsView { m->nr, m->rowPtr, m->entries };
     CrsExt* e = crsExt(m->entries, false);
     A.nnzTrue = e ? e->nnzTrue : 0;
+    A.split = e ? &e->split : nullptr;
   } else if (fmt == SB_FMT_SCS) {
     SbSCSMatrix* m = (SbSCSMatrix*)matrix;
     ScsExt* e = scsExt(m->val, false);
@@ -204,6 +206,7 @@ Operator makeOperator(void* matrix, int fmt)
     A.nr = m->nr; A.nc = e->nc; A.nrPadded = m->nrPadded;
     A.rowLen = e->rowLenPerm;
     A.nnzTrue = e->nnzTrue;
+    A.split = &e->split;
     if (!e->identityPerm) { A.oldToNew = m->oldToNewPerm; A.newToOld = m->newToOldPerm; }
     A.sell = SellView { m->nChunks, m->nr, m->C, m->chunkPtr, m->chunkLens, e->identityPerm ? m->colInd : e->colPerm, m->val };
   } else {

@@ -68,9 +68,16 @@ struct CcrsView {
   const Entry* entries;
 };
 
+// cached interior/boundary split of a converted matrix (spmvInteriorUnits)
+struct HaloSplit {
+  bool valid = false;
+  uint32_t lo = 0, hi = 0;
+};
+
 // A sparse operator as the CG driver sees it.
 struct Operator {
   int fmt;
+  HaloSplit* split = nullptr;              // cache slot in the matrix's side table
   uint32_t nr = 0, nc = 0, nrPadded = 0;   // vectors written by spmv need nrPadded slots
   uint64_t nnzTrue = 0;
   const uint32_t* rowPtr = nullptr;        // CRS/CCRS: device rowPtr (b = 27-(len-1) rule); SCS: original-order rowLen
@@ -81,6 +88,8 @@ struct Operator {
   SellView sell{};                         // col = symmetric-permuted columns when oldToNew != nullptr
   CcrsView ccrs{};
 };
+
+struct HaloGate;
 
 // Fused dot-product epilogue: *out = (accumulate ? *out : 0) + sum, reduced through scratch slot `slot` (0..3).
 struct DotArgs {
@@ -94,6 +103,11 @@ uint32_t spmvUnits(const Operator& A);
 void spmvInteriorUnits(const Operator& A, uint32_t* lo, uint32_t* hi, cudaStream_t s);
 void launchSpmv(const Operator& A, const double* x, double* y, uint32_t lo, uint32_t hi, const DotArgs* dot,
     cudaStream_t s);
+// y = A x over all units in ONE launch, ordered interior [intLo,intHi) first; the kernel waits on `gate` before the
+// first unit outside that range (those reference halo columns, which a peer is storing while the interior runs)
+bool spmvGatedAvailable(const Operator& A);
+void launchSpmvGated(const Operator& A, const double* x, double* y, uint32_t intLo, uint32_t intHi, const HaloGate& gate,
+    const DotArgs* dot, cudaStream_t s);
 
 // ---- vector kernels (vecops.cu)
 void launchWaxpby(uint32_t n, double alpha, const double* x, double beta, const double* y, double* w, cudaStream_t s);
@@ -114,14 +128,26 @@ void launchPermuteIndices(uint32_t n, const uint32_t* map, const int* in, int* o
 // `elements` overrides the device copy of Comm.elementsToSend (the CG passes row-permuted indices for SELL)
 void commExchangeOnStream(Comm* c, uint32_t numRows, double* x, const int* elements, cudaStream_t s);
 void commAllreduceDevice(Comm* c, double* d, int count, int op, cudaStream_t s);
-// NVLink peer-window transport: the exchange split in its two halves, so that interior rows run in between
+// NVLink peer-window transport
 bool commPeerMode(const Comm* c);
-void commHaloPut(Comm* c, const double* x, const int* elements, cudaStream_t s);
-void commHaloWait(Comm* c, uint32_t numRows, double* x, cudaStream_t s);
 const int* commDeviceElements(Comm* c);                    // device copy of Comm.elementsToSend
+// Direct halo delivery for one registered vector (the CG's p): the sender stores straight behind the receiver's
+// local rows, the receiver's SpMV kernel itself waits on the arrival counters before it touches the first row that
+// references a halo column (HaloGate). No acknowledge: the caller guarantees that a new exchange only starts after
+// the previous SpMV has completed on every rank (in CG the two dot-product all-reduces in between do).
+constexpr int kMaxGateSources = 8;
+struct HaloGate {
+  int nsrc = 0;                                            // 0: no gate
+  unsigned long long target = 0;
+  const unsigned long long* flag[kMaxGateSources] = {};
+};
+bool commAttachHaloVector(Comm* c, double* x, uint32_t numRows, bool localOk);   // collective; false -> use commExchangeOnStream
+void commDetachHaloVector(Comm* c);                                  // collective
+HaloGate commHaloPutDirect(Comm* c, const double* x, const int* elements, cudaStream_t s);   // returns the gate to wait on
 
 // ---- side tables keyed by the device array a Matrix struct points to
 struct ScsExt {
+  HaloSplit split;
   uint32_t* colPerm = nullptr;   // symmetric-permuted column ids (CG keeps vectors in permuted order)
   uint32_t* rowLenPerm = nullptr;
   uint32_t* rowLenOrig = nullptr;
@@ -130,6 +156,7 @@ struct ScsExt {
   uint32_t nc = 0;               // columns incl. halo (the reference's SCS struct drops it, matrix-SCS.c:38)
 };
 struct CrsExt {
+  HaloSplit split;
   uint64_t nnzTrue = 0;
   bool ownsArrays = true;
 };

@@ -45,10 +45,27 @@ static bool useLegacyKernels()
 // tmp[k] += val*x of matrix-SCS.c:216-222 (bit-identical row sums).
 // Chunk lengths / offsets of a warp's next 32 chunks live one per lane and are broadcast by shuffle, so the
 // metadata loads are off the critical path.
-template <bool DOT, int WARPS, int J, int S, int U, bool LOCKSTEP>
+// Device-side wait on a HaloGate (sb_internal.h): arrival counters written by the peers' put kernels.
+__device__ __forceinline__ void gateWait(const HaloGate& gate, int who)
+{
+  const unsigned long long* p = gate.flag[who];
+  unsigned long long v;
+  const long long start = clock64();
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    if (v >= gate.target) break;
+    __nanosleep(40);
+    if (clock64() - start > 40000000000ll) __trap();   // dead peer: fail instead of hanging the GPU
+  }
+}
+
+// GATED launches cover all chunks in one go, rotated so that the `nInterior` chunks that reference no halo column
+// come first; before the CTA's first step outside that range it waits for the halo (gateWait) and from then on
+// gathers x with ld.global.cg, because the peers store those values while this kernel is already running.
+template <bool DOT, int WARPS, int J, int S, int U, bool LOCKSTEP, bool GATED>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 spmvSell32TmaKernel(SellView A, const double* __restrict__ x, double* __restrict__ y, uint32_t lo, uint32_t hi,
-    double* partials, unsigned int* ticket, double* dotOut, bool accumulate)
+    double* partials, unsigned int* ticket, double* dotOut, bool accumulate, uint32_t rot, uint32_t nInterior, HaloGate gate)
 {
   extern __shared__ __align__(128) unsigned char ring[];
   __shared__ double scratch[32];
@@ -65,23 +82,32 @@ spmvSell32TmaKernel(SellView A, const double* __restrict__ x, double* __restrict
   }
   __syncwarp();
 
+  // logical chunk l in [0, n) is physical chunk lo + (l + rot) mod n
+  const uint64_t n = (uint64_t)hi - lo;
+  auto phys = [&](uint64_t l) {
+    uint64_t p = l + rot;
+    if (p >= n) p -= n;
+    return p + lo;
+  };
   const uint64_t stride = (uint64_t)gridDim.x * WARPS;
-  const uint64_t first = (uint64_t)lo + (uint64_t)blockIdx.x * WARPS + warp;
+  const uint64_t ctaFirst = (uint64_t)blockIdx.x * WARPS;
+  const uint64_t first = ctaFirst + warp;
   // this warp's t-th chunk is first + t*stride; lane l of a metadata block B holds chunk t = 32*B + l
   auto loadMeta = [&](uint32_t block, uint32_t& lenL, uint32_t& ptrL) {
-    const uint64_t ch = first + ((uint64_t)block * 32 + lane) * stride;
-    lenL = ch < hi ? __ldg(A.chunkLens + ch) : 0u;
-    ptrL = ch < hi ? __ldg(A.chunkPtr + ch) : 0u;
+    const uint64_t l = first + ((uint64_t)block * 32 + lane) * stride;
+    const uint64_t ch = l < n ? phys(l) : 0;
+    lenL = l < n ? __ldg(A.chunkLens + ch) : 0u;
+    ptrL = l < n ? __ldg(A.chunkPtr + ch) : 0u;
   };
 
-  // producer cursor: next slab to request = columns [pj, pj+J) of chunk pc (empty chunks have no slab)
+  // producer cursor: next slab to request = columns [pj, pj+J) of logical chunk pc (empty chunks have no slab)
   uint32_t pLenL, pPtrL, pT = 0;
   loadMeta(0, pLenL, pPtrL);
   uint32_t cLenL = pLenL, cT = 0;
   uint64_t pc = first;
   uint32_t pj = 0, plen = __shfl_sync(kFull, pLenL, 0), pptr = __shfl_sync(kFull, pPtrL, 0);
   auto produce = [&](int s) {
-    while (pc < hi && pj >= plen) {
+    while (pc < n && pj >= plen) {
       pc += stride;
       pj = 0;
       pT++;
@@ -89,7 +115,7 @@ spmvSell32TmaKernel(SellView A, const double* __restrict__ x, double* __restrict
       plen = __shfl_sync(kFull, pLenL, pT & 31u);
       pptr = __shfl_sync(kFull, pPtrL, pT & 31u);
     }
-    if (pc >= hi) return;
+    if (pc >= n) return;
     const uint32_t cols = min((uint32_t)J, plen - pj);
     if (lane == 0) {
       const uint64_t off = (uint64_t)pptr + (uint64_t)pj * 32;
@@ -106,13 +132,21 @@ spmvSell32TmaKernel(SellView A, const double* __restrict__ x, double* __restrict
   int cs = 0;
   uint32_t phases = 0;
   double dotAcc = 0.0;
+  bool gatePassed = false, useCg = false;
   // LOCKSTEP: the CTA's warps advance one chunk each per step and meet at a barrier, so that they keep working on
   // 32*WARPS consecutive rows (one shared window of x in L1) instead of drifting apart
-  const uint64_t ctaFirst = (uint64_t)lo + (uint64_t)blockIdx.x * WARPS;
-  const uint64_t nSteps = ctaFirst < hi ? (hi - ctaFirst + stride - 1) / stride : 0;
+  const uint64_t nSteps = ctaFirst < n ? (n - ctaFirst + stride - 1) / stride : 0;
   for (uint64_t step = 0; step < nSteps; step++, cT++) {
-    const uint64_t chunk = first + step * stride;
-    if (chunk >= hi) {                               // only in the CTA's last step
+    const uint64_t lchunk = first + step * stride;
+    if (GATED) {
+      useCg = ctaFirst + step * stride + WARPS > (uint64_t)nInterior;   // CTA-uniform: some warp is past the interior
+      if (useCg && !gatePassed) {
+        if ((int)threadIdx.x < gate.nsrc) gateWait(gate, threadIdx.x);
+        __syncthreads();
+        gatePassed = true;
+      }
+    }
+    if (lchunk >= n) {                               // only in the CTA's last step
       if (LOCKSTEP) __syncthreads();
       continue;
     }
@@ -121,7 +155,7 @@ spmvSell32TmaKernel(SellView A, const double* __restrict__ x, double* __restrict
       loadMeta(cT >> 5, cLenL, unused);
     }
     const uint32_t len = __shfl_sync(kFull, cLenL, cT & 31u);
-    const uint64_t row = chunk * 32 + lane;
+    const uint64_t row = phys(lchunk) * 32 + lane;
     double xr = 0.0;
     if (DOT && row < A.nr) xr = __ldg(x + row);
     double sum = 0.0;
@@ -135,9 +169,15 @@ spmvSell32TmaKernel(SellView A, const double* __restrict__ x, double* __restrict
       for (uint32_t j = 0; j < (uint32_t)J; j += U) {
         if (j < cols) {                              // warp-uniform
           double xx[U], vv[U];
+          if (GATED && useCg) {
 #pragma unroll
-          for (int u = 0; u < U; u++)
-            if (j + u < cols) xx[u] = __ldg(x + c[(j + u) * 32]);
+            for (int u = 0; u < U; u++)
+              if (j + u < cols) xx[u] = __ldcg(x + c[(j + u) * 32]);
+          } else {
+#pragma unroll
+            for (int u = 0; u < U; u++)
+              if (j + u < cols) xx[u] = __ldg(x + c[(j + u) * 32]);
+          }
 #pragma unroll
           for (int u = 0; u < U; u++)
             if (j + u < cols) vv[u] = v[(j + u) * 32];
@@ -160,43 +200,52 @@ spmvSell32TmaKernel(SellView A, const double* __restrict__ x, double* __restrict
   }
 }
 
-template <int WARPS, int J, int S, int U, bool LOCKSTEP = true>
+struct SellGate {                                     // nullptr-able extra arguments of a gated launch
+  uint32_t rot, nInterior;
+  HaloGate gate;
+};
+
+template <int WARPS, int J, int S, int U, bool LOCKSTEP, bool GATED>
 static void launchSell32TmaCfg(const SellView& A, const double* x, double* y, uint32_t lo, uint32_t hi, const DotArgs* dot,
-    cudaStream_t s)
+    const SellGate* g, cudaStream_t s)
 {
   Context& c = ctx();
   const size_t smem = (size_t)WARPS * S * J * 32 * 12;
   static bool configured = false;
   if (!configured) {
-    allowLargeSmem(spmvSell32TmaKernel<true, WARPS, J, S, U, LOCKSTEP>, smem);
-    allowLargeSmem(spmvSell32TmaKernel<false, WARPS, J, S, U, LOCKSTEP>, smem);
+    allowLargeSmem(spmvSell32TmaKernel<true, WARPS, J, S, U, LOCKSTEP, GATED>, smem);
+    allowLargeSmem(spmvSell32TmaKernel<false, WARPS, J, S, U, LOCKSTEP, GATED>, smem);
     configured = true;
   }
   uint64_t blocks = ((uint64_t)(hi - lo) + WARPS - 1) / WARPS;
   if (blocks > (uint64_t)c.numSMs) blocks = c.numSMs;
+  const uint32_t rot = g ? g->rot : 0u, nInt = g ? g->nInterior : 0u;
+  const HaloGate gate = g ? g->gate : HaloGate();
   if (dot)
-    spmvSell32TmaKernel<true, WARPS, J, S, U, LOCKSTEP><<<(int)blocks, WARPS * 32, smem, s>>>(A, x, y, lo, hi,
-        c.partials + (size_t)dot->slot * kMaxPartials, c.tickets + dot->slot, dot->out, dot->accumulate);
+    spmvSell32TmaKernel<true, WARPS, J, S, U, LOCKSTEP, GATED><<<(int)blocks, WARPS * 32, smem, s>>>(A, x, y, lo, hi,
+        c.partials + (size_t)dot->slot * kMaxPartials, c.tickets + dot->slot, dot->out, dot->accumulate, rot, nInt, gate);
   else
-    spmvSell32TmaKernel<false, WARPS, J, S, U, LOCKSTEP><<<(int)blocks, WARPS * 32, smem, s>>>(A, x, y, lo, hi, nullptr, nullptr,
-        nullptr, false);
+    spmvSell32TmaKernel<false, WARPS, J, S, U, LOCKSTEP, GATED><<<(int)blocks, WARPS * 32, smem, s>>>(A, x, y, lo, hi,
+        nullptr, nullptr, nullptr, false, rot, nInt, gate);
   SB_CUDA(cudaGetLastError());
   countLaunch();
 }
 
 static void launchSell32Tma(const SellView& A, const double* x, double* y, uint32_t lo, uint32_t hi, const DotArgs* dot,
-    cudaStream_t s)
+    const SellGate* g, cudaStream_t s)
 {
+  if (g) {
+    launchSell32TmaCfg<32, 4, 3, 4, true, true>(A, x, y, lo, hi, dot, g, s);
+    return;
+  }
   static const int cfg = envInt("SB_SELL_CFG", 0);   // tuning knob, measured in profiles/
   switch (cfg) {
-  case 1: launchSell32TmaCfg<32, 4, 3, 4, false>(A, x, y, lo, hi, dot, s); break;
-  case 2: launchSell32TmaCfg<32, 4, 4, 4>(A, x, y, lo, hi, dot, s); break;
-  case 3: launchSell32TmaCfg<24, 4, 6, 4>(A, x, y, lo, hi, dot, s); break;
-  case 4: launchSell32TmaCfg<28, 8, 2, 8>(A, x, y, lo, hi, dot, s); break;
-  case 5: launchSell32TmaCfg<16, 16, 2, 16>(A, x, y, lo, hi, dot, s); break;
-  case 6: launchSell32TmaCfg<8, 32, 2, 8>(A, x, y, lo, hi, dot, s); break;
-  case 7: launchSell32TmaCfg<24, 8, 3, 8>(A, x, y, lo, hi, dot, s); break;
-  default: launchSell32TmaCfg<32, 4, 3, 4>(A, x, y, lo, hi, dot, s); break;
+  case 1: launchSell32TmaCfg<32, 4, 3, 4, false, false>(A, x, y, lo, hi, dot, nullptr, s); break;   // free-running warps
+  case 2: launchSell32TmaCfg<32, 4, 4, 4, true, false>(A, x, y, lo, hi, dot, nullptr, s); break;
+  case 3: launchSell32TmaCfg<24, 8, 3, 8, true, false>(A, x, y, lo, hi, dot, nullptr, s); break;
+  case 4: launchSell32TmaCfg<16, 16, 2, 16, true, false>(A, x, y, lo, hi, dot, nullptr, s); break;
+  case 5: launchSell32TmaCfg<8, 32, 2, 8, true, false>(A, x, y, lo, hi, dot, nullptr, s); break;
+  default: launchSell32TmaCfg<32, 4, 3, 4, true, false>(A, x, y, lo, hi, dot, nullptr, s); break;
   }
 }
 
@@ -353,10 +402,14 @@ struct CcrsPipe {                                       // stage: {col, pad, val
   }
 };
 
-template <bool DOT, int LPR, typename L>
+// GATED launches cover all rows in one go as three runs of tiles: the interior rows [intLo, intHi) first, then the
+// rows above and below, which reference halo columns; a consumer warp waits on the gate before its first tile of
+// those (and gathers x with ld.global.cg from there on: the peers store the halo while this kernel is running).
+template <bool DOT, int LPR, typename L, bool GATED>
 __global__ void __launch_bounds__((L::kWarps + 1) * 32, 1)
 spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __restrict__ x, double* __restrict__ y,
-    uint32_t lo, uint32_t hi, uint32_t tileRows, double* partials, unsigned int* ticket, double* dotOut, bool accumulate)
+    uint32_t lo, uint32_t hi, uint32_t tileRows, double* partials, unsigned int* ticket, double* dotOut, bool accumulate,
+    uint32_t intLo, uint32_t intHi, HaloGate gate)
 {
   extern __shared__ __align__(128) unsigned char ring[];
   __shared__ double scratch[32];
@@ -375,7 +428,27 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
   }
   __syncthreads();
 
-  const uint64_t nTiles = ((uint64_t)(hi - lo) + tileRows - 1) / tileRows;
+  // tile t -> rows [r0, r1); returns whether the tile lies behind the gate
+  const uint64_t R = tileRows;
+  const uint64_t s0 = GATED ? intLo : lo, e0 = GATED ? intHi : hi;
+  const uint64_t nt0 = (e0 - s0 + R - 1) / R;
+  const uint64_t nt1 = GATED ? ((uint64_t)hi - intHi + R - 1) / R : 0;
+  const uint64_t nt2 = GATED ? ((uint64_t)intLo - lo + R - 1) / R : 0;
+  const uint64_t nTiles = nt0 + nt1 + nt2;
+  auto tileRange = [&](uint64_t t, uint64_t& r0, uint64_t& r1) {
+    uint64_t base = s0, end = e0;
+    bool gated = false;
+    if (GATED && t >= nt0) {
+      gated = true;
+      t -= nt0;
+      if (t < nt1) { base = intHi; end = hi; }
+      else { t -= nt1; base = lo; end = intLo; }
+    }
+    r0 = base + t * R;
+    r1 = r0 + R < end ? r0 + R : end;
+    return gated;
+  };
+
   double dotAcc = 0.0;
   if (warp == kPipeWarps) {
     // ---- producer: one thread keeps the ring full
@@ -383,8 +456,8 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
       uint32_t i = 0;
       for (uint64_t t = blockIdx.x; t < nTiles; t += gridDim.x, i++) {
         const uint32_t s = i % S, k = i / S;
-        const uint64_t r0 = (uint64_t)lo + t * tileRows;
-        const uint64_t r1 = r0 + tileRows < (uint64_t)hi ? r0 + tileRows : (uint64_t)hi;
+        uint64_t r0, r1;
+        tileRange(t, r0, r1);
         const uint64_t bs = __ldg(rowPtr + r0), be = __ldg(rowPtr + r1);
         const uint64_t a = r0 & ~3ull;
         const uint32_t nrp = (uint32_t)((r1 + 1 - a + 3) & ~3ull);
@@ -399,12 +472,18 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
   } else {
     // ---- consumers
     const int sub = lane % LPR, grp = lane / LPR;
+    bool gatePassed = false;
     uint32_t i = 0;
     for (uint64_t t = blockIdx.x; t < nTiles; t += gridDim.x, i++) {
       const uint32_t s = i % S, k = i / S;
-      const uint64_t r0 = (uint64_t)lo + t * tileRows;
-      const uint64_t r1 = r0 + tileRows < (uint64_t)hi ? r0 + tileRows : (uint64_t)hi;
+      uint64_t r0, r1;
+      const bool useCg = tileRange(t, r0, r1);
       const uint32_t nrows = (uint32_t)(r1 - r0);
+      if (GATED && useCg && !gatePassed) {
+        if (lane < gate.nsrc) gateWait(gate, lane);
+        __syncwarp();
+        gatePassed = true;
+      }
       mbarWait(fullBar + s, k & 1u);
       const unsigned char* st = ring + (size_t)s * L::kBytes;
       const uint32_t* rp = reinterpret_cast<const uint32_t*>(st + L::kRpOff) + (uint32_t)(r0 & 3ull);
@@ -425,9 +504,15 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
 #pragma unroll
             for (int u = 0; u < UN; u++)
               if (idx + u * LPR < end) L::fetch(st, idx + u * LPR, cc[u], vv[u]);
+            if (GATED && useCg) {
 #pragma unroll
-            for (int u = 0; u < UN; u++)
-              if (idx + u * LPR < end) xx[u] = __ldg(x + cc[u]);
+              for (int u = 0; u < UN; u++)
+                if (idx + u * LPR < end) xx[u] = __ldcg(x + cc[u]);
+            } else {
+#pragma unroll
+              for (int u = 0; u < UN; u++)
+                if (idx + u * LPR < end) xx[u] = __ldg(x + cc[u]);
+            }
 #pragma unroll
             for (int u = 0; u < UN; u++)
               if (idx + u * LPR < end) sum = mulAdd(sum, vv[u], xx[u]);
@@ -438,7 +523,7 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
             uint32_t c;
             double v;
             acc.fetchGlobal(j, c, v);
-            sum = mulAdd(sum, v, __ldg(x + c));
+            sum = mulAdd(sum, v, (GATED && useCg) ? __ldcg(x + c) : __ldg(x + c));
           }
         }
 #pragma unroll
@@ -458,27 +543,34 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
   }
 }
 
-template <int LPR, typename L>
+struct RowsGate {                                     // extra arguments of a gated launch
+  uint32_t intLo, intHi;
+  HaloGate gate;
+};
+
+template <int LPR, typename L, bool GATED>
 static void launchRowsPipe(L acc, const uint32_t* rowPtr, const double* x, double* y, uint32_t lo, uint32_t hi,
-    uint32_t tileRows, const DotArgs* dot, cudaStream_t s)
+    uint32_t tileRows, const DotArgs* dot, const RowsGate* g, cudaStream_t s)
 {
   Context& c = ctx();
   const size_t smem = (size_t)L::kStages * L::kBytes;
   static bool configured = false;
   if (!configured) {
-    allowLargeSmem(spmvRowsPipeKernel<true, LPR, L>, smem);
-    allowLargeSmem(spmvRowsPipeKernel<false, LPR, L>, smem);
+    allowLargeSmem(spmvRowsPipeKernel<true, LPR, L, GATED>, smem);
+    allowLargeSmem(spmvRowsPipeKernel<false, LPR, L, GATED>, smem);
     configured = true;
   }
-  uint64_t blocks = ((uint64_t)(hi - lo) + tileRows - 1) / tileRows;
+  uint64_t blocks = ((uint64_t)(hi - lo) + tileRows - 1) / tileRows + (GATED ? 2 : 0);
   if (blocks > (uint64_t)c.numSMs) blocks = c.numSMs;
   const int threads = (L::kWarps + 1) * 32;
+  const uint32_t intLo = g ? g->intLo : 0u, intHi = g ? g->intHi : 0u;
+  const HaloGate gate = g ? g->gate : HaloGate();
   if (dot)
-    spmvRowsPipeKernel<true, LPR, L><<<(int)blocks, threads, smem, s>>>(acc, rowPtr, x, y, lo, hi, tileRows,
-        c.partials + (size_t)dot->slot * kMaxPartials, c.tickets + dot->slot, dot->out, dot->accumulate);
+    spmvRowsPipeKernel<true, LPR, L, GATED><<<(int)blocks, threads, smem, s>>>(acc, rowPtr, x, y, lo, hi, tileRows,
+        c.partials + (size_t)dot->slot * kMaxPartials, c.tickets + dot->slot, dot->out, dot->accumulate, intLo, intHi, gate);
   else
-    spmvRowsPipeKernel<false, LPR, L><<<(int)blocks, threads, smem, s>>>(acc, rowPtr, x, y, lo, hi, tileRows, nullptr,
-        nullptr, nullptr, false);
+    spmvRowsPipeKernel<false, LPR, L, GATED><<<(int)blocks, threads, smem, s>>>(acc, rowPtr, x, y, lo, hi, tileRows, nullptr,
+        nullptr, nullptr, false, intLo, intHi, gate);
   SB_CUDA(cudaGetLastError());
   countLaunch();
 }
@@ -584,7 +676,7 @@ static void launchRows(Access acc, const uint32_t* rowPtr, uint32_t nr, const do
 // CRS and CCRS take the same decisions (same CAP), so their row sums are bit-identical to each other.
 template <typename Access, typename P>
 static bool tryRowsPipe(Access acc, const uint32_t* rowPtr, double avg, const double* x, double* y, uint32_t lo, uint32_t hi,
-    const DotArgs* dot, cudaStream_t s)
+    const DotArgs* dot, const RowsGate* g, bool probeOnly, cudaStream_t s)
 {
   // every pipe layout has CAP / WARPS = 224 non-zeros per consumer warp and pass: lanes per row = avg / 7
   const int lpr = avg <= 7.0 ? 1 : avg <= 14.0 ? 2 : avg <= 28.0 ? 4 : avg <= 56.0 ? 8 : avg <= 112.0 ? 16 : 32;
@@ -593,15 +685,35 @@ static bool tryRowsPipe(Access acc, const uint32_t* rowPtr, double avg, const do
   uint32_t tileRows = (fitRows / rowsPerPass) * rowsPerPass;
   if (tileRows > kPipeMaxRows) tileRows = (kPipeMaxRows / rowsPerPass) * rowsPerPass;
   if (tileRows < rowsPerPass) return false;
+  if (probeOnly) return true;
+#define SB_PIPE(LPRV)                                                                                            \
+  do {                                                                                                           \
+    if (g) launchRowsPipe<LPRV, P, true>(acc.template pipe<P>(), rowPtr, x, y, lo, hi, tileRows, dot, g, s);     \
+    else launchRowsPipe<LPRV, P, false>(acc.template pipe<P>(), rowPtr, x, y, lo, hi, tileRows, dot, nullptr, s); \
+  } while (0)
   switch (lpr) {
-  case 1: launchRowsPipe<1>(acc.template pipe<P>(), rowPtr, x, y, lo, hi, tileRows, dot, s); break;
-  case 2: launchRowsPipe<2>(acc.template pipe<P>(), rowPtr, x, y, lo, hi, tileRows, dot, s); break;
-  case 4: launchRowsPipe<4>(acc.template pipe<P>(), rowPtr, x, y, lo, hi, tileRows, dot, s); break;
-  case 8: launchRowsPipe<8>(acc.template pipe<P>(), rowPtr, x, y, lo, hi, tileRows, dot, s); break;
-  case 16: launchRowsPipe<16>(acc.template pipe<P>(), rowPtr, x, y, lo, hi, tileRows, dot, s); break;
-  default: launchRowsPipe<32>(acc.template pipe<P>(), rowPtr, x, y, lo, hi, tileRows, dot, s); break;
+  case 1: SB_PIPE(1); break;
+  case 2: SB_PIPE(2); break;
+  case 4: SB_PIPE(4); break;
+  case 8: SB_PIPE(8); break;
+  case 16: SB_PIPE(16); break;
+  default: SB_PIPE(32); break;
   }
+#undef SB_PIPE
   return true;
+}
+
+// returns false if the pipelined kernel cannot take this matrix (rows too long for a stage)
+template <typename Access>
+static bool launchRowsPipeAuto(Access acc, const uint32_t* rowPtr, uint32_t nr, uint64_t nnz, const double* x, double* y,
+    uint32_t lo, uint32_t hi, const DotArgs* dot, const RowsGate* g, bool probeOnly, cudaStream_t s)
+{
+  const double avg = nr ? (double)nnz / (double)nr : 0.0;
+  if (useLegacyKernels()) return false;
+  static const int cfg = envInt("SB_ROWS_CFG", Access::kDefaultCfg);   // tuning knob, measured in profiles/
+  if (cfg == 1)
+    return tryRowsPipe<Access, typename Access::template Pipe<16, 3584, Access::kStagesFor3584>>(acc, rowPtr, avg, x, y, lo, hi, dot, g, probeOnly, s);
+  return tryRowsPipe<Access, typename Access::template Pipe<23, 5376, Access::kStagesFor5376>>(acc, rowPtr, avg, x, y, lo, hi, dot, g, probeOnly, s);
 }
 
 template <typename Access>
@@ -609,15 +721,7 @@ static void launchRowsAuto(Access acc, const uint32_t* rowPtr, uint32_t nr, uint
     uint32_t lo, uint32_t hi, const DotArgs* dot, cudaStream_t s)
 {
   const double avg = nr ? (double)nnz / (double)nr : 0.0;
-  if (!useLegacyKernels()) {
-    static const int cfg = envInt("SB_ROWS_CFG", Access::kDefaultCfg);   // tuning knob, measured in profiles/
-    bool done;
-    if (cfg == 1)
-      done = tryRowsPipe<Access, typename Access::template Pipe<16, 3584, Access::kStagesFor3584>>(acc, rowPtr, avg, x, y, lo, hi, dot, s);
-    else
-      done = tryRowsPipe<Access, typename Access::template Pipe<23, 5376, Access::kStagesFor5376>>(acc, rowPtr, avg, x, y, lo, hi, dot, s);
-    if (done) return;
-  }
+  if (launchRowsPipeAuto(acc, rowPtr, nr, nnz, x, y, lo, hi, dot, nullptr, false, s)) return;
   if (avg <= 6.0) launchRows<2, Access>(acc, rowPtr, nr, x, y, lo, hi, dot, s);
   else if (avg <= 12.0) launchRows<4, Access>(acc, rowPtr, nr, x, y, lo, hi, dot, s);
   else if (avg <= 40.0) launchRows<8, Access>(acc, rowPtr, nr, x, y, lo, hi, dot, s);
@@ -627,22 +731,25 @@ static void launchRowsAuto(Access acc, const uint32_t* rowPtr, uint32_t nr, uint
 
 uint32_t spmvUnits(const Operator& A) { return A.fmt == SB_FMT_SCS ? A.sell.nChunks : A.nr; }
 
-// ---- interior / boundary split for the overlapped halo exchange (setup, once per solver)
-// bounds[0] = max(u+1) over halo-touching units u below the middle, bounds[1] = min(u) over those at or above it
+// ---- interior / boundary split for the overlapped halo exchange (setup: once per converted matrix)
+// one warp per unit; bounds[0] = max(u+1) over halo-touching units u below the middle, bounds[1] = min(u) over
+// those at or above it
 __global__ void haloTouchKernel(Operator A, uint32_t units, uint32_t* bounds)
 {
   const uint32_t mid = units / 2;
-  for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < units; u += gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warpsTotal = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < units; u += warpsTotal) {
     bool touch = false;
     if (A.fmt == SB_FMT_SCS) {
       const uint64_t b = A.sell.chunkPtr[u], e = b + (uint64_t)A.sell.chunkLens[u] * A.sell.C;
-      for (uint64_t j = b; j < e && !touch; j++) touch = A.sell.col[j] >= A.nr;
+      for (uint64_t j = b + lane; j < e; j += 32) touch |= A.sell.col[j] >= A.nr;
     } else if (A.fmt == SB_FMT_CRS) {
-      for (uint32_t j = A.crs.rowPtr[u]; j < A.crs.rowPtr[u + 1] && !touch; j++) touch = A.crs.col[j] >= A.nr;
+      for (uint32_t j = A.crs.rowPtr[u] + lane; j < A.crs.rowPtr[u + 1]; j += 32) touch |= A.crs.col[j] >= A.nr;
     } else {
-      for (uint32_t j = A.ccrs.rowPtr[u]; j < A.ccrs.rowPtr[u + 1] && !touch; j++) touch = A.ccrs.entries[j].col >= A.nr;
+      for (uint32_t j = A.ccrs.rowPtr[u] + lane; j < A.ccrs.rowPtr[u + 1]; j += 32) touch |= A.ccrs.entries[j].col >= A.nr;
     }
-    if (touch) {
+    if (__any_sync(0xffffffffu, touch) && lane == 0) {
       if (u < mid) atomicMax(bounds, u + 1);
       else atomicMin(bounds + 1, u);
     }
@@ -651,13 +758,17 @@ __global__ void haloTouchKernel(Operator A, uint32_t units, uint32_t* bounds)
 
 void spmvInteriorUnits(const Operator& A, uint32_t* lo, uint32_t* hi, cudaStream_t s)
 {
+  if (A.split && A.split->valid) {
+    *lo = A.split->lo;
+    *hi = A.split->hi;
+    return;
+  }
   const uint32_t units = spmvUnits(A);
   uint32_t h[2] = { 0u, units };
   if (units > 0) {
     uint32_t* d = (uint32_t*)allocate(64, 2 * sizeof(uint32_t));
     SB_CUDA(cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, s));
-    const int blocks = (int)(((uint64_t)units + 127) / 128 < (uint64_t)ctx().numSMs * 16 ? ((uint64_t)units + 127) / 128 : (uint64_t)ctx().numSMs * 16);
-    haloTouchKernel<<<blocks, 128, 0, s>>>(A, units, d);
+    haloTouchKernel<<<ctx().numSMs * 8, 256, 0, s>>>(A, units, d);
     SB_CUDA(cudaGetLastError());
     countLaunch();
     SB_CUDA(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, s));
@@ -666,6 +777,11 @@ void spmvInteriorUnits(const Operator& A, uint32_t* lo, uint32_t* hi, cudaStream
   }
   *lo = h[0];
   *hi = h[1] > h[0] ? h[1] : h[0];
+  if (A.split) {
+    A.split->valid = true;
+    A.split->lo = *lo;
+    A.split->hi = *hi;
+  }
 }
 
 void launchSpmv(const Operator& A, const double* x, double* y, uint32_t lo, uint32_t hi, const DotArgs* dot,
@@ -688,7 +804,7 @@ void launchSpmv(const Operator& A, const double* x, double* y, uint32_t lo, uint
     SB_CUDA(cudaGetLastError());
     countLaunch();
   } else if (A.fmt == SB_FMT_SCS && !useLegacyKernels()) {
-    launchSell32Tma(A.sell, x, y, lo, hi, dot, s);
+    launchSell32Tma(A.sell, x, y, lo, hi, dot, nullptr, s);
   } else if (A.fmt == SB_FMT_SCS) {
     uint64_t blocks = ((uint64_t)(hi - lo) + 7) / 8;
     const uint64_t cap = (uint64_t)c.numSMs * 4;
@@ -704,6 +820,38 @@ void launchSpmv(const Operator& A, const double* x, double* y, uint32_t lo, uint
     launchRowsAuto(CrsAccess { A.crs.col, A.crs.val }, A.crs.rowPtr, A.nr, A.nnzTrue, x, y, lo, hi, dot, s);
   } else {
     launchRowsAuto(CcrsAccess { A.ccrs.entries }, A.ccrs.rowPtr, A.nr, A.nnzTrue, x, y, lo, hi, dot, s);
+  }
+}
+
+bool spmvGatedAvailable(const Operator& A)
+{
+  if (useLegacyKernels()) return false;
+  if (A.fmt == SB_FMT_SCS) return A.sell.C == 32;
+  if (A.fmt == SB_FMT_CRS)
+    return launchRowsPipeAuto(CrsAccess { A.crs.col, A.crs.val }, A.crs.rowPtr, A.nr, A.nnzTrue, nullptr, nullptr, 0, A.nr, nullptr, nullptr, true, nullptr);
+  return launchRowsPipeAuto(CcrsAccess { A.ccrs.entries }, A.ccrs.rowPtr, A.nr, A.nnzTrue, nullptr, nullptr, 0, A.nr, nullptr, nullptr, true, nullptr);
+}
+
+void launchSpmvGated(const Operator& A, const double* x, double* y, uint32_t intLo, uint32_t intHi, const HaloGate& gate,
+    const DotArgs* dot, cudaStream_t s)
+{
+  const uint32_t units = spmvUnits(A);
+  if (units == 0) {
+    if (dot && !dot->accumulate) SB_CUDA(cudaMemsetAsync(dot->out, 0, sizeof(double), s));
+    return;
+  }
+  if (intHi < intLo) intHi = intLo;
+  if (A.fmt == SB_FMT_SCS) {
+    SellGate g { intLo, intHi - intLo, gate };       // rotate so that the interior chunks come first
+    launchSell32Tma(A.sell, x, y, 0, units, dot, &g, s);
+  } else {
+    RowsGate g { intLo, intHi, gate };
+    bool ok;
+    if (A.fmt == SB_FMT_CRS)
+      ok = launchRowsPipeAuto(CrsAccess { A.crs.col, A.crs.val }, A.crs.rowPtr, A.nr, A.nnzTrue, x, y, 0, A.nr, dot, &g, false, s);
+    else
+      ok = launchRowsPipeAuto(CcrsAccess { A.ccrs.entries }, A.ccrs.rowPtr, A.nr, A.nnzTrue, x, y, 0, A.nr, dot, &g, false, s);
+    if (!ok) SB_FATAL("launchSpmvGated: no pipelined kernel for this matrix (check spmvGatedAvailable first)");
   }
 }
 
