@@ -35,6 +35,11 @@ WORKLOADS = {
     "sell128": (128, 128, 128, "SCS", 32, 256, "HPCG 27-pt stencil 128^3 per GPU, SELL-C-sigma (C=32, sigma=256), fp64 CG"),
     "ccrs128": (128, 128, 128, "CCRS", 0, 0, "HPCG 27-pt stencil 128^3 per GPU, CCRS, fp64 CG"),
     "sell64": (64, 64, 64, "SCS", 32, 256, "HPCG 27-pt stencil 64^3 per GPU, SELL-C-sigma (C=32, sigma=256), fp64 CG (smoke size)"),
+    # BASELINE.json configs[4]: 512^3 GLOBAL problem split over the ranks (strong scaling), three formats
+    "strong512sell": (512, 512, -512, "SCS", 32, 256, "HPCG 27-pt stencil 512^3 global (strong scaling), SELL-C-sigma (C=32, sigma=256), fp64 CG"),
+    "strong512crs": (512, 512, -512, "CRS", 0, 0, "HPCG 27-pt stencil 512^3 global (strong scaling), CRS, fp64 CG"),
+    "strong512ccrs": (512, 512, -512, "CCRS", 0, 0, "HPCG 27-pt stencil 512^3 global (strong scaling), CCRS, fp64 CG"),
+    "strong256sell": (256, 256, -256, "SCS", 32, 256, "HPCG 27-pt stencil 256^3 global (strong scaling), SELL-C-sigma (C=32, sigma=256), fp64 CG"),
 }
 
 
@@ -129,8 +134,9 @@ def reference_arm(args, nx, ny, nz, desc, world):
     in the CGSolver.c:94-128 order so that exactly K iterations are timed after W warm-up iterations."""
     from oracle import ref
     kind = "reference"
-    threads = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    # all host cores; torchrun exports OMP_NUM_THREADS=1 to its workers, which is not what this arm measures
+    threads = int(os.environ.get("SB_REF_THREADS", "0")) or (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(threads)
     os.environ.setdefault("OMP_PROC_BIND", "close")
     os.environ.setdefault("OMP_PLACES", "cores")
     if not ref.available("CRS_fast"):
@@ -196,6 +202,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     nx, ny, nz, fmt, Cc, sigma, desc = WORKLOADS[args.workload]
+    scaling = "weak"
+    if nz < 0:                       # negative: global z extent, divided over the ranks
+        scaling = "strong"
+        if (-nz) % world:
+            raise SystemExit("workload %s needs a rank count that divides %d" % (args.workload, -nz))
+        nz = (-nz) // world
     K, W = args.steps, args.warmup
     metric, unit = "cg_gflops", "GFLOP/s"
     # flops of one CG iteration over the whole job (all ranks): 2 per stored non-zero + 10 per row
@@ -210,7 +222,7 @@ def main():
             return 0
         gf = r["value"] * flops_it_job / 1e9
         line = {"impl": "reference", "metric": metric, "value": gf, "unit": unit, "n_gpus": args.gpus, "steps": K,
-                "warmup": W, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "warmup": W, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": scaling,
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": desc, "nx": nx, "ny": ny, "nz_per_gpu": nz, "format": "CRS (reference CPU build)"},
                 "cpu_baseline": {"value": gf, "unit": unit, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
@@ -403,7 +415,7 @@ def main():
     if rank == 0:
         line = {
             "metric": metric, "value": value * 1.0, "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": desc, "nx": nx, "ny": ny, "nz_per_gpu": nz, "format": fmt, "C": Cc, "sigma": sigma,
                        "rows_per_gpu": N, "nnz_rank0": nnz, "parallelism": "row-block x%d" % world,

@@ -61,6 +61,26 @@ using namespace sb;
 
 extern "C" {
 
+// cudaMalloc / cudaFree synchronise the device and cost up to milliseconds each; a solver allocates and releases
+// the same nine vectors per solve (CGSolver.c:69-79 never frees, a library must). Released blocks are therefore
+// parked in a small exact-size cache and handed out again (contents undefined, exactly like fresh cudaMalloc memory).
+static std::mutex g_poolMutex;
+static std::unordered_map<void*, size_t> g_blockSize;               // every live or parked block
+static std::unordered_multimap<size_t, void*> g_parked;
+static size_t g_parkedBytes = 0;
+constexpr size_t kParkLimitBytes = (size_t)8 << 30;                 // total
+constexpr size_t kParkMaxBlock = (size_t)2 << 30;                   // per block
+
+static void releaseParked()
+{
+  for (auto& kv : g_parked) {
+    cudaFree(kv.second);
+    g_blockSize.erase(kv.second);
+  }
+  g_parked.clear();
+  g_parkedBytes = 0;
+}
+
 void* allocate(size_t alignment, size_t bytesize)
 {
   // cudaMalloc returns >= 256-byte aligned blocks; the reference only ever asks for 64 (ARRAY_ALIGNMENT).
@@ -70,32 +90,90 @@ void* allocate(size_t alignment, size_t bytesize)
   }
   if (alignment > 256) SB_FATAL("allocate: alignment %zu > 256 not supported on the device", alignment);
   ctx();
+  const size_t bytes = ((bytesize ? bytesize : 1) + 255) & ~(size_t)255;
+  std::lock_guard<std::mutex> lock(g_poolMutex);
+  auto it = g_parked.find(bytes);
+  if (it != g_parked.end()) {
+    void* p = it->second;
+    g_parked.erase(it);
+    g_parkedBytes -= bytes;
+    return p;
+  }
   void* p = nullptr;
-  cudaError_t e = cudaMalloc(&p, bytesize ? bytesize : 1);
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {                  // make room: give the parked blocks back first
+    cudaGetLastError();
+    releaseParked();
+    e = cudaMalloc(&p, bytes);
+  }
   if (e != cudaSuccess || p == nullptr) {
     fprintf(stderr, "Error: Insufficient memory to fulfill the request (%zu bytes on device: %s)\n", bytesize,
         cudaGetErrorString(e));
     exit(EXIT_FAILURE);
   }
+  g_blockSize[p] = bytes;
   return p;
 }
 
 void sbFree(void* p)
 {
-  if (p) SB_CUDA(cudaFree(p));
+  if (!p) return;
+  std::lock_guard<std::mutex> lock(g_poolMutex);
+  auto it = g_blockSize.find(p);
+  if (it == g_blockSize.end()) {           // not ours (or already released): plain free
+    SB_CUDA(cudaFree(p));
+    return;
+  }
+  const size_t bytes = it->second;
+  if (bytes <= kParkMaxBlock && g_parkedBytes + bytes <= kParkLimitBytes) {
+    // work queued on the stream may still use the block: it may only be reused once that work has drained
+    SB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    g_parked.emplace(bytes, p);
+    g_parkedBytes += bytes;
+    return;
+  }
+  g_blockSize.erase(it);
+  SB_CUDA(cudaFree(p));
 }
+
+// pinned host memory; small blocks (the solver's scalar mirror) are parked like device blocks
+static std::unordered_map<void*, size_t> g_hostSize;
+static std::unordered_multimap<size_t, void*> g_hostParked;
+constexpr size_t kHostParkMaxBlock = (size_t)1 << 20;
 
 void* sbAllocateHost(size_t bytesize)
 {
   ctx();
+  const size_t bytes = ((bytesize ? bytesize : 1) + 4095) & ~(size_t)4095;
+  {
+    std::lock_guard<std::mutex> lock(g_poolMutex);
+    auto it = g_hostParked.find(bytes);
+    if (it != g_hostParked.end()) {
+      void* p = it->second;
+      g_hostParked.erase(it);
+      return p;
+    }
+  }
   void* p = nullptr;
-  SB_CUDA(cudaMallocHost(&p, bytesize ? bytesize : 1));
+  SB_CUDA(cudaMallocHost(&p, bytes));
+  std::lock_guard<std::mutex> lock(g_poolMutex);
+  g_hostSize[p] = bytes;
   return p;
 }
 
 void sbFreeHost(void* p)
 {
-  if (p) SB_CUDA(cudaFreeHost(p));
+  if (!p) return;
+  {
+    std::lock_guard<std::mutex> lock(g_poolMutex);
+    auto it = g_hostSize.find(p);
+    if (it != g_hostSize.end() && it->second <= kHostParkMaxBlock && g_hostParked.size() < 64) {
+      g_hostParked.emplace(it->second, p);
+      return;
+    }
+    if (it != g_hostSize.end()) g_hostSize.erase(it);
+  }
+  SB_CUDA(cudaFreeHost(p));
 }
 
 void sbCopyToDevice(void* dev, const void* host, size_t bytes)

@@ -36,7 +36,7 @@ def main():
     L.commInit(C.byref(comm), 0, None)           # reads RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* (comm.h:48)
     assert (comm.rank, comm.size) == (rank, world)
     failures = []
-    cases = [(8, 8, 4, 10, 0.0), (16, 16, 6, 60, 1e-6), (12, 10, 3, 30, 1e-3), (32, 32, 8, 40, 0.0)]
+    cases = [(6, 5, 1, 8, 0.0), (8, 8, 4, 10, 0.0), (16, 16, 6, 60, 1e-6), (12, 10, 3, 30, 1e-3), (32, 32, 8, 40, 0.0)]
     fmts = [(api.FMT_CRS, 0), (api.FMT_SCS, 1), (api.FMT_SCS, 256), (api.FMT_CCRS, 0)]
     for (nx, ny, nz, itermax, eps) in cases:
         # oracle: global problem on one rank + the reference's partition lists for every rank
