@@ -163,6 +163,10 @@ void matrixGenerate(GMatrix* m, Parameter* p, int rank, int size, bool use_7pt_s
 /* same matrix, generated directly in device memory (rowPtr/entries are device pointers) */
 void sbGenerateDevice(GMatrix* m, Parameter* p, int rank, int size, bool use_7pt_stencil);
 void sbFreeGMatrix(GMatrix* m);                      /* releases host or device arrays of a GMatrix */
+/* matrix.h:50-51 / matrix.c:123-269 -- MatrixMarket coordinate files (real/integer/pattern, general/symmetric);
+ * host arrays, sorted by row then column exactly like the reference (stable sorts) */
+void MMMatrixRead(MMMatrix* m, char* filename);
+void matrixConvertfromMM(MMMatrix* mm, GMatrix* m);
 
 /* ---------------------------------------------------------------- format plugins */
 /* matrix.h:57 convertMatrix / solver.h:13 spMVM, one pair per format. `im` may hold host or device arrays. */
@@ -223,7 +227,7 @@ void commPartition(Comm* c, GMatrix* m);                                      /*
 void commExchange(Comm* c, CG_UINT numRows, CG_FLOAT* x);                     /* comm.h:57, comm.c:627-651 */
 void commReduction(CG_FLOAT* v, int op);                                      /* comm.h:58, comm.c:653-662 (host scalar) */
 void sbCommAllreduceDevice(Comm* c, CG_FLOAT* dev, int count, int op);        /* the same reduction on device scalars, asynchronous */
-void commDistributeMatrix(Comm* c, MMMatrix* m, MMMatrix* mLocal);            /* comm.h:50, comm.c:311-412 (single rank) */
+void commDistributeMatrix(Comm* c, MMMatrix* m, MMMatrix* mLocal);            /* comm.h:50, comm.c:311-412 */
 /* bootstrap pieces used when another launcher (torchrun) already owns the rendezvous */
 int sbCommUniqueIdBytes(void);
 void sbCommGetUniqueId(void* id);

@@ -41,6 +41,11 @@ class CCRSMatrix(C.Structure):
 MATRIX_TYPES = {FMT_CRS: CRSMatrix, FMT_SCS: SCSMatrix, FMT_CCRS: CCRSMatrix}
 
 
+class MMMatrix(C.Structure):                     # matrix.h:43-49
+    _fields_ = [("count", C.c_size_t), ("nr", C.c_int), ("nnz", C.c_int), ("totalNr", C.c_int), ("totalNnz", C.c_int),
+                ("startRow", C.c_int), ("stopRow", C.c_int), ("entries", C.c_void_p)]
+
+
 class Parameter(C.Structure):
     _fields_ = [("filename", C.c_char_p), ("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("itermax", C.c_int),
                 ("eps", C.c_double)]
@@ -98,6 +103,9 @@ def lib():
         L.matrixGenerate.argtypes = [C.POINTER(GMatrix), C.POINTER(Parameter), C.c_int, C.c_int, C.c_bool]
         L.sbGenerateDevice.argtypes = [C.POINTER(GMatrix), C.POINTER(Parameter), C.c_int, C.c_int, C.c_bool]
         L.sbFreeGMatrix.argtypes = [C.POINTER(GMatrix)]
+        L.MMMatrixRead.argtypes = [C.POINTER(MMMatrix), C.c_char_p]
+        L.matrixConvertfromMM.argtypes = [C.POINTER(MMMatrix), C.POINTER(GMatrix)]
+        L.commDistributeMatrix.argtypes = [C.POINTER(Comm), C.POINTER(MMMatrix), C.POINTER(MMMatrix)]
         for f in ("CRS", "SCS", "CCRS"):
             getattr(L, "sb%s_convertMatrix" % f).argtypes = [C.c_void_p, C.POINTER(GMatrix)]
             getattr(L, "sb%s_spMVM" % f).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -202,6 +210,22 @@ def matrixGenerate(nx, ny, nz, rank=0, size=1, use7pt=False, device=False):
     else:
         lib().matrixGenerate(C.byref(g), C.byref(p), rank, size, use7pt)
     g._device = device
+    return g
+
+
+def matrixRead(filename, comm=None):
+    """main.c:64-71: MMMatrixRead on the master, commDistributeMatrix, matrixConvertfromMM -> host GMatrix of this rank."""
+    L = lib()
+    if comm is None:
+        comm = Comm()
+        comm.rank, comm.size = 0, 1
+    mm, local = MMMatrix(), MMMatrix()
+    if comm.rank == 0:
+        L.MMMatrixRead(C.byref(mm), filename.encode())
+    L.commDistributeMatrix(C.byref(comm), C.byref(mm), C.byref(local))
+    g = GMatrix()
+    L.matrixConvertfromMM(C.byref(local), C.byref(g))
+    g._device = False
     return g
 
 

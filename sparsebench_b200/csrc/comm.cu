@@ -756,15 +756,81 @@ void commExchange(Comm* c, CG_UINT numRows, CG_FLOAT* x) { commExchangeOnStream(
 
 void commDistributeMatrix(Comm* c, MMMatrix* m, MMMatrix* mLocal)
 {
-  if (c->size > 1) SB_FATAL("commDistributeMatrix: MatrixMarket scatter over ranks is outside this package's hot path (SURVEY 8f row 2)");
-  mLocal->startRow = 0;                    // comm.c:404-410
-  mLocal->stopRow = m->nr - 1;
-  mLocal->count = m->count;
-  mLocal->nr = m->nr;
-  mLocal->nnz = m->nnz;
-  mLocal->entries = m->entries;
-  mLocal->totalNr = m->nr;                 // left unset by the reference's single-rank branch
-  mLocal->totalNnz = m->nnz;
+  CommExt* e = ext(c);
+  if (c->size <= 1 || !e) {
+    mLocal->startRow = 0;                  // comm.c:404-410
+    mLocal->stopRow = m->nr - 1;
+    mLocal->count = m->count;
+    mLocal->nr = m->nr;
+    mLocal->nnz = m->nnz;
+    mLocal->entries = m->entries;
+    mLocal->totalNr = m->nr;               // left unset by the reference's single-rank branch
+    mLocal->totalNnz = m->nnz;
+    return;
+  }
+  // comm.c:311-402: rank 0 holds the sorted entry list and scatters contiguous row blocks of
+  // N/size (+1 for the first N%size ranks) rows (sizeOfRank, comm.c:35-38). Setup-time transfer through NCCL.
+  Context& cx = ctx();
+  const int size = c->size, rank = c->rank;
+  std::vector<int> table((size_t)2 * size + 2, 0);         // totals, then (count, displ) per rank
+  if (rank == 0) {
+    table[0] = m->nr;
+    table[1] = m->nnz;
+    int cursor = 0;
+    size_t at = 0;
+    for (int i = 0; i < size; i++) {
+      const int numRows = m->nr / size + ((m->nr % size > i) ? 1 : 0);
+      const int stopRow = cursor + numRows - 1;
+      cursor += numRows;
+      const size_t begin = at;                              // scanMM (comm.c:276-296) for rows that all hold entries
+      while (at < m->count && m->entries[at].row <= stopRow) at++;
+      table[(size_t)2 + 2 * i] = (int)(at - begin);
+      table[(size_t)3 + 2 * i] = (int)begin;
+      printf("Rank %d count %d displ %d start %d stop %d\n", i, (int)(at - begin), (int)begin, stopRow - numRows + 1, stopRow);
+    }
+  }
+  int* dTable = (int*)allocate(64, sizeof(int) * table.size());
+  if (rank == 0) SB_CUDA(cudaMemcpyAsync(dTable, table.data(), sizeof(int) * table.size(), cudaMemcpyHostToDevice, cx.stream));
+  SB_NCCL(ncclBroadcast(dTable, dTable, table.size(), ncclInt32, 0, e->nccl, cx.stream));
+  SB_CUDA(cudaMemcpyAsync(table.data(), dTable, sizeof(int) * table.size(), cudaMemcpyDeviceToHost, cx.stream));
+  SB_CUDA(cudaStreamSynchronize(cx.stream));
+  sbFree(dTable);
+  const int count = table[(size_t)2 + 2 * rank];
+  mLocal->count = (size_t)count;
+  mLocal->totalNr = table[0];
+  mLocal->totalNnz = table[1];
+  void* host = nullptr;
+  if (posix_memalign(&host, 64, sizeof(MMEntry) * (size_t)(count ? count : 1)) != 0) SB_FATAL("commDistributeMatrix: out of host memory");
+  mLocal->entries = (MMEntry*)host;
+  // MPI_Scatterv (comm.c:373-381)
+  const size_t allBytes = rank == 0 ? sizeof(MMEntry) * m->count : 0;
+  char* dAll = rank == 0 ? (char*)allocate(64, allBytes) : nullptr;
+  char* dMine = (char*)allocate(64, sizeof(MMEntry) * (size_t)(count ? count : 1));
+  if (rank == 0) SB_CUDA(cudaMemcpyAsync(dAll, m->entries, allBytes, cudaMemcpyHostToDevice, cx.stream));
+  SB_NCCL(ncclGroupStart());
+  if (rank == 0)
+    for (int i = 1; i < size; i++) {
+      const size_t cnt = (size_t)table[(size_t)2 + 2 * i], off = (size_t)table[(size_t)3 + 2 * i];
+      if (cnt) SB_NCCL(ncclSend(dAll + off * sizeof(MMEntry), cnt * sizeof(MMEntry), ncclChar, i, e->nccl, cx.stream));
+    }
+  else if (count)
+    SB_NCCL(ncclRecv(dMine, (size_t)count * sizeof(MMEntry), ncclChar, 0, e->nccl, cx.stream));
+  SB_NCCL(ncclGroupEnd());
+  if (rank == 0) {
+    memcpy(mLocal->entries, m->entries + table[3], sizeof(MMEntry) * (size_t)count);
+    SB_CUDA(cudaStreamSynchronize(cx.stream));
+  } else {
+    SB_CUDA(cudaMemcpyAsync(mLocal->entries, dMine, sizeof(MMEntry) * (size_t)count, cudaMemcpyDeviceToHost, cx.stream));
+    SB_CUDA(cudaStreamSynchronize(cx.stream));
+  }
+  sbFree(dAll);
+  sbFree(dMine);
+  if (count == 0) SB_FATAL("commDistributeMatrix: rank %d received no matrix entries (fewer rows than ranks?)", rank);
+  mLocal->startRow = mLocal->entries[0].row;               // comm.c:383-386
+  mLocal->stopRow = mLocal->entries[count - 1].row;
+  mLocal->nr = mLocal->stopRow - mLocal->startRow + 1;
+  mLocal->nnz = count;
+  printf("Rank %d count %zu start %d stop %d\n", rank, mLocal->count, mLocal->startRow, mLocal->stopRow);
 }
 
 SbPartitionPlan* sbPartitionLocal(GMatrix* m, int rank, int size, const CG_UINT* startRows, int* wantCounts)

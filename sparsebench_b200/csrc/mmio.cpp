@@ -1,0 +1,131 @@
+// MatrixMarket input path (replaces MMMatrixRead / matrixConvertfromMM, matrix.c:123-269).
+// Host-side I/O, run once: the arrays it produces are HOST arrays (posix_memalign, like the reference's
+// allocate.c) -- convertMatrix and commPartition accept host GMatrix input and move it to the device.
+//
+// Behaviour follows the reference: coordinate format, real / integer / pattern values, general or symmetric
+// storage (off-diagonal entries are mirrored right behind the entry they come from, matrix.c:208-212), then a
+// sort by column followed by a STABLE sort by row (matrix.c:220-228), i.e. rows ascending, columns ascending
+// inside a row, duplicates in file order. Anything else is rejected with the reference's messages + exit.
+#include <ctype.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "sparsebench_b200.h"
+
+namespace {
+
+void* hostAlloc(size_t bytes)
+{
+  void* p = nullptr;
+  if (posix_memalign(&p, 64, bytes ? bytes : 64) != 0) {   // allocate.c:12-36 (ARRAY_ALIGNMENT = 64)
+    fprintf(stderr, "Error: Insufficient memory to fulfill the request\n");
+    exit(EXIT_FAILURE);
+  }
+  return p;
+}
+
+std::string lower(const char* s)
+{
+  std::string r(s);
+  for (char& c : r) c = (char)tolower((unsigned char)c);
+  return r;
+}
+
+} // namespace
+
+extern "C" {
+
+void MMMatrixRead(MMMatrix* m, char* filename)
+{
+  FILE* f = fopen(filename, "r");
+  if (!f) {
+    printf("Unable to open file.\n");                                  // matrix.c:129-132
+    exit(EXIT_FAILURE);
+  }
+  // banner: %%MatrixMarket matrix coordinate <field> <symmetry>
+  char line[1100], tag[64], object[64], format[64], field[64], symmetry[64];
+  if (!fgets(line, sizeof(line), f) ||
+      sscanf(line, "%63s %63s %63s %63s %63s", tag, object, format, field, symmetry) != 5 ||
+      lower(tag) != "%%matrixmarket") {
+    printf("Could not process Matrix Market banner.\n");               // :134-137
+    exit(EXIT_FAILURE);
+  }
+  const std::string obj = lower(object), fmt = lower(format), fld = lower(field), sym = lower(symmetry);
+  const bool isMatrix = obj == "matrix", isSparse = fmt == "coordinate";
+  const bool isReal = fld == "real", isInteger = fld == "integer", isPattern = fld == "pattern";
+  const bool isSymmetric = sym == "symmetric", isGeneral = sym == "general";
+  if (!((isReal || isPattern || isInteger) && isMatrix && isSparse)) {
+    fprintf(stderr, "Sorry, this application does not support ");     // :139-145
+    fprintf(stderr, "Market Market type: [%s %s %s %s]\n", obj.c_str(), fmt.c_str(), fld.c_str(), sym.c_str());
+    exit(EXIT_FAILURE);
+  }
+  if (!(isSymmetric || isGeneral)) {
+    printf("The matrix market file provided is not supported.\n Reason :\n");   // :156-171
+    printf(" * matrix has to be symmetric\n");
+    exit(EXIT_FAILURE);
+  }
+  // size line: first line that is not a comment
+  int M = 0, N = 0, nz = 0;
+  do {
+    if (!fgets(line, sizeof(line), f)) exit(EXIT_FAILURE);
+  } while (line[0] == '%');
+  while (sscanf(line, "%d %d %d", &M, &N, &nz) != 3) {                 // blank lines before the size line
+    if (!fgets(line, sizeof(line), f)) exit(EXIT_FAILURE);
+  }
+  printf("Read matrix %s with %d non zeroes and %d rows\n", filename, nz, M);   // :178
+
+  std::vector<MMEntry> e;
+  e.reserve((size_t)nz * (isSymmetric ? 2 : 1));
+  for (int i = 0; i < nz; i++) {
+    int row = 0, col = 0;
+    double v = 1.0;
+    int got;
+    if (isPattern) got = fscanf(f, "%d %d\n", &row, &col) + 1;
+    else got = fscanf(f, "%d %d %lg\n", &row, &col, &v);
+    if (got != 3) {
+      fprintf(stderr, "MMMatrixRead: malformed entry %d in %s\n", i + 1, filename);
+      exit(EXIT_FAILURE);
+    }
+    row--;                                                             // :201-202
+    col--;
+    e.push_back(MMEntry { row, col, v });
+    if (isSymmetric && row != col) e.push_back(MMEntry { col, row, v });   // :208-212
+  }
+  fclose(f);
+  std::stable_sort(e.begin(), e.end(), [](const MMEntry& a, const MMEntry& b) { return a.col < b.col; });   // :220
+  std::stable_sort(e.begin(), e.end(), [](const MMEntry& a, const MMEntry& b) { return a.row < b.row; });   // :224
+  m->entries = (MMEntry*)hostAlloc(sizeof(MMEntry) * e.size());
+  if (!e.empty()) memcpy(m->entries, e.data(), sizeof(MMEntry) * e.size());
+  m->nr = M;                                                           // :215-217
+  m->nnz = (int)e.size();
+  m->count = e.size();
+}
+
+void matrixConvertfromMM(MMMatrix* mm, GMatrix* m)
+{
+  m->startRow = (CG_UINT)mm->startRow;                                 // matrix.c:233-239
+  m->stopRow = (CG_UINT)mm->stopRow;
+  m->totalNr = (CG_UINT)mm->totalNr;
+  m->totalNnz = (CG_UINT)mm->totalNnz;
+  m->nr = (CG_UINT)mm->nr;
+  m->nc = (CG_UINT)mm->nr;
+  m->nnz = (CG_UINT)mm->nnz;
+  m->entries = (Entry*)hostAlloc(sizeof(Entry) * (size_t)m->nnz);
+  m->rowPtr = (CG_UINT*)hostAlloc(sizeof(CG_UINT) * ((size_t)m->nr + 1));
+  memset(m->entries, 0, sizeof(Entry) * (size_t)m->nnz);              // defined padding bytes
+  std::vector<CG_UINT> perRow((size_t)m->nr, 0);
+  for (size_t i = 0; i < mm->count; i++) perRow[(size_t)(mm->entries[i].row - mm->startRow)]++;   // :253-255
+  m->rowPtr[0] = 0;
+  for (CG_UINT r = 0; r < m->nr; r++) m->rowPtr[r + 1] = m->rowPtr[r] + perRow[r];                // :259-261
+  for (size_t i = 0; i < mm->count; i++) {                             // entries are already in row order (:263-266)
+    m->entries[i].val = (CG_FLOAT)mm->entries[i].val;
+    m->entries[i].col = (CG_UINT)mm->entries[i].col;
+  }
+}
+
+} // extern "C"

@@ -81,6 +81,38 @@ def main():
             api.destroyMatrix(A)
             if fmt != api.FMT_CCRS:
                 L.sbFreeGMatrix(C.byref(g))
+    # MatrixMarket path over the ranks (main.c:64-71, comm.c:311-402): rank 0 reads, row blocks are scattered
+    nxm, nym, nzm = 7, 6, 3 * world + 1                      # row count not divisible by the rank count
+    mg = orc.generate(nxm, nym, nzm)
+    path = "/tmp/sb_mgpu_check_%d.mtx" % os.getppid()
+    if rank == 0:
+        with open(path, "w") as f:
+            f.write("%%%%MatrixMarket matrix coordinate real general\n%d %d %d\n" % (mg.nr, mg.nr, mg.nnz))
+            rows = np.repeat(np.arange(mg.nr), np.diff(mg.rowPtr.astype(np.int64)))
+            order = np.random.default_rng(1).permutation(mg.nnz)    # unsorted file
+            for j in order:
+                f.write("%d %d %r\n" % (rows[j] + 1, mg.col[j] + 1, float(mg.val[j])))
+    g = api.matrixRead(path, comm)
+    per = [mg.nr // world + (1 if mg.nr % world > r else 0) for r in range(world)]      # sizeOfRank, comm.c:35-38
+    lo = sum(per[:rank])
+    hi = lo + per[rank]
+    check((g.nr, g.startRow, g.stopRow, g.totalNr) == (hi - lo, lo, hi - 1, mg.nr), "mm: row block %r" % ((g.nr, g.startRow, g.stopRow),), failures)
+    rp, col, val = api.gmatrix_arrays(g)
+    check(np.array_equal(rp, mg.rowPtr[lo:hi + 1] - mg.rowPtr[lo]), "mm: rowPtr slice differs", failures)
+    check(np.array_equal(col, mg.col[mg.rowPtr[lo]:mg.rowPtr[hi]]), "mm: columns differ", failures)
+    check(np.array_equal(val, mg.val[mg.rowPtr[lo]:mg.rowPtr[hi]]), "mm: values differ", failures)
+    L.commPartition(C.byref(comm), C.byref(g))
+    kref, href, xref = orc.cg_crs(mg, np.ones(mg.nr), np.zeros(mg.nr), 40, 1e-8)      # file input: b = 1 (CGSolver.c:34-36)
+    for fmt, sigma in fmts:
+        A = api.convertMatrix(fmt, g, 32, sigma)
+        k, hist, x, _ = api.solveCG(A, 40, 1e-8, comm=comm, generated=False, want_x=True)
+        ok = k == kref and len(hist) == len(href) and float(np.max(np.abs(hist - href) / np.maximum(href, 1e-10 * href[0]))) <= CG_TOL
+        check(ok, "mm: CG fmt=%s sigma=%d k=%d/%d" % (api.FMT_NAMES[fmt], sigma, k, kref), failures)
+        check(float(np.max(np.abs(x - xref[lo:hi]))) <= 1e-9, "mm: solution fmt=%s" % api.FMT_NAMES[fmt], failures)
+        api.destroyMatrix(A)
+    if rank == 0:
+        os.unlink(path)
+
     # global reductions (comm.c:653-662)
     v = C.c_double(float(rank + 1))
     L.commReduction(C.byref(v), api.OP_SUM)

@@ -143,3 +143,52 @@ def test_partition_matches_oracle_on_irregular_matrix():
         for f in ("sources", "recvCounts", "rdispls", "destinations", "sendCounts", "sdispls", "elementsToSend"):
             assert np.array_equal(d[f], o[f]), (r, f)
         assert np.array_equal(api.gmatrix_arrays(gmats[r])[1], omats[r].col)
+
+
+# ------------------------------------------------------------------------------------------- MatrixMarket path
+def _write_mm(path, field, symm, entries, n):
+    with open(path, "w") as f:
+        f.write("%%%%MatrixMarket matrix coordinate %s %s\n%% comment line\n%d %d %d\n" % (field, symm, n, n, len(entries)))
+        for (r, c, v) in entries:
+            f.write("%d %d\n" % (r + 1, c + 1) if field == "pattern" else "%d %d %r\n" % (r + 1, c + 1, v))
+
+
+def test_mm_reader_bit_exact_on_reference_fixtures(fixtures_dir):
+    """MMMatrixRead + matrixConvertfromMM (matrix.c:123-269) through the C ABI vs the oracle's restatement."""
+    from oracle import mmio
+    for name in ["test%d.mtx" % t for t in range(11)] + ["matrix_band_klein.mtx"]:
+        path = os.path.join(fixtures_dir, name)
+        g = api.matrixRead(path)
+        rp, col, val = api.gmatrix_arrays(g)
+        m = mmio.read_mm(path)
+        assert np.array_equal(rp, m.rowPtr) and np.array_equal(col, m.col) and np.array_equal(val, m.val), name
+        assert (g.nr, g.nc, g.nnz, g.startRow, g.stopRow) == (m.nr, m.nr, m.nnz, 0, m.nr - 1)
+        api.lib().sbFreeGMatrix(C.byref(g))
+
+
+@pytest.mark.parametrize("field,symm", [("real", "general"), ("real", "symmetric"), ("integer", "symmetric"),
+                                        ("pattern", "general"), ("pattern", "symmetric")])
+def test_mm_reader_fields_symmetry_and_duplicates(tmp_path, field, symm):
+    """mirroring of off-diagonals (matrix.c:208-212), pattern values = 1, unsorted input, duplicate entries kept in
+    file order by the two stable sorts (:220-228)"""
+    from oracle import mmio
+    rng = np.random.default_rng(5)
+    n = 23
+    entries = []
+    for _ in range(140):
+        r, c = int(rng.integers(0, n)), int(rng.integers(0, n))
+        if symm == "symmetric" and c > r:
+            r, c = c, r
+        v = float(rng.integers(-9, 10)) if field == "integer" else float(rng.standard_normal())
+        entries.append((r, c, v))
+    entries += [(i, i, 4.0) for i in range(n)] + entries[:5]          # every row non-empty; 5 duplicates
+    path = str(tmp_path / "m.mtx")
+    _write_mm(path, field, symm, entries, n)
+    g = api.matrixRead(path)
+    rp, col, val = api.gmatrix_arrays(g)
+    m = mmio.read_mm(path)
+    assert np.array_equal(rp, m.rowPtr) and np.array_equal(col, m.col) and np.array_equal(val, m.val)
+    from oracle import ref
+    if ref.available("CRS"):
+        mr = ref.csr_from_gmatrix(ref.read_mm(path))                    # the reference's own reader
+        assert np.array_equal(rp, mr.rowPtr) and np.array_equal(col, mr.col) and np.array_equal(val, mr.val)

@@ -259,6 +259,21 @@ def test_cg_klein_anchor(fixtures_dir):
             api.destroyMatrix(A)
 
 
+def test_cg_klein_end_to_end_through_the_mm_path(fixtures_dir):
+    """main.c:64-71 + :170-198 through the C ABI only: MMMatrixRead -> commDistributeMatrix -> matrixConvertfromMM ->
+    commPartition -> convertMatrix -> solveCG on data/matrix_band_klein.mtx"""
+    comm = api.Comm()
+    api.lib().commInit(C.byref(comm), 0, None)
+    g = api.matrixRead(os.path.join(fixtures_dir, "matrix_band_klein.mtx"), comm)
+    api.lib().commPartition(C.byref(comm), C.byref(g))
+    for fmt in (api.FMT_CRS, api.FMT_SCS, api.FMT_CCRS):
+        A = make_matrix(fmt, g, 16)
+        k, hist, x, _ = api.solveCG(A, 10, 0.0, comm=comm, generated=False, want_x=True)
+        assert k == 3 and list(hist) == [10.0, 10.0, 0.0] and np.isnan(x).all()
+        api.destroyMatrix(A)
+    api.lib().commFinalize(C.byref(comm))
+
+
 def test_cg_host_vectors_and_custom_rhs():
     """explicit b / x0 in host memory (SB_CG_HOST_VECTORS path used by bench.py's e2e leg), SELL permutation undone"""
     n = 12
