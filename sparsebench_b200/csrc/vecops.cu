@@ -125,6 +125,10 @@ void launchDot(uint32_t n, const double* x, const double* y, double* dResult, in
 // rho[j] = r_j . r_j (rho[0] from the initial residual), pAp[k] = p_k . A p_k. Iteration k (1-based,
 // CGSolver.c:107-129) uses rtrans = rho[k-1], oldrtrans = rho[k-2].
 
+// Both kernels keep 4 independent 16-byte loads per array in flight per thread (kVecUnroll); at 128^3 the whole
+// vector is one pass of the grid, so the kernels are a single DRAM/L2 round trip instead of a dependent chain.
+constexpr int kVecUnroll = 4;
+
 // p = r + beta*p with beta = rho[k-1]/rho[k-2]  (CGSolver.c:111-114); k == 1: p = r + 0*r (:109).
 __global__ void __launch_bounds__(kVecThreads)
 cgUpdatePKernel(uint32_t n, int k, const double* __restrict__ rho, const double* __restrict__ r, double* __restrict__ p)
@@ -134,26 +138,26 @@ cgUpdatePKernel(uint32_t n, int k, const double* __restrict__ rho, const double*
   const uint64_t n2 = n / 2;
   const double2* r2 = reinterpret_cast<const double2*>(r);
   double2* p2 = reinterpret_cast<double2*>(p);
-  if (k == 1) {
-    for (uint64_t i = tid; i < n2; i += stride) {
-      const double2 a = r2[i];
-      double2 o;
-      o.x = __dadd_rn(a.x, __dmul_rn(0.0, a.x));
-      o.y = __dadd_rn(a.y, __dmul_rn(0.0, a.y));
-      p2[i] = o;
-    }
-    if (tid == 0 && (n & 1u)) p[n - 1] = __dadd_rn(r[n - 1], __dmul_rn(0.0, r[n - 1]));
-    return;
+  // k == 1: p = r + 0*r, i.e. beta = 0 applied to r itself (waxpby(1, r, 0, r, p))
+  const double beta = k == 1 ? 0.0 : __ddiv_rn(rho[k - 1], rho[k - 2]);
+  for (uint64_t i0 = tid; i0 < n2; i0 += kVecUnroll * stride) {
+    double2 a[kVecUnroll], b[kVecUnroll];
+#pragma unroll
+    for (int u = 0; u < kVecUnroll; u++)
+      if (i0 + u * stride < n2) {
+        a[u] = r2[i0 + u * stride];
+        b[u] = k == 1 ? a[u] : p2[i0 + u * stride];
+      }
+#pragma unroll
+    for (int u = 0; u < kVecUnroll; u++)
+      if (i0 + u * stride < n2) {
+        double2 o;
+        o.x = __dadd_rn(a[u].x, __dmul_rn(beta, b[u].x));
+        o.y = __dadd_rn(a[u].y, __dmul_rn(beta, b[u].y));
+        p2[i0 + u * stride] = o;
+      }
   }
-  const double beta = __ddiv_rn(rho[k - 1], rho[k - 2]);
-  for (uint64_t i = tid; i < n2; i += stride) {
-    const double2 a = r2[i], b = p2[i];
-    double2 o;
-    o.x = __dadd_rn(a.x, __dmul_rn(beta, b.x));
-    o.y = __dadd_rn(a.y, __dmul_rn(beta, b.y));
-    p2[i] = o;
-  }
-  if (tid == 0 && (n & 1u)) p[n - 1] = __dadd_rn(r[n - 1], __dmul_rn(beta, p[n - 1]));
+  if (tid == 0 && (n & 1u)) p[n - 1] = __dadd_rn(r[n - 1], __dmul_rn(beta, k == 1 ? r[n - 1] : p[n - 1]));
 }
 
 // alpha = rho[k-1]/pAp[k]; x += alpha*p; r += (-alpha)*Ap; rho[k] = r.r   (CGSolver.c:126-128 + :112 of the
@@ -174,17 +178,29 @@ cgUpdateXRKernel(uint32_t n, int k, double* __restrict__ rho, const double* __re
   const double2* p2 = reinterpret_cast<const double2*>(p);
   const double2* q2 = reinterpret_cast<const double2*>(Ap);
   double a0 = 0.0, a1 = 0.0;
-  for (uint64_t i = tid; i < n2; i += stride) {
-    const double2 xv = x2[i], pv = p2[i], rv = r2[i], qv = q2[i];
-    double2 xo, ro;
-    xo.x = __dadd_rn(xv.x, __dmul_rn(alpha, pv.x));
-    xo.y = __dadd_rn(xv.y, __dmul_rn(alpha, pv.y));
-    ro.x = __dadd_rn(rv.x, __dmul_rn(nalpha, qv.x));
-    ro.y = __dadd_rn(rv.y, __dmul_rn(nalpha, qv.y));
-    x2[i] = xo;
-    r2[i] = ro;
-    a0 = fma(ro.x, ro.x, a0);
-    a1 = fma(ro.y, ro.y, a1);
+  for (uint64_t i0 = tid; i0 < n2; i0 += 2 * stride) {
+    double2 xv[2], pv[2], rv[2], qv[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++)
+      if (i0 + u * stride < n2) {
+        xv[u] = x2[i0 + u * stride];
+        pv[u] = p2[i0 + u * stride];
+        rv[u] = r2[i0 + u * stride];
+        qv[u] = q2[i0 + u * stride];
+      }
+#pragma unroll
+    for (int u = 0; u < 2; u++)
+      if (i0 + u * stride < n2) {
+        double2 xo, ro;
+        xo.x = __dadd_rn(xv[u].x, __dmul_rn(alpha, pv[u].x));
+        xo.y = __dadd_rn(xv[u].y, __dmul_rn(alpha, pv[u].y));
+        ro.x = __dadd_rn(rv[u].x, __dmul_rn(nalpha, qv[u].x));
+        ro.y = __dadd_rn(rv[u].y, __dmul_rn(nalpha, qv[u].y));
+        x2[i0 + u * stride] = xo;
+        r2[i0 + u * stride] = ro;
+        a0 = fma(ro.x, ro.x, a0);
+        a1 = fma(ro.y, ro.y, a1);
+      }
   }
   double acc = a0 + a1;
   if (tid == 0 && (n & 1u)) {
@@ -201,7 +217,7 @@ cgUpdateXRKernel(uint32_t n, int k, double* __restrict__ rho, const double* __re
 void launchCgUpdateP(uint32_t n, int k, const double* rho, const double* r, double* p, cudaStream_t s)
 {
   if (n == 0) return;
-  cgUpdatePKernel<<<vecGrid(n, 4), kVecThreads, 0, s>>>(n, k, rho, r, p);
+  cgUpdatePKernel<<<vecGrid(n, 2 * kVecUnroll), kVecThreads, 0, s>>>(n, k, rho, r, p);
   SB_CUDA(cudaGetLastError());
   countLaunch();
 }
