@@ -176,6 +176,10 @@ void sbSCS_convertMatrix(SbSCSMatrix* m, GMatrix* im);                        /*
 void sbSCS_spMVM(SbSCSMatrix* m, const CG_FLOAT* x, CG_FLOAT* y);             /* matrix-SCS.c:198-228 */
 void sbCCRS_convertMatrix(SbCCRSMatrix* m, GMatrix* im);                      /* matrix-CCRS.c:12 (alias intent) */
 void sbCCRS_spMVM(SbCCRSMatrix* m, const CG_FLOAT* x, CG_FLOAT* y);           /* matrix-CCRS.c:14-31 */
+/* y = A x in ONE launch that takes the units [intLo, intHi) first (rows for CRS/CCRS, chunks for SCS) and the rest
+ * afterwards: the kernel the multi-GPU CG uses to overlap the halo exchange, here without a
+ * halo to wait for. Returns 0 if the matrix has no pipelined kernel (then nothing was launched). */
+int sbSpmvOrdered(void* matrix, int fmt, const CG_FLOAT* x, CG_FLOAT* y, CG_UINT intLo, CG_UINT intHi);
 void sbCRS_destroyMatrix(SbCRSMatrix* m);
 void sbSCS_destroyMatrix(SbSCSMatrix* m);
 void sbCCRS_destroyMatrix(SbCCRSMatrix* m);

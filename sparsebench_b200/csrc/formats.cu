@@ -68,7 +68,7 @@ static DeviceInput stageInput(const GMatrix* im)
     in.stored = last;
   } else {
     in.stored = im->rowPtr[nr];
-    uint32_t* rp = (uint32_t*)allocate(64, sizeof(uint32_t) * (nr + 1));
+    uint32_t* rp = (uint32_t*)allocate(64, sizeof(uint32_t) * (nr + 1 + 8));   // +8: bulk-copy granularity (CCRS shares it)
     Entry* en = (Entry*)allocate(64, sizeof(Entry) * (in.stored ? in.stored : 1));
     SB_CUDA(cudaMemcpyAsync(rp, im->rowPtr, sizeof(uint32_t) * (nr + 1), cudaMemcpyHostToDevice, c.stream));
     SB_CUDA(cudaMemcpyAsync(en, im->entries, sizeof(Entry) * in.stored, cudaMemcpyHostToDevice, c.stream));
@@ -234,7 +234,7 @@ void sbCRS_convertMatrix(SbCRSMatrix* m, GMatrix* im)
   copyHeader(&m->nr, im);
   DeviceInput in = stageInput(im);
   const size_t nr = im->nr;
-  m->rowPtr = (CG_UINT*)allocate(64, sizeof(CG_UINT) * (nr + 1));
+  m->rowPtr = (CG_UINT*)allocate(64, sizeof(CG_UINT) * (nr + 1 + 8));   // +8: 16-byte granularity of the bulk copies
   // +8: the staged SpMV kernel widens its bulk copies to 16-byte granularity (up to 3 elements past the end)
   m->colInd = (CG_UINT*)allocate(64, sizeof(CG_UINT) * (in.stored + 8));
   m->val = (CG_FLOAT*)allocate(64, sizeof(CG_FLOAT) * (in.stored + 8));

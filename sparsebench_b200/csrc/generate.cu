@@ -133,7 +133,7 @@ void sbGenerateDevice(GMatrix* m, Parameter* p, int rank, int size, bool use_7pt
   sb::Context& c = sb::ctx();
   const size_t n = (size_t)g.localRows;
   uint32_t* len = (uint32_t*)allocate(64, sizeof(uint32_t) * n);
-  m->rowPtr = (CG_UINT*)allocate(64, sizeof(CG_UINT) * (n + 1));
+  m->rowPtr = (CG_UINT*)allocate(64, sizeof(CG_UINT) * (n + 1 + 8));   // +8: bulk-copy granularity of the SpMV kernels (CCRS shares this array)
   const int threads = 256;
   const int blocks = (int)((n + threads - 1) / threads < (size_t)c.numSMs * 16 ? (n + threads - 1) / threads : (size_t)c.numSMs * 16);
   rowLengthKernel<<<blocks, threads, 0, c.stream>>>(g, len);

@@ -496,8 +496,9 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
         const uint32_t rs = live ? rp[g] : 0u, re = live ? rp[g + 1] : 0u;
         double sum = 0.0;
         if (fits) {
-          uint32_t idx = rs - (uint32_t)org + sub;
-          const uint32_t end = re - (uint32_t)org;
+          // lanes without a row get an empty range (0 - org would wrap and alias real entries)
+          uint32_t idx = live ? rs - (uint32_t)org + sub : 0u;
+          const uint32_t end = live ? re - (uint32_t)org : 0u;
           while (__any_sync(0xffffffffu, idx < end)) {
             uint32_t cc[UN];
             double vv[UN], xx[UN];
@@ -871,6 +872,17 @@ void sbCCRS_spMVM(SbCCRSMatrix* m, const CG_FLOAT* x, CG_FLOAT* y)
 {
   Operator A = makeOperator(m, SB_FMT_CCRS);
   launchSpmv(A, x, y, 0, A.nr, nullptr, ctx().stream);
+}
+
+int sbSpmvOrdered(void* matrix, int fmt, const CG_FLOAT* x, CG_FLOAT* y, CG_UINT intLo, CG_UINT intHi)
+{
+  // The single-launch kernel of the multi-GPU CG (interior units first, then the boundary units behind a halo
+  // gate), launched with an open gate: lets a single-GPU test check its unit ordering against the plain kernel.
+  Operator A = makeOperator(matrix, fmt);
+  if (fmt == SB_FMT_SCS) A.sell.col = ((SbSCSMatrix*)matrix)->colInd;   // reference semantics, like sbSCS_spMVM
+  if (!spmvGatedAvailable(A)) return 0;
+  launchSpmvGated(A, x, y, intLo, intHi, HaloGate(), nullptr, ctx().stream);
+  return 1;
 }
 
 void sbSCS_spMVM(SbSCSMatrix* m, const CG_FLOAT* x, CG_FLOAT* y)

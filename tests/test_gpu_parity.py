@@ -170,6 +170,28 @@ def test_scs_ragged_rows_bit_exact(nr, maxlen, sigma):
     api.destroyMatrix(A)
 
 
+@pytest.mark.parametrize("fmt", [api.FMT_CRS, api.FMT_SCS, api.FMT_CCRS])
+@pytest.mark.parametrize("nx,ny,nz", [(16, 16, 12), (33, 7, 9), (40, 40, 40)])
+def test_ordered_single_launch_spmv_matches_plain_kernel(fmt, nx, ny, nz):
+    """the interior-first / boundary-last kernel of the multi-GPU CG (open gate) gives the plain kernel's bits for
+    any split, including an empty interior and an empty boundary"""
+    m = orc.generate(nx, ny, nz)
+    g = api.matrixGenerate(nx, ny, nz, device=True)
+    A = make_matrix(fmt, g, 256)
+    units = A.nChunks if fmt == api.FMT_SCS else A.nr
+    slots = A.nrPadded if fmt == api.FMT_SCS else A.nr
+    x = np.random.default_rng(3).standard_normal(m.nr)
+    xd = api.to_device(x)
+    yref = dev_spmv(A, x, slots)
+    plane = max(1, (nx * ny) // (32 if fmt == api.FMT_SCS else 1))
+    for lo, hi in [(0, units), (plane, units - plane), (0, units - plane), (plane, units), (units // 2, units // 2),
+                   (units, units), (1, 2), (units - 1, units)]:
+        yd = api.to_device(np.full(slots, np.nan))
+        assert api.lib().sbSpmvOrdered(C.byref(A), fmt, xd.ptr, yd.ptr, lo, hi) == 1
+        assert np.array_equal(api.to_host(yd, np.float64, slots), yref), (lo, hi)
+    api.destroyMatrix(A)
+
+
 # ------------------------------------------------------------------------------------------- vector kernels
 @pytest.mark.parametrize("n", [1, 2, 3, 255, 1000, 4097, 1 << 20])
 def test_waxpby_bit_exact_and_in_place(n):
