@@ -31,6 +31,8 @@ struct CgSolver {
   double eps = 0.0;
   int itermax = 0, flags = 0, printFreq = 1;
   bool fused = true, print = false, generated = false, profile = false, overlap = true, gated = false;
+  bool fusedReduce = false;                // multi-GPU: all-reduces split into push (producer) / collect (consumer)
+  PeerReduce pendingRho;                   // epoch of the newest rho that has been pushed but not yet collected
   int* elemsPerm = nullptr;                // SELL with a row permutation: elementsToSend in solver (permuted) numbering
   uint32_t intLo = 0, intHi = 0;           // SpMV units [intLo, intHi) reference no halo column
   uint32_t n = 0;
@@ -167,6 +169,7 @@ struct CgSolver {
         const bool can = overlap && spmvGatedAvailable(A);
         if (can) spmvInteriorUnits(A, &intLo, &intHi, s);
         gated = commAttachHaloVector(comm, p, A.nr, can);
+        fusedReduce = gated && fused && getenv("SB_NO_FUSED_REDUCE") == nullptr;
       }
     }
 
@@ -220,12 +223,28 @@ struct CgSolver {
           stopped = true;
           break;
         }
-        launchCgUpdateP(n, k, rho, r, p, s);                   // :109 / :111-114
+        if (fusedReduce) {
+          // rho[k-1] is summed over the ranks inside the p update, p.Ap inside the x/r update: no all-reduce launches
+          launchCgUpdateP(n, k, rho, r, p, pendingRho.size ? &pendingRho : nullptr, s);   // :109 / :111-114
+          mark(R_UPDATE_P);
+          if (k >= 2) {                                         // the global rho[k-1] exists now: send it to the host
+            SB_CUDA(cudaMemcpyAsync(hRho + k - 1, rho + k - 1, sizeof(double), cudaMemcpyDeviceToHost, s));
+            SB_CUDA(cudaEventRecord(ring[(k - 1) % kEventRing], s));
+          }
+          const PeerReduce prPAp = commBeginReduce(comm);
+          DotArgs d { pAp + k, false, 1, &prPAp };
+          spmvWithHalo(&d);                                     // :122-125
+          pendingRho = commBeginReduce(comm);
+          launchCgUpdateXR(n, k, rho, pAp, x, r, p, Ap, 2, &prPAp, &pendingRho, s);       // :126-128 (+ :112 of iteration k+1)
+          mark(R_UPDATE_XR);
+          continue;
+        }
+        launchCgUpdateP(n, k, rho, r, p, nullptr, s);          // :109 / :111-114
         mark(R_UPDATE_P);
         DotArgs d { pAp + k, false, 1 };
         spmvWithHalo(&d);                                      // :122-125
         allreduce(pAp + k, SB_SUM);
-        launchCgUpdateXR(n, k, rho, pAp, x, r, p, Ap, 2, s);   // :126-128 (+ :112 of iteration k+1)
+        launchCgUpdateXR(n, k, rho, pAp, x, r, p, Ap, 2, nullptr, nullptr, s);   // :126-128 (+ :112 of iteration k+1)
         mark(R_UPDATE_XR);
         allreduce(rho + k, SB_SUM);
         SB_CUDA(cudaMemcpyAsync(hRho + k, rho + k, sizeof(double), cudaMemcpyDeviceToHost, s));

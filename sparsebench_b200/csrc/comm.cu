@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "peer_window.h"
 #include "sb_internal.h"
 #include "sb_partition.h"
 
@@ -46,17 +47,7 @@ namespace sb {
 // MPI_Neighbor_alltoallv (C1) of comm.c:627-651 are one launch. The all-reduce of a dot product is one
 // single-CTA kernel: every rank stores its partial into slot [rank] of every peer and sums the slots of its
 // own window in rank order, so all ranks obtain bit-identical results.
-constexpr int kMaxRanks = 64;
-constexpr int kRedDepth = 4;
 constexpr long long kSpinTimeoutCycles = 40000000000ll;   // ~20 s: a dead peer must not hang the GPU forever
-
-struct CtrlWindow {
-  unsigned long long haloFlag[kMaxRanks];              // [source rank] newest exchange completely stored by that source
-  unsigned long long haloAck[kMaxRanks];               // [dest rank]   newest exchange that dest has copied out of its slot
-  unsigned long long directFlag[kMaxRanks];            // [source rank] arrival counter of direct (registered-vector) exchanges
-  unsigned long long redFlag[kRedDepth][kMaxRanks];    // [epoch % depth][rank] epoch of the value below
-  double redVal[kRedDepth][kMaxRanks];
-};
 
 struct PutPlan {
   int ndest;
@@ -663,6 +654,20 @@ void commAllreduceDevice(Comm* c, double* d, int count, int op, cudaStream_t s)
     return;
   }
   SB_NCCL(ncclAllReduce(d, d, (size_t)count, ncclDouble, op == SB_MAX ? ncclMax : ncclSum, e->nccl, s));
+}
+
+// Next epoch of the peer-window all-reduce, for kernels that fuse the push / collect halves (peer mode only).
+PeerReduce commBeginReduce(Comm* c)
+{
+  CommExt* e = ext(c);
+  PeerReduce pr;
+  if (!e || e->mode != COMM_PEER) SB_FATAL("commBeginReduce needs the peer-window transport");
+  pr.size = e->size;
+  pr.rank = e->rank;
+  pr.epoch = ++e->redEpoch;
+  pr.mine = e->ctrl;
+  pr.peers = e->dPeerCtrl;
+  return pr;
 }
 
 const int* commDeviceElements(Comm* c)

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "peer_window.h"
+
 namespace sb {
 
 // Matrix values / indices are read exactly once per SpMV: keep them out of L1 so the cache stays with the
@@ -58,8 +60,11 @@ __device__ __forceinline__ double blockSum(double v, double* scratch)
 // One-kernel grid reduction: every block deposits its partial, the last block to arrive (atomic ticket)
 // adds all partials in a fixed order, so the result does not depend on block scheduling.
 // out = (accumulate ? *out : 0) + sum(partials). The ticket resets itself for the next launch.
+// With `push` (multi-GPU) the last block additionally stores the sum into slot [rank] of every peer's control
+// window -- the first half of an all-reduce whose second half (peerCollect) runs in the prologue of the kernel
+// that consumes the scalar, so no separate all-reduce launch sits between the two.
 __device__ __forceinline__ void gridSum(double blockPartial, double* partials, unsigned int* ticket, double* out,
-    bool accumulate, double* scratch)
+    bool accumulate, double* scratch, const PeerReduce* push = nullptr)
 {
   __shared__ bool amLast;
   if (threadIdx.x == 0) {
@@ -74,8 +79,47 @@ __device__ __forceinline__ void gridSum(double blockPartial, double* partials, u
     double v = 0.0;
     for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) v += __ldcg(partials + i);
     v = blockSum(v, scratch);
-    if (threadIdx.x == 0) *out = accumulate ? (*out + v) : v;
+    if (threadIdx.x == 0) {
+      v = accumulate ? (*out + v) : v;
+      *out = v;
+      scratch[0] = v;
+    }
+    if (push && push->size > 0) {
+      __syncthreads();
+      if ((int)threadIdx.x < push->size) {
+        const double mine = scratch[0];
+        CtrlWindow* w = push->peers[threadIdx.x];
+        const int slot = (int)(push->epoch % kRedDepth);
+        *(volatile double*)&w->redVal[slot][push->rank] = mine;
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&w->redFlag[slot][push->rank]), "l"(push->epoch) : "memory");
+      }
+    }
   }
+}
+
+// Second half of the all-reduce: every thread of the calling block gets the global sum. `vals` is shared memory
+// for kMaxRanks doubles. Contains block barriers: call from all threads.
+__device__ __forceinline__ double peerCollect(const PeerReduce& pr, double* vals)
+{
+  const int slot = (int)(pr.epoch % kRedDepth);
+  if ((int)threadIdx.x < pr.size) {
+    const unsigned long long* flag = &pr.mine->redFlag[slot][threadIdx.x];
+    unsigned long long seen;
+    const long long start = clock64();
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
+      if (seen >= pr.epoch) break;
+      __nanosleep(40);
+      if (clock64() - start > 40000000000ll) __trap();   // dead peer: fail instead of hanging the GPU
+    }
+    vals[threadIdx.x] = *(volatile double*)&pr.mine->redVal[slot][threadIdx.x];
+  }
+  __syncthreads();
+  double acc = vals[0];
+  for (int r = 1; r < pr.size; r++) acc += vals[r];      // rank order: same bits on every rank
+  __syncthreads();
+  return acc;
 }
 
 // ---- mbarrier + 1-D bulk copy (TMA, SASS UBLKCP): asynchronous global -> shared streaming of the matrix

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include "peer_window.h"
 #include "sparsebench_b200.h"
 
 // Error convention of the reference: message + exit(EXIT_FAILURE) (allocate.c:19-33).
@@ -96,6 +97,7 @@ struct DotArgs {
   double* out;
   bool accumulate;
   int slot;
+  const PeerReduce* push = nullptr;   // multi-GPU: the last block also stores the sum into every peer's window
 };
 // y = A x on units [lo,hi) (rows for CRS/CCRS, chunks for SELL); with `dot` also sum_i x[i]*y[i] over them.
 uint32_t spmvUnits(const Operator& A);
@@ -114,9 +116,11 @@ void launchWaxpby(uint32_t n, double alpha, const double* x, double beta, const 
 // *dResult (device) = sum x[i]*y[i], deterministic one-kernel grid reduction through scratch slot `slot`
 void launchDot(uint32_t n, const double* x, const double* y, double* dResult, int slot, cudaStream_t s);
 // fused CG passes: rho[j] = r_j.r_j, pAp[k] = p_k.Ap_k live on the device, k is the 1-based iteration
-void launchCgUpdateP(uint32_t n, int k, const double* rho, const double* r, double* p, cudaStream_t s);
-void launchCgUpdateXR(uint32_t n, int k, double* rho, const double* pAp, double* x, double* r, const double* p,
-    const double* Ap, int slot, cudaStream_t s);
+// collect*: the scalar this kernel needs (rho[k-1] resp. pAp[k]) is still spread over the peer window and is summed
+// in the kernel's prologue; pushRho: rho[k] is pushed to the peers instead of being all-reduced by a separate kernel
+void launchCgUpdateP(uint32_t n, int k, double* rho, const double* r, double* p, const PeerReduce* collectRho, cudaStream_t s);
+void launchCgUpdateXR(uint32_t n, int k, double* rho, double* pAp, double* x, double* r, const double* p,
+    const double* Ap, int slot, const PeerReduce* collectPAp, const PeerReduce* pushRho, cudaStream_t s);
 void launchInitVectors(uint32_t n, const uint32_t* rowPtr, const uint32_t* rowLen, bool generated, double* x, double* b,
     cudaStream_t s);
 void launchScatter(uint32_t n, const uint32_t* map, const double* in, double* out, cudaStream_t s);   // out[map[i]] = in[i]
@@ -131,6 +135,7 @@ void commAllreduceDevice(Comm* c, double* d, int count, int op, cudaStream_t s);
 // NVLink peer-window transport
 bool commPeerMode(const Comm* c);
 const int* commDeviceElements(Comm* c);                    // device copy of Comm.elementsToSend
+PeerReduce commBeginReduce(Comm* c);                       // next all-reduce epoch, for fused push / collect
 // Direct halo delivery for one registered vector (the CG's p): the sender stores straight behind the receiver's
 // local rows, the receiver's SpMV kernel itself waits on the arrival counters before it touches the first row that
 // references a halo column (HaloGate). No acknowledge: the caller guarantees that a new exchange only starts after

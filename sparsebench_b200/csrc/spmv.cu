@@ -65,7 +65,8 @@ __device__ __forceinline__ void gateWait(const HaloGate& gate, int who)
 template <bool DOT, int WARPS, int J, int S, int U, bool LOCKSTEP, bool GATED>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 spmvSell32TmaKernel(SellView A, const double* __restrict__ x, double* __restrict__ y, uint32_t lo, uint32_t hi,
-    double* partials, unsigned int* ticket, double* dotOut, bool accumulate, uint32_t rot, uint32_t nInterior, HaloGate gate)
+    double* partials, unsigned int* ticket, double* dotOut, bool accumulate, uint32_t rot, uint32_t nInterior, HaloGate gate,
+    PeerReduce push)
 {
   extern __shared__ __align__(128) unsigned char ring[];
   __shared__ double scratch[32];
@@ -196,7 +197,7 @@ spmvSell32TmaKernel(SellView A, const double* __restrict__ x, double* __restrict
   }
   if (DOT) {
     const double b = blockSum(dotAcc, scratch);
-    gridSum(b, partials, ticket, dotOut, accumulate, scratch);
+    gridSum(b, partials, ticket, dotOut, accumulate, scratch, push.size ? &push : nullptr);
   }
 }
 
@@ -223,10 +224,11 @@ static void launchSell32TmaCfg(const SellView& A, const double* x, double* y, ui
   const HaloGate gate = g ? g->gate : HaloGate();
   if (dot)
     spmvSell32TmaKernel<true, WARPS, J, S, U, LOCKSTEP, GATED><<<(int)blocks, WARPS * 32, smem, s>>>(A, x, y, lo, hi,
-        c.partials + (size_t)dot->slot * kMaxPartials, c.tickets + dot->slot, dot->out, dot->accumulate, rot, nInt, gate);
+        c.partials + (size_t)dot->slot * kMaxPartials, c.tickets + dot->slot, dot->out, dot->accumulate, rot, nInt, gate,
+        dot->push ? *dot->push : PeerReduce());
   else
     spmvSell32TmaKernel<false, WARPS, J, S, U, LOCKSTEP, GATED><<<(int)blocks, WARPS * 32, smem, s>>>(A, x, y, lo, hi,
-        nullptr, nullptr, nullptr, false, rot, nInt, gate);
+        nullptr, nullptr, nullptr, false, rot, nInt, gate, PeerReduce());
   SB_CUDA(cudaGetLastError());
   countLaunch();
 }
@@ -409,7 +411,7 @@ template <bool DOT, int LPR, typename L, bool GATED>
 __global__ void __launch_bounds__((L::kWarps + 1) * 32, 1)
 spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __restrict__ x, double* __restrict__ y,
     uint32_t lo, uint32_t hi, uint32_t tileRows, double* partials, unsigned int* ticket, double* dotOut, bool accumulate,
-    uint32_t intLo, uint32_t intHi, HaloGate gate)
+    uint32_t intLo, uint32_t intHi, HaloGate gate, PeerReduce push)
 {
   extern __shared__ __align__(128) unsigned char ring[];
   __shared__ double scratch[32];
@@ -540,7 +542,7 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
   }
   if (DOT) {
     const double b = blockSum(dotAcc, scratch);
-    gridSum(b, partials, ticket, dotOut, accumulate, scratch);
+    gridSum(b, partials, ticket, dotOut, accumulate, scratch, push.size ? &push : nullptr);
   }
 }
 
@@ -568,10 +570,11 @@ static void launchRowsPipe(L acc, const uint32_t* rowPtr, const double* x, doubl
   const HaloGate gate = g ? g->gate : HaloGate();
   if (dot)
     spmvRowsPipeKernel<true, LPR, L, GATED><<<(int)blocks, threads, smem, s>>>(acc, rowPtr, x, y, lo, hi, tileRows,
-        c.partials + (size_t)dot->slot * kMaxPartials, c.tickets + dot->slot, dot->out, dot->accumulate, intLo, intHi, gate);
+        c.partials + (size_t)dot->slot * kMaxPartials, c.tickets + dot->slot, dot->out, dot->accumulate, intLo, intHi, gate,
+        dot->push ? *dot->push : PeerReduce());
   else
     spmvRowsPipeKernel<false, LPR, L, GATED><<<(int)blocks, threads, smem, s>>>(acc, rowPtr, x, y, lo, hi, tileRows, nullptr,
-        nullptr, nullptr, false, intLo, intHi, gate);
+        nullptr, nullptr, false, intLo, intHi, gate, PeerReduce());
   SB_CUDA(cudaGetLastError());
   countLaunch();
 }

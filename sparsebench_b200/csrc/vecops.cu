@@ -131,15 +131,27 @@ constexpr int kVecUnroll = 4;
 
 // p = r + beta*p with beta = rho[k-1]/rho[k-2]  (CGSolver.c:111-114); k == 1: p = r + 0*r (:109).
 __global__ void __launch_bounds__(kVecThreads)
-cgUpdatePKernel(uint32_t n, int k, const double* __restrict__ rho, const double* __restrict__ r, double* __restrict__ p)
+cgUpdatePKernel(uint32_t n, int k, double* rho, const double* __restrict__ r, double* __restrict__ p, PeerReduce collectRho)
 {
+  __shared__ double peerVals[kMaxRanks];
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   const uint64_t n2 = n / 2;
   const double2* r2 = reinterpret_cast<const double2*>(r);
   double2* p2 = reinterpret_cast<double2*>(p);
+  // multi-GPU: rho[k-1] was pushed to the peer windows by the previous x/r update; sum it here (every block gets
+  // the same bits) and let one thread store the global value for the host's convergence test
+  double rtrans = 0.0;
+  if (k > 1) {
+    if (collectRho.size > 0) {
+      rtrans = peerCollect(collectRho, peerVals);
+      if (tid == 0) rho[k - 1] = rtrans;
+    } else {
+      rtrans = rho[k - 1];
+    }
+  }
   // k == 1: p = r + 0*r, i.e. beta = 0 applied to r itself (waxpby(1, r, 0, r, p))
-  const double beta = k == 1 ? 0.0 : __ddiv_rn(rho[k - 1], rho[k - 2]);
+  const double beta = k == 1 ? 0.0 : __ddiv_rn(rtrans, rho[k - 2]);
   for (uint64_t i0 = tid; i0 < n2; i0 += kVecUnroll * stride) {
     double2 a[kVecUnroll], b[kVecUnroll];
 #pragma unroll
@@ -163,14 +175,22 @@ cgUpdatePKernel(uint32_t n, int k, const double* __restrict__ rho, const double*
 // alpha = rho[k-1]/pAp[k]; x += alpha*p; r += (-alpha)*Ap; rho[k] = r.r   (CGSolver.c:126-128 + :112 of the
 // next iteration, which reads the same r)
 __global__ void __launch_bounds__(kVecThreads)
-cgUpdateXRKernel(uint32_t n, int k, double* __restrict__ rho, const double* __restrict__ pAp, double* __restrict__ x,
+cgUpdateXRKernel(uint32_t n, int k, double* rho, double* pAp, double* __restrict__ x,
     double* __restrict__ r, const double* __restrict__ p, const double* __restrict__ Ap, double* partials,
-    unsigned int* ticket)
+    unsigned int* ticket, PeerReduce collectPAp, PeerReduce pushRho)
 {
   __shared__ double scratch[32];
+  __shared__ double peerVals[kMaxRanks];
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  const double alpha = __ddiv_rn(rho[k - 1], pAp[k]);
+  double pApK;
+  if (collectPAp.size > 0) {                         // multi-GPU: p.Ap was pushed to the peer windows by the SpMV
+    pApK = peerCollect(collectPAp, peerVals);
+    if (tid == 0) pAp[k] = pApK;
+  } else {
+    pApK = pAp[k];
+  }
+  const double alpha = __ddiv_rn(rho[k - 1], pApK);
   const double nalpha = -alpha;
   const uint64_t n2 = n / 2;
   double2* x2 = reinterpret_cast<double2*>(x);
@@ -211,27 +231,28 @@ cgUpdateXRKernel(uint32_t n, int k, double* __restrict__ rho, const double* __re
     acc = fma(ro, ro, acc);
   }
   const double b = blockSum(acc, scratch);
-  gridSum(b, partials, ticket, rho + k, false, scratch);
+  gridSum(b, partials, ticket, rho + k, false, scratch, pushRho.size ? &pushRho : nullptr);
 }
 
-void launchCgUpdateP(uint32_t n, int k, const double* rho, const double* r, double* p, cudaStream_t s)
+void launchCgUpdateP(uint32_t n, int k, double* rho, const double* r, double* p, const PeerReduce* collectRho, cudaStream_t s)
 {
-  if (n == 0) return;
-  cgUpdatePKernel<<<vecGrid(n, 2 * kVecUnroll), kVecThreads, 0, s>>>(n, k, rho, r, p);
+  if (n == 0 && !collectRho) return;
+  cgUpdatePKernel<<<vecGrid(n, 2 * kVecUnroll), kVecThreads, 0, s>>>(n, k, rho, r, p, collectRho ? *collectRho : PeerReduce());
   SB_CUDA(cudaGetLastError());
   countLaunch();
 }
 
-void launchCgUpdateXR(uint32_t n, int k, double* rho, const double* pAp, double* x, double* r, const double* p,
-    const double* Ap, int slot, cudaStream_t s)
+void launchCgUpdateXR(uint32_t n, int k, double* rho, double* pAp, double* x, double* r, const double* p,
+    const double* Ap, int slot, const PeerReduce* collectPAp, const PeerReduce* pushRho, cudaStream_t s)
 {
   Context& c = ctx();
-  if (n == 0) {
+  if (n == 0 && !collectPAp && !pushRho) {
     SB_CUDA(cudaMemsetAsync(rho + k, 0, sizeof(double), s));
     return;
   }
   cgUpdateXRKernel<<<vecGrid(n, 4), kVecThreads, 0, s>>>(n, k, rho, pAp, x, r, p, Ap,
-      c.partials + (size_t)slot * kMaxPartials, c.tickets + slot);
+      c.partials + (size_t)slot * kMaxPartials, c.tickets + slot, collectPAp ? *collectPAp : PeerReduce(),
+      pushRho ? *pushRho : PeerReduce());
   SB_CUDA(cudaGetLastError());
   countLaunch();
 }
