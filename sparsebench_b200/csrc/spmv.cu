@@ -45,23 +45,50 @@ static bool useLegacyKernels()
 // tmp[k] += val*x of matrix-SCS.c:216-222 (bit-identical row sums).
 // Chunk lengths / offsets of a warp's next 32 chunks live one per lane and are broadcast by shuffle, so the
 // metadata loads are off the critical path.
-// Device-side wait on a HaloGate (sb_internal.h): arrival counters written by the peers' put kernels.
-__device__ __forceinline__ void gateWait(const HaloGate& gate, int who)
+// x gather. Plain kernels use the read-only path (ld.global.nc). Gated kernels read halo values that peers store
+// WHILE the kernel runs: those loads must be coherent ones -- then the acquire on the arrival counter plus the
+// block / warp barrier behind it orders them after the peers' stores (ld.global.nc gives no such guarantee).
+template <bool COHERENT>
+__device__ __forceinline__ double gatherX(const double* p)
 {
-  const unsigned long long* p = gate.flag[who];
-  unsigned long long v;
-  const long long start = clock64();
-  for (;;) {
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    if (v >= gate.target) break;
-    __nanosleep(40);
-    if (clock64() - start > 40000000000ll) __trap();   // dead peer: fail instead of hanging the GPU
+  if (COHERENT) {
+    double v;
+    asm("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+  }
+  return __ldg(p);
+}
+
+// Device-side wait on a HaloGate (sb_internal.h): arrival counters written by the peers' put kernels.
+// The gate's counter addresses are parked in shared memory at kernel start (statically indexed copy of the kernel
+// parameter), so that the wait itself is a small dynamic loop that costs the hot path no registers.
+struct GateSmem {
+  const unsigned long long* flag[kMaxGateSources];
+};
+__device__ __forceinline__ void gateStore(GateSmem& g, const HaloGate& gate)
+{
+#pragma unroll
+  for (int i = 0; i < kMaxGateSources; i++) g.flag[i] = gate.flag[i];
+}
+// Called by ONE thread.
+__device__ __noinline__ void gateWait(const GateSmem* g, int nsrc, unsigned long long target)
+{
+  for (int i = 0; i < nsrc; i++) {
+    const unsigned long long* p = g->flag[i];
+    unsigned long long v;
+    const long long start = clock64();
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+      if (v >= target) break;
+      __nanosleep(40);
+      if (clock64() - start > 40000000000ll) __trap();   // dead peer: fail instead of hanging the GPU
+    }
   }
 }
 
 // GATED launches cover all chunks in one go, rotated so that the `nInterior` chunks that reference no halo column
-// come first; before the CTA's first step outside that range it waits for the halo (gateWait) and from then on
-// gathers x with ld.global.cg, because the peers store those values while this kernel is already running.
+// come first; before the CTA's first step outside that range it waits for the halo (gateWait). All x gathers of a
+// gated kernel are coherent loads (gatherX), because the peers store halo values while it is already running.
 template <bool DOT, int WARPS, int J, int S, int U, bool LOCKSTEP, bool GATED>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 spmvSell32TmaKernel(SellView A, const double* __restrict__ x, double* __restrict__ y, uint32_t lo, uint32_t hi,
@@ -71,11 +98,13 @@ spmvSell32TmaKernel(SellView A, const double* __restrict__ x, double* __restrict
   extern __shared__ __align__(128) unsigned char ring[];
   __shared__ double scratch[32];
   __shared__ uint64_t bars[WARPS * S];
+  __shared__ GateSmem gateSmem;
   constexpr uint32_t kStageBytes = J * 32 * 12;
   constexpr uint32_t kFull = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char* mine = ring + (size_t)warp * S * kStageBytes;
   uint64_t* bar = bars + warp * S;
+  if (GATED && threadIdx.x == 0) gateStore(gateSmem, gate);
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < S; s++) mbarInit(bar + s, 1);
@@ -142,7 +171,7 @@ spmvSell32TmaKernel(SellView A, const double* __restrict__ x, double* __restrict
     if (GATED) {
       useCg = ctaFirst + step * stride + WARPS > (uint64_t)nInterior;   // CTA-uniform: some warp is past the interior
       if (useCg && !gatePassed) {
-        if ((int)threadIdx.x < gate.nsrc) gateWait(gate, threadIdx.x);
+        if (threadIdx.x == 0) gateWait(&gateSmem, gate.nsrc, gate.target);
         __syncthreads();
         gatePassed = true;
       }
@@ -170,15 +199,9 @@ spmvSell32TmaKernel(SellView A, const double* __restrict__ x, double* __restrict
       for (uint32_t j = 0; j < (uint32_t)J; j += U) {
         if (j < cols) {                              // warp-uniform
           double xx[U], vv[U];
-          if (GATED && useCg) {
 #pragma unroll
-            for (int u = 0; u < U; u++)
-              if (j + u < cols) xx[u] = __ldcg(x + c[(j + u) * 32]);
-          } else {
-#pragma unroll
-            for (int u = 0; u < U; u++)
-              if (j + u < cols) xx[u] = __ldg(x + c[(j + u) * 32]);
-          }
+          for (int u = 0; u < U; u++)
+            if (j + u < cols) xx[u] = gatherX<GATED>(x + c[(j + u) * 32]);
 #pragma unroll
           for (int u = 0; u < U; u++)
             if (j + u < cols) vv[u] = v[(j + u) * 32];
@@ -406,7 +429,7 @@ struct CcrsPipe {                                       // stage: {col, pad, val
 
 // GATED launches cover all rows in one go as three runs of tiles: the interior rows [intLo, intHi) first, then the
 // rows above and below, which reference halo columns; a consumer warp waits on the gate before its first tile of
-// those (and gathers x with ld.global.cg from there on: the peers store the halo while this kernel is running).
+// those (x gathers of a gated kernel are coherent loads: the peers store the halo while this kernel is running).
 template <bool DOT, int LPR, typename L, bool GATED>
 __global__ void __launch_bounds__((L::kWarps + 1) * 32, 1)
 spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __restrict__ x, double* __restrict__ y,
@@ -416,12 +439,14 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
   extern __shared__ __align__(128) unsigned char ring[];
   __shared__ double scratch[32];
   __shared__ uint64_t fullBar[L::kStages], emptyBar[L::kStages];
+  __shared__ GateSmem gateSmem;
   constexpr uint32_t S = L::kStages;
   constexpr int kPipeWarps = L::kWarps;
   constexpr int UN = 8;                                  // elements per lane per batch
   constexpr int GPW = 32 / LPR;                          // rows per warp per pass
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
+    if (GATED) gateStore(gateSmem, gate);
     for (uint32_t s = 0; s < S; s++) {
       mbarInit(fullBar + s, 1);
       mbarInit(emptyBar + s, kPipeWarps);
@@ -482,7 +507,7 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
       const bool useCg = tileRange(t, r0, r1);
       const uint32_t nrows = (uint32_t)(r1 - r0);
       if (GATED && useCg && !gatePassed) {
-        if (lane < gate.nsrc) gateWait(gate, lane);
+        if (lane == 0) gateWait(&gateSmem, gate.nsrc, gate.target);
         __syncwarp();
         gatePassed = true;
       }
@@ -507,15 +532,9 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
 #pragma unroll
             for (int u = 0; u < UN; u++)
               if (idx + u * LPR < end) L::fetch(st, idx + u * LPR, cc[u], vv[u]);
-            if (GATED && useCg) {
 #pragma unroll
-              for (int u = 0; u < UN; u++)
-                if (idx + u * LPR < end) xx[u] = __ldcg(x + cc[u]);
-            } else {
-#pragma unroll
-              for (int u = 0; u < UN; u++)
-                if (idx + u * LPR < end) xx[u] = __ldg(x + cc[u]);
-            }
+            for (int u = 0; u < UN; u++)
+              if (idx + u * LPR < end) xx[u] = gatherX<GATED>(x + cc[u]);
 #pragma unroll
             for (int u = 0; u < UN; u++)
               if (idx + u * LPR < end) sum = mulAdd(sum, vv[u], xx[u]);
@@ -526,7 +545,7 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
             uint32_t c;
             double v;
             acc.fetchGlobal(j, c, v);
-            sum = mulAdd(sum, v, (GATED && useCg) ? __ldcg(x + c) : __ldg(x + c));
+            sum = mulAdd(sum, v, gatherX<GATED>(x + c));
           }
         }
 #pragma unroll

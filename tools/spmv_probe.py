@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--sigma", type=int, default=256)
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--dirty", action="store_true")
+    ap.add_argument("--ordered", action="store_true")
     ap.add_argument("--cg", type=int, default=0, help="also run this many fused CG iterations")
     a = ap.parse_args()
     L = api.lib()
@@ -50,6 +51,16 @@ def main():
     ms, med = min(times), sorted(times)[len(times) // 2]
     print("spmv %s %d^2x%d: min %.4f ms (%.1f GB/s, %.1f GFLOP/s)  median %.4f  back-to-back %.4f ms (%.1f GB/s)  first %.4f"
           % (a.fmt, n, nz, ms, B / ms / 1e6, 2 * nnz / ms / 1e6, med, blk, B / blk / 1e6, times[0]))
+    if a.ordered:
+        units = A.nChunks if a.fmt == "SCS" else A.nr
+        plane = (n * n) // (32 if a.fmt == "SCS" else 1)
+        for (lo, hi) in ((0, units), (plane, units - plane)):
+            times = []
+            for i in range(a.reps):
+                t.start()
+                L.sbSpmvOrdered(C.byref(A), fmt, x.ptr, y.ptr, lo, hi)
+                times.append(t.stop_ms())
+            print("ordered single-launch kernel, interior [%d,%d): min %.4f median %.4f ms" % (lo, hi, min(times), sorted(times)[len(times) // 2]))
     if a.dirty:
         # the CG context: a vector update that leaves x dirty in L2 right before every SpMV
         r = api.to_device(np.zeros(N))
