@@ -389,10 +389,19 @@ struct CrsPipe {                                        // stage: val[CAP+8] | c
     bulkLoad(dst, val + a, n * 8, bar);
     bulkLoad(dst + kColOff, col + a, n * 4, bar);
   }
+  static constexpr bool kSplitFetch = true;             // column ids first: they die once their gather is issued
   __device__ __forceinline__ static void fetch(const unsigned char* st, uint32_t i, uint32_t& c, double& v)
   {
     v = reinterpret_cast<const double*>(st)[i];
     c = reinterpret_cast<const uint32_t*>(st + kColOff)[i];
+  }
+  __device__ __forceinline__ static uint32_t fetchCol(const unsigned char* st, uint32_t i)
+  {
+    return reinterpret_cast<const uint32_t*>(st + kColOff)[i];
+  }
+  __device__ __forceinline__ static double fetchVal(const unsigned char* st, uint32_t i)
+  {
+    return reinterpret_cast<const double*>(st)[i];
   }
   __device__ __forceinline__ void fetchGlobal(uint64_t j, uint32_t& c, double& v) const
   {
@@ -413,11 +422,20 @@ struct CcrsPipe {                                       // stage: {col, pad, val
   {
     bulkLoad(dst, entries + s, (uint32_t)(e - s) * 16, bar);
   }
+  static constexpr bool kSplitFetch = false;            // one LDS.128 per record beats two narrower reads
   __device__ __forceinline__ static void fetch(const unsigned char* st, uint32_t i, uint32_t& c, double& v)
   {
-    const double2 e = reinterpret_cast<const double2*>(st)[i];   // one 16-byte record
+    const double2 e = reinterpret_cast<const double2*>(st)[i];   // one 16-byte {col, pad, val} record
     c = (uint32_t)__double_as_longlong(e.x);
     v = e.y;
+  }
+  __device__ __forceinline__ static uint32_t fetchCol(const unsigned char* st, uint32_t i)
+  {
+    return reinterpret_cast<const uint32_t*>(st)[4 * i];
+  }
+  __device__ __forceinline__ static double fetchVal(const unsigned char* st, uint32_t i)
+  {
+    return reinterpret_cast<const double*>(st)[2 * i + 1];
   }
   __device__ __forceinline__ void fetchGlobal(uint64_t j, uint32_t& c, double& v) const
   {
@@ -527,14 +545,23 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
           uint32_t idx = live ? rs - (uint32_t)org + sub : 0u;
           const uint32_t end = live ? re - (uint32_t)org : 0u;
           while (__any_sync(0xffffffffu, idx < end)) {
-            uint32_t cc[UN];
             double vv[UN], xx[UN];
+            if constexpr (L::kSplitFetch) {
 #pragma unroll
-            for (int u = 0; u < UN; u++)
-              if (idx + u * LPR < end) L::fetch(st, idx + u * LPR, cc[u], vv[u]);
+              for (int u = 0; u < UN; u++)
+                if (idx + u * LPR < end) xx[u] = gatherX<GATED>(x + L::fetchCol(st, idx + u * LPR));
 #pragma unroll
-            for (int u = 0; u < UN; u++)
-              if (idx + u * LPR < end) xx[u] = gatherX<GATED>(x + cc[u]);
+              for (int u = 0; u < UN; u++)
+                if (idx + u * LPR < end) vv[u] = L::fetchVal(st, idx + u * LPR);
+            } else {
+              uint32_t cc[UN];
+#pragma unroll
+              for (int u = 0; u < UN; u++)
+                if (idx + u * LPR < end) L::fetch(st, idx + u * LPR, cc[u], vv[u]);
+#pragma unroll
+              for (int u = 0; u < UN; u++)
+                if (idx + u * LPR < end) xx[u] = gatherX<GATED>(x + cc[u]);
+            }
 #pragma unroll
             for (int u = 0; u < UN; u++)
               if (idx + u * LPR < end) sum = mulAdd(sum, vv[u], xx[u]);
@@ -552,7 +579,7 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
         for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         if (live && sub == 0) {
           y[r0 + g] = sum;
-          if (DOT) dotAcc = fma(sum, __ldg(x + r0 + g), dotAcc);
+          if (DOT) dotAcc = fma(sum, __ldg(x + r0 + g), dotAcc);   // L1 hit: the row's own diagonal was just gathered
         }
       }
       __syncwarp();
