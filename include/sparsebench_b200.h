@@ -26,8 +26,14 @@
 extern "C" {
 #endif
 
-typedef unsigned int CG_UINT;   /* util.h:35-38 (UINT_TYPE=1) */
-typedef double CG_FLOAT;        /* util.h:49-52 (PRECISION=2) */
+/* util.h:35-53 defines CG_UINT / CG_FLOAT as macros (UINT_TYPE=1, PRECISION=2); when the reference's util.h was
+ * included first (a reference translation unit compiled against this header, see integration/), those are used */
+#ifndef CG_UINT
+typedef unsigned int CG_UINT;
+#endif
+#ifndef CG_FLOAT
+typedef double CG_FLOAT;
+#endif
 
 /* ---------------------------------------------------------------- data structures */
 typedef struct {                /* matrix.h:24-27 (16 bytes: 4 B padding after col) */
@@ -106,12 +112,14 @@ typedef struct {                /* matrix.h:43-49 */
   MMEntry* entries;
 } MMMatrix;
 
+#ifndef __PARAMETER_H_           /* the reference's own parameter.h (identical layout) wins when it was included first */
 typedef struct {                /* parameter.h:8-13 */
   char* filename;
   int nx, ny, nz;
   int itermax;
   double eps;
 } Parameter;
+#endif
 
 enum { SB_MAX = 0, SB_SUM = 1 };   /* comm.h:25 `enum op { MAX = 0, SUM }` */
 
@@ -226,6 +234,8 @@ int sbCGFinish(void* solver, SbCGInfo* info, double loopMs);
 
 /* ---------------------------------------------------------------- communication (comm.c) */
 void commInit(Comm* c, int argc, char** argv);                                /* comm.h:48, comm.c:863-878 */
+void commPrintBanner(Comm* c);                                                /* comm.h:59, comm.c:185-274 (one line per rank: GPU instead of CPU affinity) */
+void commAbort(Comm* c, char* msg);                                           /* comm.h:60, comm.c:880-891: finalize + exit(EXIT_SUCCESS) */
 void commFinalize(Comm* c);                                                   /* comm.h:49, comm.c:893-910 */
 void commPartition(Comm* c, GMatrix* m);                                      /* comm.h:51, comm.c:414-625 */
 void commExchange(Comm* c, CG_UINT numRows, CG_FLOAT* x);                     /* comm.h:57, comm.c:627-651 */

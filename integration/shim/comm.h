@@ -1,0 +1,21 @@
+/* Stand-in for the reference's src/comm.h, src/matrix.h and src/solver.h: lets UNMODIFIED reference translation
+ * units (main.c, profiler.c) compile against include/sparsebench_b200.h. It is force-included (gcc -include) ahead of
+ * everything else and claims the include guards of the three headers it replaces, so that the reference's own copies
+ * -- found first by #include "..." because they sit next to main.c -- expand to nothing. */
+#ifndef SB200_SHIM_COMM_H
+#define SB200_SHIM_COMM_H
+#define __COMM_H_
+#define __MATRIX_H_
+#define __SOLVER_H_
+#include "parameter.h" /* the reference's own (no shim of that name): its Parameter typedef wins */
+#include "util.h"      /* the reference's own: CG_UINT / CG_FLOAT macros, HLINE */
+#include "sparsebench_b200.h"
+
+enum op { MAX = 0, SUM };                                  /* comm.h:25 */
+static inline int commIsMaster(Comm* c) { return c->rank == 0; }   /* comm.h:62 */
+static inline void commBarrier(void)                       /* comm.h:63-68 */
+{
+  double zero = 0.0;
+  commReduction(&zero, SUM);
+}
+#endif

@@ -373,8 +373,31 @@ int sbSolveCG(Comm* comm, Parameter* param, void* matrix, int fmt, SbCGInfo* inf
   return k;
 }
 
-int sbCRS_solveCG(Comm* comm, Parameter* param, SbCRSMatrix* m) { return sbSolveCG(comm, param, m, SB_FMT_CRS, nullptr); }
-int sbSCS_solveCG(Comm* comm, Parameter* param, SbSCSMatrix* m) { return sbSolveCG(comm, param, m, SB_FMT_SCS, nullptr); }
-int sbCCRS_solveCG(Comm* comm, Parameter* param, SbCCRSMatrix* m) { return sbSolveCG(comm, param, m, SB_FMT_CCRS, nullptr); }
+// The reference accumulates wall time per region in the global _t[] of its profiler.c (profiler.c:17,
+// profiler.h:18-24: WAXPBY, SPMVM, DDOT, COMM) from PROFILE() macros inside CGSolver.c, and its profilerPrint turns
+// them into MB/s and MFlop/s. CGSolver.c is replaced by this file, so when the program contains that array (weak
+// reference: only then) the drop-in solveCG fills it from CUDA-event times of its own kernels. The dot products are
+// fused into the vector and SpMV kernels here and have no time of their own: the vector-kernel time is split
+// 24:16 between WAXPBY and DDOT like the reference's own per-iteration byte model (profiler.c:19-22).
+extern double _t[4] __attribute__((weak));
+
+static int solveDropIn(Comm* comm, Parameter* param, void* m, int fmt)
+{
+  if (!&_t[0]) return sbSolveCG(comm, param, m, fmt, nullptr);
+  SbCGInfo info;
+  memset(&info, 0, sizeof(info));
+  info.flags = SB_CG_FUSED | SB_CG_PRINT | SB_CG_PROFILE;
+  const int k = sbSolveCG(comm, param, m, fmt, &info);
+  const double vec = (info.regionMs[SB_REGION_UPDATE_P] + info.regionMs[SB_REGION_UPDATE_XR]) * 1e-3;
+  _t[0] += vec * 0.6;
+  _t[2] += vec * 0.4;
+  _t[1] += (info.regionMs[SB_REGION_SPMV] + info.regionMs[SB_REGION_SPMV_BOUNDARY]) * 1e-3;
+  _t[3] += (info.regionMs[SB_REGION_EXCHANGE] + info.regionMs[SB_REGION_HALO_WAIT] + info.regionMs[SB_REGION_ALLREDUCE]) * 1e-3;
+  return k;
+}
+
+int sbCRS_solveCG(Comm* comm, Parameter* param, SbCRSMatrix* m) { return solveDropIn(comm, param, m, SB_FMT_CRS); }
+int sbSCS_solveCG(Comm* comm, Parameter* param, SbSCSMatrix* m) { return solveDropIn(comm, param, m, SB_FMT_SCS); }
+int sbCCRS_solveCG(Comm* comm, Parameter* param, SbCCRSMatrix* m) { return solveDropIn(comm, param, m, SB_FMT_CCRS); }
 
 } // extern "C"

@@ -712,6 +712,40 @@ void commInit(Comm* c, int argc, char** argv)
   attach(c, rank, size, local % ndev, &id);
 }
 
+void commPrintBanner(Comm* c)
+{
+  // comm.c:185-274 prints the build configuration and where every rank runs (host, pid, CPU affinity mask); here
+  // the interesting placement is the GPU of every rank
+  cudaDeviceProp prop;
+  int dev = 0;
+  SB_CUDA(cudaGetDevice(&dev));
+  SB_CUDA(cudaGetDeviceProperties(&prop, dev));
+  char host[256] = "";
+  gethostname(host, sizeof(host) - 1);
+  if (c->rank == 0) {
+    printf("sparsebench_b200: CUDA hot path for sm_100a, double precision floats and integer type unsigned int\n");
+    if (c->size > 1) printf("One process per GPU using %d ranks, transport: %s\n", c->size, commPeerMode(c) ? "NVLink peer windows" : "NCCL");
+  }
+  for (int i = 0; i < c->size; i++) {
+    if (i == c->rank) {
+      printf("Process with rank %d running on Node %s with pid %d on GPU %d (%s, %d SMs)\n", c->rank, host, (int)getpid(), dev,
+          prop.name, prop.multiProcessorCount);
+      fflush(stdout);
+    }
+    if (c->size > 1) {
+      double z = 0.0;
+      commReduction(&z, SB_SUM);                          // commBarrier() of comm.c:211,219
+    }
+  }
+}
+
+void commAbort(Comm* c, char* msg)
+{
+  if (c->rank == 0 && msg) printf("%s\n", msg);           // comm.c:880-891
+  commFinalize(c);
+  exit(EXIT_SUCCESS);
+}
+
 void commFinalize(Comm* c)
 {
   free(c->sources); free(c->recvCounts); free(c->rdispls);          // comm.c:896-903
