@@ -198,6 +198,15 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly ONE line, the JSON result: native libraries (NCCL's version banner, the reference's
+    # printf) write to file descriptor 1 directly, so fd 1 is pointed at stderr for the run and the line goes to a
+    # private duplicate of the original stdout
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(result_fd, (json.dumps(obj) + "\n").encode())
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -218,7 +227,7 @@ def main():
             return 0
         r = reference_arm(args, nx, ny, nz, desc, world)
         if r is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_CRS_fast.so was not built"}))
+            emit({"impl": "reference", "unavailable": "oracle/_ref/libref_CRS_fast.so was not built"})
             return 0
         gf = r["value"] * flops_it_job / 1e9
         line = {"impl": "reference", "metric": metric, "value": gf, "unit": unit, "n_gpus": args.gpus, "steps": K,
@@ -230,7 +239,7 @@ def main():
                 "e2e": {"value": gf, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "cg": {"iterations_per_sec": r["value"]},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -436,7 +445,7 @@ def main():
                    "frac_of_peak": B_it / (ms / K * 1e-3) / 1e9 / peak, "kernel_ms_per_iteration": region,
                    "residual_initial": resid0, "residual_final": resid, "max_error_vs_xexact": info.maxError},
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         L.commFinalize(C.byref(comm))
         dist.destroy_process_group()

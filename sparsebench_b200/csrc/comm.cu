@@ -84,7 +84,6 @@ struct CommExt {
   std::vector<double*> peerHalo;
   PutPlan* dPut = nullptr;
   WaitPlan* dWait = nullptr;
-  unsigned int* dTickets = nullptr;
   unsigned long long haloSeq = 0, redEpoch = 0;
   // registered halo vector (direct delivery)
   std::vector<double*> peerVec;
@@ -190,8 +189,6 @@ static void attach(Comm* c, int rank, int size, int device, const ncclUniqueId* 
   SB_NCCL(ncclCommInitRank(&e->nccl, size, *id, rank));
   e->dScalar = (double*)allocate(64, sizeof(double) * 8);
   e->hScalar = (double*)sbAllocateHost(sizeof(double) * 8);
-  e->dTickets = (unsigned int*)allocate(64, sizeof(unsigned int) * 4);
-  SB_CUDA(cudaMemset(e->dTickets, 0, sizeof(unsigned int) * 4));
   c->communicator = e;
   g_world = e;
   // SB_COMM=nccl keeps every exchange on NCCL (the measured baseline); default: NVLink peer windows
@@ -763,7 +760,6 @@ void commFinalize(Comm* c)
       sbFree(e->ctrl);
       sbFree(e->dPeerCtrl);
     }
-    sbFree(e->dTickets);
     sbFree(e->dScalar);
     sbFreeHost(e->hScalar);
     ncclCommDestroy(e->nccl);

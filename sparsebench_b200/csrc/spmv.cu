@@ -162,15 +162,15 @@ spmvSell32TmaKernel(SellView A, const double* __restrict__ x, double* __restrict
   int cs = 0;
   uint32_t phases = 0;
   double dotAcc = 0.0;
-  bool gatePassed = false, useCg = false;
+  bool gatePassed = false;
   // LOCKSTEP: the CTA's warps advance one chunk each per step and meet at a barrier, so that they keep working on
   // 32*WARPS consecutive rows (one shared window of x in L1) instead of drifting apart
   const uint64_t nSteps = ctaFirst < n ? (n - ctaFirst + stride - 1) / stride : 0;
   for (uint64_t step = 0; step < nSteps; step++, cT++) {
     const uint64_t lchunk = first + step * stride;
     if (GATED) {
-      useCg = ctaFirst + step * stride + WARPS > (uint64_t)nInterior;   // CTA-uniform: some warp is past the interior
-      if (useCg && !gatePassed) {
+      // CTA-uniform: is some warp of this step past the interior chunks?
+      if (!gatePassed && ctaFirst + step * stride + WARPS > (uint64_t)nInterior) {
         if (threadIdx.x == 0) gateWait(&gateSmem, gate.nsrc, gate.target);
         __syncthreads();
         gatePassed = true;
@@ -522,9 +522,9 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
     for (uint64_t t = blockIdx.x; t < nTiles; t += gridDim.x, i++) {
       const uint32_t s = i % S, k = i / S;
       uint64_t r0, r1;
-      const bool useCg = tileRange(t, r0, r1);
+      const bool behindGate = tileRange(t, r0, r1);
       const uint32_t nrows = (uint32_t)(r1 - r0);
-      if (GATED && useCg && !gatePassed) {
+      if (GATED && behindGate && !gatePassed) {
         if (lane == 0) gateWait(&gateSmem, gate.nsrc, gate.target);
         __syncwarp();
         gatePassed = true;
