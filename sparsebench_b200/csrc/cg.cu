@@ -32,6 +32,7 @@ struct CgSolver {
   int itermax = 0, flags = 0, printFreq = 1;
   bool fused = true, print = false, generated = false, profile = false, overlap = true, gated = false;
   bool fusedReduce = false;                // multi-GPU: all-reduces split into push (producer) / collect (consumer)
+  bool fusedPut = false;                   // multi-GPU: the p update stores boundary values straight into the neighbours' p
   PeerReduce pendingRho;                   // epoch of the newest rho that has been pushed but not yet collected
   int* elemsPerm = nullptr;                // SELL with a row permutation: elementsToSend in solver (permuted) numbering
   uint32_t intLo = 0, intHi = 0;           // SpMV units [intLo, intHi) reference no halo column
@@ -71,12 +72,13 @@ struct CgSolver {
   // commExchange + spMVM (CGSolver.c:95-96,122-123). With the peer-window transport my boundary values are stored
   // straight behind the neighbours' copy of p, and ONE SpMV launch multiplies the rows that reference no halo
   // column while those stores are in flight, waits on the arrival counters, and finishes with the boundary rows.
-  void spmvWithHalo(const DotArgs* dot)
+  void spmvWithHalo(const DotArgs* dot, const HaloGate* already = nullptr)
   {
     const uint32_t units = spmvUnits(A);
     if (commActive(comm)) {
       if (gated) {
-        const HaloGate gate = commHaloPutDirect(comm, p, elemsPerm, s);
+        // `already`: the p update itself delivered the halo (FusedPut); otherwise a put kernel does
+        const HaloGate gate = already ? *already : commHaloPutDirect(comm, p, elemsPerm, s);
         mark(R_EXCHANGE);
         launchSpmvGated(A, p, Ap, intLo, intHi, gate, dot, s);
         mark(R_SPMV);
@@ -168,8 +170,9 @@ struct CgSolver {
       if (commPeerMode(comm)) {
         const bool can = overlap && spmvGatedAvailable(A);
         if (can) spmvInteriorUnits(A, &intLo, &intHi, s);
-        gated = commAttachHaloVector(comm, p, A.nr, can);
+        gated = commAttachHaloVector(comm, p, A.nr, can, elemsPerm);
         fusedReduce = gated && fused && getenv("SB_NO_FUSED_REDUCE") == nullptr;
+        fusedPut = fusedReduce && commFusedPutAvailable(comm) && getenv("SB_NO_FUSED_PUT") == nullptr;
       }
     }
 
@@ -225,7 +228,10 @@ struct CgSolver {
         }
         if (fusedReduce) {
           // rho[k-1] is summed over the ranks inside the p update, p.Ap inside the x/r update: no all-reduce launches
-          launchCgUpdateP(n, k, rho, r, p, pendingRho.size ? &pendingRho : nullptr, s);   // :109 / :111-114
+          FusedPut fp;
+          HaloGate gate;
+          if (fusedPut) gate = commFusedPutBegin(comm, &fp);    // the halo exchange (:122) rides on the p update
+          launchCgUpdateP(n, k, rho, r, p, pendingRho.size ? &pendingRho : nullptr, fusedPut ? &fp : nullptr, s);   // :109 / :111-114
           mark(R_UPDATE_P);
           if (k >= 2) {                                         // the global rho[k-1] exists now: send it to the host
             SB_CUDA(cudaMemcpyAsync(hRho + k - 1, rho + k - 1, sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -233,13 +239,13 @@ struct CgSolver {
           }
           const PeerReduce prPAp = commBeginReduce(comm);
           DotArgs d { pAp + k, false, 1, &prPAp };
-          spmvWithHalo(&d);                                     // :122-125
+          spmvWithHalo(&d, fusedPut ? &gate : nullptr);         // :122-125
           pendingRho = commBeginReduce(comm);
           launchCgUpdateXR(n, k, rho, pAp, x, r, p, Ap, 2, &prPAp, &pendingRho, s);       // :126-128 (+ :112 of iteration k+1)
           mark(R_UPDATE_XR);
           continue;
         }
-        launchCgUpdateP(n, k, rho, r, p, nullptr, s);          // :109 / :111-114
+        launchCgUpdateP(n, k, rho, r, p, nullptr, nullptr, s); // :109 / :111-114
         mark(R_UPDATE_P);
         DotArgs d { pAp + k, false, 1 };
         spmvWithHalo(&d);                                      // :122-125

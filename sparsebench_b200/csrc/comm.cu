@@ -90,6 +90,8 @@ struct CommExt {
   PutPlan* dPutDirect = nullptr;
   unsigned long long directSeq = 0;
   bool attached = false;
+  FusedPut fused;                  // valid (ndest > 0) when the attached vector's sends fit kMaxFusedDests
+  std::vector<int*> fusedInv;      // device inverse maps owned by `fused`
 };
 
 static CommExt* g_world = nullptr;   // commReduction has no Comm* argument (it used MPI_COMM_WORLD, comm.c:653-662)
@@ -296,16 +298,18 @@ __device__ __forceinline__ void spinUntilAtLeast(const unsigned long long* p, un
 // number `seq` is complete at a receiver when its counter for this source has reached seq * kPutBlocks.
 constexpr int kPutBlocks = 32, kWaitBlocks = 32, kHaloThreads = 512;
 
-__device__ __forceinline__ void signalAddSys(unsigned long long* p)
+__device__ __forceinline__ void signalAddSys(unsigned long long* p, unsigned long long n = 1)
 {
-  asm volatile("red.release.sys.global.add.u64 [%0], 1;" ::"l"(p) : "memory");
+  asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(n) : "memory");
 }
 
 __global__ void __launch_bounds__(kHaloThreads)
 haloPutKernel(const PutPlan* __restrict__ plan, const int* __restrict__ elements, const double* __restrict__ x,
     unsigned long long seq, bool direct)
 {
+  __shared__ unsigned int stored[kMaxRanks];            // direct mode: elements this block delivered per destination
   const int nd = plan->ndest;
+  if ((int)threadIdx.x < kMaxRanks) stored[threadIdx.x] = 0;
   // the slot of parity seq&1 was last filled by exchange seq-2: wait until every receiver has drained that one
   if (!direct && (int)threadIdx.x < nd && seq > 2) spinUntilAtLeast(plan->ack[threadIdx.x], (seq - 2) * kWaitBlocks);
   __syncthreads();
@@ -328,12 +332,16 @@ haloPutKernel(const PutPlan* __restrict__ plan, const int* __restrict__ elements
         int d = 0;
         while (i >= plan->sdispl[d + 1]) d++;
         plan->remote[par][d][i - plan->sdispl[d]] = v[u];
+        if (direct) atomicAdd(&stored[d], 1u);
       }
     }
   }
   // the barrier orders every thread's stores before the signalling threads' release (cumulative, system scope)
   __syncthreads();
-  if ((int)threadIdx.x < nd) signalAddSys(plan->remoteFlag[threadIdx.x]);
+  if ((int)threadIdx.x < nd) {
+    if (!direct) signalAddSys(plan->remoteFlag[threadIdx.x]);
+    else if (stored[threadIdx.x]) signalAddSys(plan->remoteFlag[threadIdx.x], stored[threadIdx.x]);   // receivers count elements
+  }
 }
 
 // Receiver side: wait for every source's `seq`, copy the slot behind the local part of x, acknowledge.
@@ -534,7 +542,7 @@ void commHaloWait(Comm* c, uint32_t numRows, double* x, cudaStream_t s)
   }
 }
 
-bool commAttachHaloVector(Comm* c, double* x, uint32_t numRows, bool localOk)
+bool commAttachHaloVector(Comm* c, double* x, uint32_t numRows, bool localOk, const int* elements)
 {
   CommExt* e = ext(c);
   if (!e || e->mode != COMM_PEER) return false;
@@ -570,6 +578,32 @@ bool commAttachHaloVector(Comm* c, double* x, uint32_t numRows, bool localOk)
   put.sdispl[c->outdegree] = c->totalSendCount;
   e->dPutDirect = (PutPlan*)allocate(64, sizeof(PutPlan));
   sbCopyToDevice(e->dPutDirect, &put, sizeof(put));
+  // inverse maps for the delivery fused into the producing kernel: element -> position in the destination's halo
+  e->fused = FusedPut();
+  if (c->outdegree > 0 && c->outdegree <= kMaxFusedDests) {
+    std::vector<int> elems((size_t)c->totalSendCount);
+    if (elements) sbCopyToHost(elems.data(), elements, sizeof(int) * elems.size());
+    else memcpy(elems.data(), c->elementsToSend, sizeof(int) * elems.size());
+    e->fused.ndest = c->outdegree;
+    for (int i = 0; i < c->outdegree; i++) {
+      const int b = c->sdispls[i], cnt = c->sendCounts[i];
+      int lo = elems[(size_t)b], hi = elems[(size_t)b];
+      for (int j = 1; j < cnt; j++) {
+        lo = std::min(lo, elems[(size_t)(b + j)]);
+        hi = std::max(hi, elems[(size_t)(b + j)]);
+      }
+      std::vector<int> inv((size_t)(hi - lo + 1), -1);
+      for (int j = 0; j < cnt; j++) inv[(size_t)(elems[(size_t)(b + j)] - lo)] = j;
+      int* dInv = (int*)allocate(64, sizeof(int) * inv.size());
+      sbCopyToDevice(dInv, inv.data(), sizeof(int) * inv.size());
+      e->fusedInv.push_back(dInv);
+      e->fused.lo[i] = (uint32_t)lo;
+      e->fused.hi[i] = (uint32_t)hi;
+      e->fused.inv[i] = dInv;
+      e->fused.remote[i] = put.remote[0][i];
+      e->fused.remoteFlag[i] = put.remoteFlag[i];
+    }
+  }
   e->directSeq = 0;
   SB_CUDA(cudaMemset(e->ctrl->directFlag, 0, sizeof(e->ctrl->directFlag)));
   SB_CUDA(cudaDeviceSynchronize());
@@ -589,6 +623,9 @@ void commDetachHaloVector(Comm* c)
   e->peerVec.clear();
   sbFree(e->dPutDirect);
   e->dPutDirect = nullptr;
+  for (int* p : e->fusedInv) sbFree(p);
+  e->fusedInv.clear();
+  e->fused = FusedPut();
   ncclBarrier(e);
   e->attached = false;
 }
@@ -605,8 +642,33 @@ HaloGate commHaloPutDirect(Comm* c, const double* x, const int* elements, cudaSt
     countLaunch();
   }
   g.nsrc = c->indegree;
-  g.target = e->directSeq * kPutBlocks;
-  for (int i = 0; i < c->indegree; i++) g.flag[i] = &e->ctrl->directFlag[c->sources[i]];
+  for (int i = 0; i < c->indegree; i++) {
+    g.flag[i] = &e->ctrl->directFlag[c->sources[i]];
+    g.target[i] = e->directSeq * (unsigned long long)c->recvCounts[i];     // senders signal element counts
+  }
+  return g;
+}
+
+bool commFusedPutAvailable(const Comm* c)
+{
+  CommExt* e = ext(c);
+  return e && e->attached && (c->outdegree == 0 || e->fused.ndest > 0);
+}
+
+// The next exchange of the registered vector is performed by the caller's own kernel (FusedPut): returns what that
+// kernel needs and the gate the receiving SpMV waits on.
+HaloGate commFusedPutBegin(Comm* c, FusedPut* fp)
+{
+  CommExt* e = ext(c);
+  if (!e || !e->attached) SB_FATAL("commFusedPutBegin: no registered halo vector");
+  e->directSeq++;
+  *fp = e->fused;
+  HaloGate g;
+  g.nsrc = c->indegree;
+  for (int i = 0; i < c->indegree; i++) {
+    g.flag[i] = &e->ctrl->directFlag[c->sources[i]];
+    g.target[i] = e->directSeq * (unsigned long long)c->recvCounts[i];
+  }
   return g;
 }
 

@@ -91,6 +91,7 @@ struct Operator {
 };
 
 struct HaloGate;
+struct FusedPut;
 
 // Fused dot-product epilogue: *out = (accumulate ? *out : 0) + sum, reduced through scratch slot `slot` (0..3).
 struct DotArgs {
@@ -118,7 +119,8 @@ void launchDot(uint32_t n, const double* x, const double* y, double* dResult, in
 // fused CG passes: rho[j] = r_j.r_j, pAp[k] = p_k.Ap_k live on the device, k is the 1-based iteration
 // collect*: the scalar this kernel needs (rho[k-1] resp. pAp[k]) is still spread over the peer window and is summed
 // in the kernel's prologue; pushRho: rho[k] is pushed to the peers instead of being all-reduced by a separate kernel
-void launchCgUpdateP(uint32_t n, int k, double* rho, const double* r, double* p, const PeerReduce* collectRho, cudaStream_t s);
+void launchCgUpdateP(uint32_t n, int k, double* rho, const double* r, double* p, const PeerReduce* collectRho,
+    const FusedPut* put, cudaStream_t s);
 void launchCgUpdateXR(uint32_t n, int k, double* rho, double* pAp, double* x, double* r, const double* p,
     const double* Ap, int slot, const PeerReduce* collectPAp, const PeerReduce* pushRho, cudaStream_t s);
 void launchInitVectors(uint32_t n, const uint32_t* rowPtr, const uint32_t* rowLen, bool generated, double* x, double* b,
@@ -143,10 +145,23 @@ PeerReduce commBeginReduce(Comm* c);                       // next all-reduce ep
 constexpr int kMaxGateSources = 8;
 struct HaloGate {
   int nsrc = 0;                                            // 0: no gate
-  unsigned long long target = 0;
+  unsigned long long target[kMaxGateSources] = {};         // elements received from source i since the vector was attached
   const unsigned long long* flag[kMaxGateSources] = {};
 };
-bool commAttachHaloVector(Comm* c, double* x, uint32_t numRows, bool localOk);   // collective; false -> use commExchangeOnStream
+// The same delivery fused into the kernel that produces the values (the CG's p update): element e of the vector
+// goes to position inv[d][e - lo[d]] of destination d's halo (negative: not sent there).
+constexpr int kMaxFusedDests = 4;
+struct FusedPut {
+  int ndest = 0;                                           // 0: not in use
+  uint32_t lo[kMaxFusedDests] = {}, hi[kMaxFusedDests] = {};   // inclusive element range that holds everything sent to d
+  const int* inv[kMaxFusedDests] = {};
+  double* remote[kMaxFusedDests] = {};
+  unsigned long long* remoteFlag[kMaxFusedDests] = {};
+};
+// collective; false -> use commExchangeOnStream. `elements` overrides Comm.elementsToSend (device, solver numbering)
+bool commAttachHaloVector(Comm* c, double* x, uint32_t numRows, bool localOk, const int* elements);
+bool commFusedPutAvailable(const Comm* c);                           // few enough destinations for FusedPut
+HaloGate commFusedPutBegin(Comm* c, FusedPut* fp);                   // next exchange, performed by the caller's kernel
 void commDetachHaloVector(Comm* c);                                  // collective
 HaloGate commHaloPutDirect(Comm* c, const double* x, const int* elements, cudaStream_t s);   // returns the gate to wait on
 

@@ -64,17 +64,22 @@ __device__ __forceinline__ double gatherX(const double* p)
 // parameter), so that the wait itself is a small dynamic loop that costs the hot path no registers.
 struct GateSmem {
   const unsigned long long* flag[kMaxGateSources];
+  unsigned long long target[kMaxGateSources];
 };
 __device__ __forceinline__ void gateStore(GateSmem& g, const HaloGate& gate)
 {
 #pragma unroll
-  for (int i = 0; i < kMaxGateSources; i++) g.flag[i] = gate.flag[i];
+  for (int i = 0; i < kMaxGateSources; i++) {
+    g.flag[i] = gate.flag[i];
+    g.target[i] = gate.target[i];
+  }
 }
 // Called by ONE thread.
-__device__ __noinline__ void gateWait(const GateSmem* g, int nsrc, unsigned long long target)
+__device__ __noinline__ void gateWait(const GateSmem* g, int nsrc)
 {
   for (int i = 0; i < nsrc; i++) {
     const unsigned long long* p = g->flag[i];
+    const unsigned long long target = g->target[i];
     unsigned long long v;
     const long long start = clock64();
     for (;;) {
@@ -171,7 +176,7 @@ spmvSell32TmaKernel(SellView A, const double* __restrict__ x, double* __restrict
     if (GATED) {
       // CTA-uniform: is some warp of this step past the interior chunks?
       if (!gatePassed && ctaFirst + step * stride + WARPS > (uint64_t)nInterior) {
-        if (threadIdx.x == 0) gateWait(&gateSmem, gate.nsrc, gate.target);
+        if (threadIdx.x == 0) gateWait(&gateSmem, gate.nsrc);
         __syncthreads();
         gatePassed = true;
       }
@@ -525,7 +530,7 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
       const bool behindGate = tileRange(t, r0, r1);
       const uint32_t nrows = (uint32_t)(r1 - r0);
       if (GATED && behindGate && !gatePassed) {
-        if (lane == 0) gateWait(&gateSmem, gate.nsrc, gate.target);
+        if (lane == 0) gateWait(&gateSmem, gate.nsrc);
         __syncwarp();
         gatePassed = true;
       }

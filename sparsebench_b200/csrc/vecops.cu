@@ -131,9 +131,24 @@ constexpr int kVecUnroll = 4;
 
 // p = r + beta*p with beta = rho[k-1]/rho[k-2]  (CGSolver.c:111-114); k == 1: p = r + 0*r (:109).
 __global__ void __launch_bounds__(kVecThreads)
-cgUpdatePKernel(uint32_t n, int k, double* rho, const double* __restrict__ r, double* __restrict__ p, PeerReduce collectRho)
+cgUpdatePKernel(uint32_t n, int k, double* rho, const double* __restrict__ r, double* __restrict__ p, PeerReduce collectRho,
+    FusedPut put)
 {
   __shared__ double peerVals[kMaxRanks];
+  __shared__ unsigned int delivered[kMaxFusedDests];     // halo elements this block stored at each neighbour
+  if (put.ndest > 0 && threadIdx.x < kMaxFusedDests) delivered[threadIdx.x] = 0;
+  // multi-GPU: a freshly computed p[e] that a neighbour needs goes straight behind that neighbour's local rows
+  auto deliver = [&](uint32_t e, double v) {
+#pragma unroll
+    for (int d = 0; d < kMaxFusedDests; d++)
+      if (d < put.ndest && e >= put.lo[d] && e <= put.hi[d]) {
+        const int pos = __ldg(put.inv[d] + (e - put.lo[d]));
+        if (pos >= 0) {
+          put.remote[d][pos] = v;
+          atomicAdd(&delivered[d], 1u);
+        }
+      }
+  };
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   const uint64_t n2 = n / 2;
@@ -167,9 +182,26 @@ cgUpdatePKernel(uint32_t n, int k, double* rho, const double* __restrict__ r, do
         o.x = __dadd_rn(a[u].x, __dmul_rn(beta, b[u].x));
         o.y = __dadd_rn(a[u].y, __dmul_rn(beta, b[u].y));
         p2[i0 + u * stride] = o;
+        if (put.ndest > 0) {
+          const uint32_t e = (uint32_t)(2 * (i0 + u * stride));
+          deliver(e, o.x);
+          deliver(e + 1, o.y);
+        }
       }
   }
-  if (tid == 0 && (n & 1u)) p[n - 1] = __dadd_rn(r[n - 1], __dmul_rn(beta, k == 1 ? r[n - 1] : p[n - 1]));
+  if (tid == 0 && (n & 1u)) {
+    const double v = __dadd_rn(r[n - 1], __dmul_rn(beta, k == 1 ? r[n - 1] : p[n - 1]));
+    p[n - 1] = v;
+    if (put.ndest > 0) deliver(n - 1, v);
+  }
+  if (put.ndest > 0) {
+    // the barrier orders every thread's peer stores before the signalling threads' release (system scope)
+    __syncthreads();
+    if ((int)threadIdx.x < put.ndest && delivered[threadIdx.x] > 0)
+      asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(put.remoteFlag[threadIdx.x]),
+                   "l"((unsigned long long)delivered[threadIdx.x])
+                   : "memory");
+  }
 }
 
 // alpha = rho[k-1]/pAp[k]; x += alpha*p; r += (-alpha)*Ap; rho[k] = r.r   (CGSolver.c:126-128 + :112 of the
@@ -234,10 +266,12 @@ cgUpdateXRKernel(uint32_t n, int k, double* rho, double* pAp, double* __restrict
   gridSum(b, partials, ticket, rho + k, false, scratch, pushRho.size ? &pushRho : nullptr);
 }
 
-void launchCgUpdateP(uint32_t n, int k, double* rho, const double* r, double* p, const PeerReduce* collectRho, cudaStream_t s)
+void launchCgUpdateP(uint32_t n, int k, double* rho, const double* r, double* p, const PeerReduce* collectRho,
+    const FusedPut* put, cudaStream_t s)
 {
   if (n == 0 && !collectRho) return;
-  cgUpdatePKernel<<<vecGrid(n, 2 * kVecUnroll), kVecThreads, 0, s>>>(n, k, rho, r, p, collectRho ? *collectRho : PeerReduce());
+  cgUpdatePKernel<<<vecGrid(n, 2 * kVecUnroll), kVecThreads, 0, s>>>(n, k, rho, r, p, collectRho ? *collectRho : PeerReduce(),
+      put ? *put : FusedPut());
   SB_CUDA(cudaGetLastError());
   countLaunch();
 }
