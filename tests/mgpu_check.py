@@ -113,6 +113,47 @@ def main():
     if rank == 0:
         os.unlink(path)
 
+    # an irregular SPD matrix (random long-range couplings, 1..40 entries per row): every rank neighbours every other
+    # one, halo lists are not contiguous planes, the SELL sort really permutes rows, row lengths vary
+    rng = np.random.default_rng(7)
+    nI = 1500 + 37 * world
+    rowsets = [set([i]) for i in range(nI)]
+    for i in range(nI):
+        for j in rng.integers(0, nI, int(rng.integers(0, 20))):
+            rowsets[i].add(int(j)); rowsets[int(j)].add(i)
+        if i + 1 < nI:
+            rowsets[i].add(i + 1); rowsets[i + 1].add(i)
+    rp = np.zeros(nI + 1, np.uint32)
+    cols, vals = [], []
+    for i in range(nI):
+        cs = sorted(rowsets[i])
+        for c2 in cs:
+            cols.append(c2)
+            vals.append(float(len(rowsets[i]) + len(rowsets[c2])) if c2 == i else -1.0 / (1 + ((i + c2) % 3)))
+        rp[i + 1] = len(cols)
+    mi = orc.Csr(rp, np.array(cols, np.uint32), np.array(vals))
+    pathI = "/tmp/sb_mgpu_irregular_%d.mtx" % os.getppid()
+    if rank == 0:
+        with open(pathI, "w") as f:
+            f.write("%%%%MatrixMarket matrix coordinate real general\n%d %d %d\n" % (nI, nI, mi.nnz))
+            rowsI = np.repeat(np.arange(nI), np.diff(mi.rowPtr.astype(np.int64)))
+            for j in range(mi.nnz):
+                f.write("%d %d %r\n" % (rowsI[j] + 1, mi.col[j] + 1, float(mi.val[j])))
+    gI = api.matrixRead(pathI, comm)
+    loI = int(gI.startRow)
+    L.commPartition(C.byref(comm), C.byref(gI))
+    krefI, hrefI, xrefI = orc.cg_crs(mi, np.ones(nI), np.zeros(nI), 60, 1e-9)
+    for fmt, sigma in fmts + [(api.FMT_SCS, 64)]:
+        A = api.convertMatrix(fmt, gI, 32, sigma)
+        for flags in (api.CG_FUSED, api.CG_FUSED | api.CG_NO_OVERLAP):
+            k, hist, x, _ = api.solveCG(A, 60, 1e-9, comm=comm, generated=False, flags=flags, want_x=True)
+            ok = k == krefI and len(hist) == len(hrefI) and float(np.max(np.abs(hist - hrefI) / np.maximum(hrefI, 1e-10 * hrefI[0]))) <= CG_TOL
+            check(ok, "irregular: CG fmt=%s sigma=%d flags=%d k=%d/%d" % (api.FMT_NAMES[fmt], sigma, flags, k, krefI), failures)
+            check(float(np.max(np.abs(x - xrefI[loI:loI + gI.nr]))) <= 1e-9, "irregular: solution fmt=%s sigma=%d flags=%d" % (api.FMT_NAMES[fmt], sigma, flags), failures)
+        api.destroyMatrix(A)
+    if rank == 0:
+        os.unlink(pathI)
+
     # global reductions (comm.c:653-662)
     v = C.c_double(float(rank + 1))
     L.commReduction(C.byref(v), api.OP_SUM)
