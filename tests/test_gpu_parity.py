@@ -255,6 +255,24 @@ def test_cg_history_and_iteration_count(fmt, sigma, n, itermax, eps, flags):
     api.destroyMatrix(A)
 
 
+@pytest.mark.parametrize("fmt,sigma", [(api.FMT_CRS, 0), (api.FMT_SCS, 1), (api.FMT_SCS, 64), (api.FMT_SCS, 256), (api.FMT_CCRS, 0)])
+@pytest.mark.parametrize("n,extra", [(1574, 20), (3001, 6), (700, 60)])
+def test_cg_irregular_spd_matrix(fmt, sigma, n, extra):
+    """file-input rules (b = 1, CGSolver.c:34-36) on a matrix whose rows really get permuted by the SELL sort and whose
+    row lengths select different lanes-per-row variants of the CRS/CCRS kernel"""
+    from matrices import irregular_spd
+    m = irregular_spd(n, max_extra=extra)
+    kref, href, xref = orc.cg_crs(m, np.ones(n), np.zeros(n), 80, 1e-9)
+    g = api.gmatrix_from_csr(m.rowPtr, m.col, m.val)
+    A = make_matrix(fmt, g, sigma)
+    for flags in (api.CG_FUSED, 0):
+        k, hist, x, _ = api.solveCG(A, 80, 1e-9, generated=False, flags=flags, want_x=True)
+        assert k == kref
+        assert_history(hist, href)
+        assert np.max(np.abs(x - xref)) <= 1e-9
+    api.destroyMatrix(A)
+
+
 def test_cg_golden_transcripts(golden):
     """printed residuals of the reference's own solveCG (tests/golden/ref_vectors.npz)"""
     for (n, itermax, eps) in [(8, 12, 0.0), (16, 20, 1.0), (16, 60, 1e-6), (10, 150, 1e-9)]:
