@@ -242,6 +242,10 @@ void commExchange(Comm* c, CG_UINT numRows, CG_FLOAT* x);                     /*
 void commReduction(CG_FLOAT* v, int op);                                      /* comm.h:58, comm.c:653-662 (host scalar) */
 void sbCommAllreduceDevice(Comm* c, CG_FLOAT* dev, int count, int op);        /* the same reduction on device scalars, asynchronous */
 void commDistributeMatrix(Comm* c, MMMatrix* m, MMMatrix* mLocal);            /* comm.h:50, comm.c:311-412 */
+/* matrixBinfile.h:22-23 / matrixBinfile.c:38-236 -- .bmx files (24-byte header, u32 sizes and row offsets, {u32 col;
+ * f32 val} records); plain POSIX I/O instead of MPI-IO, every rank reads its own row block; host arrays */
+void matrixBinWrite(GMatrix* m, Comm* c, char* filename);
+void matrixBinRead(GMatrix* m, Comm* c, char* filename);
 /* bootstrap pieces used when another launcher (torchrun) already owns the rendezvous */
 int sbCommUniqueIdBytes(void);
 void sbCommGetUniqueId(void* id);

@@ -106,6 +106,8 @@ def lib():
         L.MMMatrixRead.argtypes = [C.POINTER(MMMatrix), C.c_char_p]
         L.matrixConvertfromMM.argtypes = [C.POINTER(MMMatrix), C.POINTER(GMatrix)]
         L.commDistributeMatrix.argtypes = [C.POINTER(Comm), C.POINTER(MMMatrix), C.POINTER(MMMatrix)]
+        L.matrixBinWrite.argtypes = [C.POINTER(GMatrix), C.POINTER(Comm), C.c_char_p]
+        L.matrixBinRead.argtypes = [C.POINTER(GMatrix), C.POINTER(Comm), C.c_char_p]
         for f in ("CRS", "SCS", "CCRS"):
             getattr(L, "sb%s_convertMatrix" % f).argtypes = [C.c_void_p, C.POINTER(GMatrix)]
             getattr(L, "sb%s_spMVM" % f).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]

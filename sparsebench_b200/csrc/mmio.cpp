@@ -129,3 +129,108 @@ void matrixConvertfromMM(MMMatrix* mm, GMatrix* m)
 }
 
 } // extern "C"
+
+// ------------------------------------------------------------------------------------------- .bmx binary files
+// Replaces matrixBinWrite / matrixBinRead (matrixBinfile.c:38-236), which go through MPI-IO. File layout, as that
+// code writes it: 24 bytes "# SparseBench DataFile" (NUL padded, :56-61), u32 totalNr, u32 totalNnz, u32
+// rowPtr[totalNr+1] (global entry offsets, :75-82), then totalNnz records {u32 col; f32 val} (:19-35, :92-103).
+// Values are float32 on disk. Every rank reads its own row block with plain POSIX I/O: rows split like sizeOfRank
+// (:14-17, :157-164), row pointers made local by subtracting the block's first entry offset (:189-205). Host arrays.
+// Parity note: the reference implementation needs an MPI library to compile, which this image does not have; these
+// two functions are pinned by the layout above (tests parse the file independently), not by a reference run.
+namespace {
+
+constexpr size_t kBmxHeader = 24;
+struct FEntry {               // matrixBinfile.h:11-14
+  unsigned int col;
+  float val;
+};
+
+void readExact(FILE* f, void* dst, size_t bytes, const char* what)
+{
+  if (fread(dst, 1, bytes, f) != bytes) {
+    printf("ERROR reading %s!\n", what);           // matrixBinfile.c:125-127,141-148
+    exit(EXIT_FAILURE);
+  }
+}
+
+} // namespace
+
+extern "C" {
+
+void matrixBinWrite(GMatrix* m, Comm* c, char* filename)
+{
+  if (c->size > 1) {
+    fprintf(stderr, "ERROR: Matrix writing only supported for single rank\n");   // matrixBinfile.c:42-45
+    return;
+  }
+  FILE* f = fopen(filename, "wb");
+  if (!f) {
+    fprintf(stderr, "ERROR: cannot open %s for writing\n", filename);
+    exit(EXIT_FAILURE);
+  }
+  printf("Writing matrix to %s\n", filename);
+  char header[kBmxHeader];
+  memset(header, 0, sizeof(header));
+  strncpy(header, "# SparseBench DataFile", sizeof(header) - 1);
+  const unsigned int totalNr = m->totalNr, totalNnz = m->rowPtr[m->nr];   // entries actually stored
+  bool ok = fwrite(header, 1, kBmxHeader, f) == kBmxHeader && fwrite(&totalNr, 4, 1, f) == 1 && fwrite(&totalNnz, 4, 1, f) == 1 &&
+            fwrite(m->rowPtr, 4, (size_t)totalNr + 1, f) == (size_t)totalNr + 1;
+  std::vector<FEntry> out((size_t)totalNnz);
+  for (size_t i = 0; i < out.size(); i++) {
+    out[i].col = (unsigned int)m->entries[i].col;
+    out[i].val = (float)m->entries[i].val;            // :99-102
+  }
+  ok = ok && fwrite(out.data(), sizeof(FEntry), out.size(), f) == out.size();
+  if (fclose(f) != 0 || !ok) {
+    fprintf(stderr, "ERROR: writing %s failed\n", filename);
+    exit(EXIT_FAILURE);
+  }
+}
+
+void matrixBinRead(GMatrix* m, Comm* c, char* filename)
+{
+  FILE* f = fopen(filename, "rb");
+  if (!f) {
+    fprintf(stderr, "ERROR: cannot open %s\n", filename);
+    exit(EXIT_FAILURE);
+  }
+  if (c->rank == 0) printf("Reading matrix from %s\n", filename);
+  char header[kBmxHeader];
+  unsigned int totalNr = 0, totalNnz = 0;
+  readExact(f, header, kBmxHeader, "header");
+  readExact(f, &totalNr, 4, "unsigned");
+  readExact(f, &totalNnz, 4, "unsigned");
+  m->totalNr = totalNr;
+  m->totalNnz = totalNnz;
+  // row block of this rank (matrixBinfile.c:157-176)
+  unsigned int startRow = 0, numRows = 0;
+  for (int i = 0; i <= c->rank; i++) {
+    startRow += numRows;
+    numRows = totalNr / (unsigned int)c->size + ((totalNr % (unsigned int)c->size > (unsigned int)i) ? 1u : 0u);
+  }
+  m->nr = numRows;
+  m->nc = numRows;
+  m->startRow = startRow;
+  m->stopRow = startRow + numRows - 1;
+  m->rowPtr = (CG_UINT*)hostAlloc(sizeof(CG_UINT) * ((size_t)numRows + 1));
+  const long rowPtrAt = (long)(kBmxHeader + 8);
+  if (fseek(f, rowPtrAt + 4L * (long)startRow, SEEK_SET) != 0) exit(EXIT_FAILURE);
+  readExact(f, m->rowPtr, 4 * ((size_t)numRows + 1), "rowptr");
+  const unsigned int entryOffset = m->rowPtr[0];        // = non-zeros of all lower ranks (:195-205)
+  for (unsigned int i = 0; i <= numRows; i++) m->rowPtr[i] -= entryOffset;
+  m->nnz = m->rowPtr[numRows];
+  std::vector<FEntry> in((size_t)m->nnz);
+  const long entriesAt = rowPtrAt + 4L * ((long)totalNr + 1);
+  if (fseek(f, entriesAt + 8L * (long)entryOffset, SEEK_SET) != 0) exit(EXIT_FAILURE);
+  readExact(f, in.data(), sizeof(FEntry) * in.size(), "entries");
+  fclose(f);
+  m->entries = (Entry*)hostAlloc(sizeof(Entry) * (size_t)(m->nnz ? m->nnz : 1));
+  memset(m->entries, 0, sizeof(Entry) * (size_t)(m->nnz ? m->nnz : 1));
+  for (size_t i = 0; i < in.size(); i++) {              // :229-232
+    m->entries[i].col = (CG_UINT)in[i].col;
+    m->entries[i].val = (CG_FLOAT)in[i].val;
+  }
+}
+
+} // extern "C"

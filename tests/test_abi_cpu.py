@@ -192,3 +192,45 @@ def test_mm_reader_fields_symmetry_and_duplicates(tmp_path, field, symm):
     if ref.available("CRS"):
         mr = ref.csr_from_gmatrix(ref.read_mm(path))                    # the reference's own reader
         assert np.array_equal(rp, mr.rowPtr) and np.array_equal(col, mr.col) and np.array_equal(val, mr.val)
+
+
+# ------------------------------------------------------------------------------------------- .bmx files
+def _parse_bmx(path):
+    """independent reader of the layout matrixBinfile.c:38-105 writes"""
+    raw = open(path, "rb").read()
+    assert raw[:22] == b"# SparseBench DataFile" and raw[22:24] == b"\0\0"
+    nr, nnz = np.frombuffer(raw, np.uint32, 2, 24)
+    rp = np.frombuffer(raw, np.uint32, nr + 1, 32)
+    rec = np.frombuffer(raw, np.dtype([("col", np.uint32), ("val", np.float32)]), nnz, 32 + 4 * (nr + 1))
+    assert len(raw) == 32 + 4 * (nr + 1) + 8 * nnz
+    return int(nr), int(nnz), rp, rec["col"], rec["val"]
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 7])
+def test_bmx_write_then_read_per_rank(tmp_path, fixtures_dir, P):
+    """matrixBinWrite (single rank, main.c:42-52) and matrixBinRead for every rank of P (row blocks of sizeOfRank)"""
+    L = api.lib()
+    one = api.Comm()
+    one.rank, one.size = 0, 1
+    g = api.matrixRead(os.path.join(fixtures_dir, "matrix_band_klein.mtx"))
+    rp0, col0, val0 = api.gmatrix_arrays(g)
+    path = str(tmp_path / "klein.bmx")
+    L.matrixBinWrite(C.byref(g), C.byref(one), path.encode())
+    nr, nnz, rp, col, val = _parse_bmx(path)
+    assert (nr, nnz) == (g.nr, int(rp0[-1])) and np.array_equal(rp, rp0) and np.array_equal(col, col0)
+    assert np.array_equal(val, val0.astype(np.float32))
+    start = 0
+    for r in range(P):
+        c = api.Comm()
+        c.rank, c.size = r, P
+        m = api.GMatrix()
+        L.matrixBinRead(C.byref(m), C.byref(c), path.encode())
+        m._device = False
+        n = nr // P + (1 if nr % P > r else 0)
+        assert (m.nr, m.nc, m.startRow, m.stopRow, m.totalNr, m.totalNnz) == (n, n, start, start + n - 1, nr, nnz)
+        rpl, cl, vl = api.gmatrix_arrays(m)
+        lo, hi = int(rp0[start]), int(rp0[start + n])
+        assert m.nnz == hi - lo and np.array_equal(rpl, rp0[start:start + n + 1] - lo)
+        assert np.array_equal(cl, col0[lo:hi]) and np.array_equal(vl, val0[lo:hi].astype(np.float32).astype(np.float64))
+        L.sbFreeGMatrix(C.byref(m))
+        start += n
