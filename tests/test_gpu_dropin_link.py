@@ -51,3 +51,24 @@ def test_reference_driver_linked_against_the_library(fmt, case):
     for mine, ref in zip(lines, gold):
         assert close_lines(mine, ref), (mine, ref)
     assert "Function   Rate(MB/s)  Rate(MFlop/s)  Walltime(s)" in r.stdout      # the reference's own profilerPrint ran
+
+
+def test_reference_driver_bmx_round_trip(tmp_path):
+    """main.c:42-52 (`-c file.mtx` writes file.bmx) and main.c:72-76 (`.bmx` input) through the linked reference driver:
+    the klein matrix converted to .bmx and solved from there prints the klein golden (its values are exact in float32)"""
+    import shutil
+    exe = os.path.join(ROOT, "integration", "_build", "sparseBench-CRS-B200")
+    if not os.path.exists(exe):
+        pytest.skip("integration/_build not built")
+    mtx = str(tmp_path / "klein.mtx")
+    shutil.copy(KLEIN, mtx)
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    r = subprocess.run([exe, "-c", mtx], capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0 and os.path.exists(str(tmp_path / "klein.bmx")), r.stdout + r.stderr
+    r = subprocess.run([exe, "-m", str(tmp_path / "klein.bmx"), "-i", "10"], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    lines = [re.sub(r"and took .*", "and took", ln) for ln in r.stdout.splitlines() if KEEP.match(ln)]
+    gold = GOLD["klein"]["lines"]
+    assert len(lines) == len(gold) and all(close_lines(a, b) for a, b in zip(lines, gold)), (lines, gold)
