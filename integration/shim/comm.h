@@ -7,6 +7,7 @@
 #define __COMM_H_
 #define __MATRIX_H_
 #define __SOLVER_H_
+#include <stdlib.h>
 #include "parameter.h" /* the reference's own (no shim of that name): its Parameter typedef wins */
 #include "util.h"      /* the reference's own: CG_UINT / CG_FLOAT macros, HLINE */
 #include "sparsebench_b200.h"
@@ -18,4 +19,20 @@ static inline void commBarrier(void)                       /* comm.h:63-68 */
   double zero = 0.0;
   commReduction(&zero, SUM);
 }
+
+#ifdef SCS
+/* The reference's main.c leaves Matrix.C and Matrix.sigma uninitialised (matrix-SCS.c:42-43 overwrites them with 1, a
+ * work-in-progress state); the caller has to provide them. This glue does, with the benchmark's C = 32, sigma = 256
+ * unless SB_SCS_C / SB_SCS_SIGMA say otherwise. */
+#undef convertMatrix
+static inline void sbShimConvertMatrix(Matrix* m, GMatrix* im)
+{
+  const char* c = getenv("SB_SCS_C");
+  const char* s = getenv("SB_SCS_SIGMA");
+  m->C = c ? (CG_UINT)atoi(c) : 32u;
+  m->sigma = s ? (CG_UINT)atoi(s) : 256u;
+  sbSCS_convertMatrix(m, im);
+}
+#define convertMatrix sbShimConvertMatrix
+#endif
 #endif

@@ -33,7 +33,7 @@ def close_lines(a, b):
     return True
 
 
-@pytest.mark.parametrize("fmt", ["CRS", "CCRS"])
+@pytest.mark.parametrize("fmt", ["CRS", "CCRS", "SCS"])
 @pytest.mark.parametrize("case", sorted(GOLD))
 def test_reference_driver_linked_against_the_library(fmt, case):
     exe = os.path.join(ROOT, "integration", "_build", "sparseBench-%s-B200" % fmt)
