@@ -5,6 +5,10 @@
  * reference file:line it follows). It is pinned against
  *   - the reference's 7 golden files and the klein anchor (tests/golden/, tests/test_oracle_*.py),
  *   - the reference's own sources compiled under oracle/_ref/ (same tests, when _ref is present).
+ * Two parts have no pin in the reference's own test suite ("parity unpinned" there): the multi-rank halo lists
+ * (pinned here by the unmodified comm.c driven through the in-process MPI shim, oracle/mpi_shim) and CG on the SCS
+ * format (the reference's initVectors is CRS-only; pinned to the CRS history, which a permutation leaves unchanged
+ * up to rounding).
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load it. The product (sparsebench_b200/) never links, imports or calls anything in oracle/.
  */
