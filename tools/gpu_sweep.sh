@@ -3,7 +3,7 @@
 set -u
 mkdir -p gpurun_out
 best=0; bestms=999
-for cfg in 0 1 2 3 4 5 6 7 8; do
+for cfg in 0 1 2 3 4 5; do
   SB_SELL_CFG=$cfg timeout 120 python tools/spmv_probe.py --n 256 --fmt SCS --reps 4 > gpurun_out/sweep_$cfg.log 2>&1
   ms=$(tail -1 gpurun_out/sweep_$cfg.log | sed 's/.*: \([0-9.]*\) ms.*/\1/')
   echo "cfg $cfg: $(tail -1 gpurun_out/sweep_$cfg.log)"
