@@ -409,6 +409,40 @@ def main():
         L.sbFreeHost(hb); L.sbFreeHost(hx)
         note('e2e done')
 
+    # ---- BASELINE.json configs[1] beside the headline (single GPU, default workload only): 128^3 CRS CG, same method
+    also = None
+    if world == 1 and args.workload == "sell256" and not args.no_e2e:
+        try:
+            wl = WORKLOADS["crs128"]
+            ax, ay, az = wl[0], wl[1], wl[2]
+            g1 = api.matrixGenerate(ax, ay, az, 0, 1, device=True)
+            A1 = api.convertMatrix(api.FMT_CRS, g1)
+            L.sbFreeGMatrix(C.byref(g1))
+            p1 = api.Parameter(b"generate", ax, ay, az, W + K + 1, 0.0)
+            i1 = api.CGInfo()
+            i1.flags = api.CG_FUSED
+            h1 = np.zeros(W + K + 5)
+            i1.history = h1.ctypes.data_as(C.POINTER(C.c_double))
+            i1.historyCap = len(h1)
+            one = api.Comm()
+            one.rank, one.size = 0, 1
+            S1 = L.sbCGCreate(C.byref(one), C.byref(p1), C.byref(A1), api.FMT_CRS, C.byref(i1))
+            L.sbCGIterate(S1, W + 1)
+            L.sbDeviceSynchronize()
+            timer.start()
+            k1 = L.sbCGIterate(S1, W + K + 1)
+            ms1 = timer.stop_ms()
+            L.sbCGFinish(S1, C.byref(i1), ms1)
+            api.destroyMatrix(A1)
+            N1, nnz1 = ax * ay * az, local_nnz(ax, ay, az, 0, 1)
+            done = k1 - (W + 1)
+            b_it1 = 12 * nnz1 + 16 * N1 + 72 * N1
+            also = {"workload": wl[6], "steps": done, "ms_per_step": ms1 / done, "iterations_per_sec": done / (ms1 * 1e-3),
+                    "gflops": (2 * nnz1 + 10 * N1) * done / (ms1 * 1e-3) / 1e9, "cg_gbs": b_it1 * done / (ms1 * 1e-3) / 1e9,
+                    "frac_of_peak": b_it1 * done / (ms1 * 1e-3) / 1e9 / peak}
+        except Exception as e:
+            also = {"workload": "crs128", "failed": repr(e)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -438,6 +472,7 @@ def main():
                          "algorithmic_bytes_per_launch": B_spmv, "avg_launch_ms": spmv_ms,
                          "frac_of_nominal_8000": achieved / 8000.0},
             "cpu_baseline": cpu,
+            "configs1": also,
             "spmv": {"gflops": F_spmv / (spmv_only_ms * 1e-3) / 1e9, "gbs": B_spmv / (spmv_only_ms * 1e-3) / 1e9,
                      "gbs_format_bytes": B_spmv_fmt / (spmv_only_ms * 1e-3) / 1e9, "ms": spmv_only_ms,
                      "frac_of_peak": B_spmv / (spmv_only_ms * 1e-3) / 1e9 / peak, "mode": "x=1, back-to-back (main.c:200-216)"},
