@@ -145,7 +145,8 @@ typedef struct {                /* comm.h:27-46, the _MPI member set is always p
 /* ---------------------------------------------------------------- runtime (allocate.c, timing.c) */
 /* allocate.h:9 -- device allocation (alignment honoured up to 512 B); exits on failure */
 void* allocate(size_t alignment, size_t bytesize);
-void sbFree(void* devPtr);
+void sbFree(void* devPtr);                           /* released blocks are parked for reuse (SB_POOL_MB caps the cache, default 8192) */
+void sbTrimPool(void);                               /* returns every parked block to the driver (before handing the GPU to another allocator) */
 void* sbAllocateHost(size_t bytesize);               /* pinned host memory for staging */
 void sbFreeHost(void* hostPtr);
 void sbCopyToDevice(void* dev, const void* host, size_t bytes);
@@ -222,6 +223,7 @@ typedef struct {
   double solveMs;         /* out: device time of the iteration loop (CUDA events), CGSolver.c:106,130 */
   double maxError;        /* out: max|x - 1| for generated matrices (CGSolver.c:40-60), else -1 */
   double regionMs[SB_REGION_COUNT]; /* out (SB_CG_PROFILE): device time per kernel class, replaces _t[] of profiler.c:17 */
+  double createMs, finishMs; /* out (sbSolveCG): host wall time before / after the loop: allocation, uploads, pre-loop (CGSolver.c:69-102) / check, download, free */
 } SbCGInfo;
 /* solveCG with explicit right-hand side / history capture; returns the reference's k */
 int sbSolveCG(Comm* comm, Parameter* param, void* matrix, int fmt, SbCGInfo* info);

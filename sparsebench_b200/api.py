@@ -73,7 +73,7 @@ class Comm(C.Structure):
 class CGInfo(C.Structure):
     _fields_ = [("flags", C.c_int), ("b", C.c_void_p), ("x", C.c_void_p), ("history", C.POINTER(C.c_double)),
                 ("historyCap", C.c_int), ("nhist", C.c_int), ("solveMs", C.c_double), ("maxError", C.c_double),
-                ("regionMs", C.c_double * 7)]
+                ("regionMs", C.c_double * 7), ("createMs", C.c_double), ("finishMs", C.c_double)]
 
 
 _configured = False

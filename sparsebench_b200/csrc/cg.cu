@@ -10,6 +10,7 @@
 // per-iteration pipeline drain.
 #include <math.h>
 #include <string.h>
+#include <time.h>
 
 #include <vector>
 
@@ -34,7 +35,8 @@ struct CgSolver {
   bool fusedReduce = false;                // multi-GPU: all-reduces split into push (producer) / collect (consumer)
   bool fusedPut = false;                   // multi-GPU: the p update stores boundary values straight into the neighbours' p
   PeerReduce pendingRho;                   // epoch of the newest rho that has been pushed but not yet collected
-  int* elemsPerm = nullptr;                // SELL with a row permutation: elementsToSend in solver (permuted) numbering
+  const int* elems = nullptr;              // multi-GPU send list in solver numbering (owned by the Comm)
+  bool pBorrowed = false;                  // p is the Comm's persistent, peer-mapped halo vector
   uint32_t intLo = 0, intHi = 0;           // SpMV units [intLo, intHi) reference no halo column
   uint32_t n = 0;
   size_t rowSlots = 0, colSlots = 0;
@@ -47,19 +49,35 @@ struct CgSolver {
   double normr = 0.0, rtrans = 0.0, oldrtrans = 0.0;
   int k = 1;
   bool stopped = false;
-  // optional per-kernel event timing
+  // optional per-kernel event timing: a fixed pool of events created in setup(), drained into regionMs whenever
+  // it is full, so the timed loop never creates an event and a long run never holds more than kProfEvents
+  static constexpr int kProfEvents = 512;
   std::vector<cudaEvent_t> evPool;
-  std::vector<int> evRegion;
+  int evRegion[kProfEvents];
+  int evUsed = 0;
   double regionMs[R_COUNT] = { 0, 0, 0, 0, 0, 0, 0 };
+  double createMs = 0.0;
+
+  void drainMarks()
+  {
+    if (evUsed < 2) return;
+    SB_CUDA(cudaEventSynchronize(evPool[(size_t)evUsed - 1]));
+    for (int i = 1; i < evUsed; i++) {
+      float ms = 0.f;
+      SB_CUDA(cudaEventElapsedTime(&ms, evPool[(size_t)i - 1], evPool[(size_t)i]));
+      if (evRegion[i] >= 0) regionMs[evRegion[i]] += ms;
+    }
+    std::swap(evPool[0], evPool[(size_t)evUsed - 1]);         // the last stamp opens the next batch
+    evRegion[0] = -1;
+    evUsed = 1;
+  }
 
   void mark(int region)
   {
     if (!profile) return;
-    cudaEvent_t e;
-    SB_CUDA(cudaEventCreate(&e));
-    SB_CUDA(cudaEventRecord(e, s));
-    evPool.push_back(e);
-    evRegion.push_back(region);
+    if (evUsed == kProfEvents) drainMarks();
+    SB_CUDA(cudaEventRecord(evPool[(size_t)evUsed], s));
+    evRegion[evUsed++] = region;
   }
 
   void allreduce(double* d, int op)
@@ -78,33 +96,34 @@ struct CgSolver {
     if (commActive(comm)) {
       if (gated) {
         // `already`: the p update itself delivered the halo (FusedPut); otherwise a put kernel does
-        const HaloGate gate = already ? *already : commHaloPutDirect(comm, p, elemsPerm, s);
+        const HaloGate gate = already ? *already : commHaloPutDirect(comm, p, elems, s);
         mark(R_EXCHANGE);
         launchSpmvGated(A, p, Ap, intLo, intHi, gate, dot, s);
         mark(R_SPMV);
         return;
       }
-      commExchangeOnStream(comm, A.nr, p, elemsPerm, s);
+      commExchangeOnStream(comm, A.nr, p, elems, s);
       mark(R_EXCHANGE);
     }
     launchSpmv(A, p, Ap, 0, units, dot, s);
     mark(R_SPMV);
   }
 
-  // caller vector (host or device, original row order) -> device vector in solver order
-  void importVector(const double* src, double* dst)
+  // caller vector (host or device, original row order) -> device vector in solver order, on stream `st`;
+  // `stage` receives a host vector that still has to be permuted
+  void importVector(const double* src, double* dst, double* stage, cudaStream_t st)
   {
     const size_t bytes = sizeof(double) * n;
     const bool dev = isDevicePointer(src);
     if (!A.oldToNew) {
-      SB_CUDA(cudaMemcpyAsync(dst, src, bytes, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+      SB_CUDA(cudaMemcpyAsync(dst, src, bytes, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
     } else {
       const double* staged = src;
       if (!dev) {
-        SB_CUDA(cudaMemcpyAsync(tmp, src, bytes, cudaMemcpyHostToDevice, s));
-        staged = tmp;
+        SB_CUDA(cudaMemcpyAsync(stage, src, bytes, cudaMemcpyHostToDevice, st));
+        staged = stage;
       }
-      launchScatter(n, A.oldToNew, staged, dst, s);           // dst[oldToNew[i]] = src[i]
+      launchScatter(n, A.oldToNew, staged, dst, st);          // dst[oldToNew[i]] = src[i]
     }
   }
 
@@ -145,8 +164,26 @@ struct CgSolver {
     rowSlots = (size_t)(A.nrPadded > n ? A.nrPadded : n) + 2;
     colSlots = (A.nc > rowSlots ? (size_t)A.nc : rowSlots) + 2;
     const int nScal = (itermax > 0 ? itermax : 0) + 4;
+    // direct halo delivery into p + gated single-launch SpMV: p is then the Comm's persistent vector, which every
+    // peer mapped when the partition was first solved on (no per-solve registration)
+    if (commActive(comm)) {
+      if (commPeerMode(comm)) {
+        const bool can = overlap && spmvGatedAvailable(A);
+        if (can) spmvInteriorUnits(A, &intLo, &intHi, s);
+        p = commAcquireHaloVector(comm, A.nr, colSlots, can);
+        pBorrowed = gated = p != nullptr;
+      }
+      elems = commSolverElements(comm, A.permKey, A.oldToNew, s);   // vectors are row-permuted: send p[oldToNew[element]]
+      if (gated) {
+        fusedReduce = fused && getenv("SB_NO_FUSED_REDUCE") == nullptr;
+        fusedPut = fusedReduce && getenv("SB_NO_FUSED_PUT") == nullptr && commPrepareFusedPut(comm, A.permKey, elems);
+      }
+    }
     r = (double*)allocate(64, sizeof(double) * rowSlots);
-    p = (double*)allocate(64, sizeof(double) * colSlots);
+    if (!p) {
+      p = (double*)allocate(64, sizeof(double) * colSlots);
+      SB_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * colSlots, s));
+    }
     Ap = (double*)allocate(64, sizeof(double) * rowSlots);
     x = (double*)allocate(64, sizeof(double) * rowSlots);
     b = (double*)allocate(64, sizeof(double) * rowSlots);
@@ -154,36 +191,44 @@ struct CgSolver {
     rho = (double*)allocate(64, sizeof(double) * nScal);
     pAp = (double*)allocate(64, sizeof(double) * nScal);
     hRho = (double*)sbAllocateHost(sizeof(double) * nScal);
-    SB_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * colSlots, s));
     SB_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * rowSlots, s));
     SB_CUDA(cudaMemsetAsync(rho, 0, sizeof(double) * nScal, s));
     SB_CUDA(cudaMemsetAsync(pAp, 0, sizeof(double) * nScal, s));
     for (int i = 0; i < kEventRing; i++) SB_CUDA(cudaEventCreateWithFlags(&ring[i], cudaEventDisableTiming));
+    if (profile) {
+      evPool.resize(kProfEvents);
+      for (cudaEvent_t& e : evPool) SB_CUDA(cudaEventCreate(&e));
+    }
     hist.reserve((size_t)nScal);
 
-    if (commActive(comm)) {
-      if (A.oldToNew && comm->totalSendCount > 0) {           // vectors are row-permuted: send p[oldToNew[element]]
-        elemsPerm = (int*)allocate(64, sizeof(int) * (size_t)comm->totalSendCount);
-        launchPermuteIndices((uint32_t)comm->totalSendCount, A.oldToNew, commDeviceElements(comm), elemsPerm, s);
-      }
-      // direct halo delivery into p + gated single-launch SpMV (collective decision inside commAttachHaloVector)
-      if (commPeerMode(comm)) {
-        const bool can = overlap && spmvGatedAvailable(A);
-        if (can) spmvInteriorUnits(A, &intLo, &intHi, s);
-        gated = commAttachHaloVector(comm, p, A.nr, can, elemsPerm);
-        fusedReduce = gated && fused && getenv("SB_NO_FUSED_REDUCE") == nullptr;
-        fusedPut = fusedReduce && commFusedPutAvailable(comm) && getenv("SB_NO_FUSED_PUT") == nullptr;
+    // initVectors (CGSolver.c:19-38), or caller-supplied b / x0. x0 is needed first (p = x0, A p); a host b travels
+    // on the side stream behind it while the main stream already multiplies, and joins before r = b - A p.
+    launchInitVectors(n, A.rowPtr, A.rowLen, generated, x, b, s);
+    cudaEvent_t bReady = nullptr;
+    if (info && info->b) {
+      if (isDevicePointer(info->b)) {
+        importVector(info->b, b, tmp, s);
+      } else {
+        cudaEvent_t bFree;
+        SB_CUDA(cudaEventCreateWithFlags(&bFree, cudaEventDisableTiming));
+        SB_CUDA(cudaEventCreateWithFlags(&bReady, cudaEventDisableTiming));
+        if (info->x) importVector(info->x, x, Ap, s);          // queue x0 ahead of b on the link
+        SB_CUDA(cudaEventRecord(bFree, s));
+        SB_CUDA(cudaStreamWaitEvent(c.commStream, bFree, 0));
+        importVector(info->b, b, tmp, c.commStream);
+        SB_CUDA(cudaEventRecord(bReady, c.commStream));
+        SB_CUDA(cudaEventDestroy(bFree));
       }
     }
-
-    // initVectors (CGSolver.c:19-38), or caller-supplied b / x0
-    launchInitVectors(n, A.rowPtr, A.rowLen, generated, x, b, s);
-    if (info && info->b) importVector(info->b, b);
-    if (info && info->x) importVector(info->x, x);
+    if (info && info->x && !bReady) importVector(info->x, x, Ap, s);
 
     // pre-loop (CGSolver.c:94-100)
     launchWaxpby(n, 1.0, x, 0.0, x, p, s);
     spmvWithHalo(nullptr);
+    if (bReady) {
+      SB_CUDA(cudaStreamWaitEvent(s, bReady, 0));
+      SB_CUDA(cudaEventDestroy(bReady));
+    }
     launchWaxpby(n, 1.0, b, -1.0, Ap, r, s);
     launchDot(n, r, r, rho, 0, s);
     allreduce(rho, SB_SUM);
@@ -198,9 +243,7 @@ struct CgSolver {
     if (printFreq < 1) printFreq = 1;
     k = 1;
     if (profile) {   // drop the pre-loop marks, start the clock here
-      for (cudaEvent_t e : evPool) cudaEventDestroy(e);
-      evPool.clear();
-      evRegion.clear();
+      evUsed = 0;
       mark(-1);
     }
   }
@@ -289,7 +332,7 @@ struct CgSolver {
   {
     Context& c = ctx();
     SB_CUDA(cudaStreamSynchronize(s));
-    if (gated) commDetachHaloVector(comm);
+    if (pBorrowed) commReleaseHaloVector(comm);
     if (fused && (int)hist.size() < k) {
       // iteration k-1 was the last one executed; record its normr = sqrt(rho[k-2])
       const double last = k >= 3 ? sqrt(hRho[k - 2]) : normr;
@@ -316,16 +359,14 @@ struct CgSolver {
       info->maxError = maxErr;
       for (int i = 0; i < R_COUNT; i++) info->regionMs[i] = 0.0;
       if (profile) {
-        for (size_t i = 1; i < evPool.size(); i++) {
-          float ms = 0.f;
-          SB_CUDA(cudaEventElapsedTime(&ms, evPool[i - 1], evPool[i]));
-          if (evRegion[i] >= 0) info->regionMs[evRegion[i]] += ms;
-        }
+        drainMarks();
+        for (int i = 0; i < R_COUNT; i++) info->regionMs[i] = regionMs[i];
       }
     }
     for (cudaEvent_t e : evPool) cudaEventDestroy(e);
     for (int i = 0; i < kEventRing; i++) SB_CUDA(cudaEventDestroy(ring[i]));
-    sbFree(r); sbFree(p); sbFree(Ap); sbFree(x); sbFree(b); sbFree(tmp); sbFree(rho); sbFree(pAp); sbFree(elemsPerm);
+    sbFree(r); sbFree(Ap); sbFree(x); sbFree(b); sbFree(tmp); sbFree(rho); sbFree(pAp);
+    if (!pBorrowed) sbFree(p);
     sbFreeHost(hRho);
     return k;
   }
@@ -356,12 +397,18 @@ int sbCGFinish(void* solver, SbCGInfo* info, double loopMs)
   return k;
 }
 
+static double wallMs()
+{
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec * 1e3 + (double)ts.tv_nsec * 1e-6;
+}
+
 int sbSolveCG(Comm* comm, Parameter* param, void* matrix, int fmt, SbCGInfo* info)
 {
-  const bool trace = getenv("SB_CG_TRACE") != nullptr;
-  const double t0 = trace ? getTimeStamp() : 0.0;
-  CgSolver* S = (CgSolver*)sbCGCreate(comm, param, matrix, fmt, info);
-  const double t1 = trace ? getTimeStamp() : 0.0;
+  const double t0 = wallMs();
+  CgSolver* S = (CgSolver*)sbCGCreate(comm, param, matrix, fmt, info);   // ends with a drained stream (initial residual)
+  const double t1 = wallMs();
   cudaEvent_t a, b;
   SB_CUDA(cudaEventCreate(&a));
   SB_CUDA(cudaEventCreate(&b));
@@ -373,9 +420,15 @@ int sbSolveCG(Comm* comm, Parameter* param, void* matrix, int fmt, SbCGInfo* inf
   SB_CUDA(cudaEventElapsedTime(&ms, a, b));
   SB_CUDA(cudaEventDestroy(a));
   SB_CUDA(cudaEventDestroy(b));
-  const double t2 = trace ? getTimeStamp() : 0.0;
+  const double t2 = wallMs();
   const int k = sbCGFinish(S, info, ms);
-  if (trace) fprintf(stderr, "[sbSolveCG] create %.2f ms, loop %.2f ms (device %.2f), finish %.2f ms\n", (t1 - t0) * 1e3, (t2 - t1) * 1e3, ms, (getTimeStamp() - t2) * 1e3);
+  const double t3 = wallMs();
+  if (info) {
+    info->createMs = t1 - t0;
+    info->finishMs = t3 - t2;
+  }
+  if (getenv("SB_CG_TRACE"))
+    fprintf(stderr, "[sbSolveCG] create %.2f ms, loop %.2f ms (device %.2f), finish %.2f ms\n", t1 - t0, t2 - t1, ms, t3 - t2);
   return k;
 }
 
@@ -389,7 +442,7 @@ extern double _t[4] __attribute__((weak));
 
 static int solveDropIn(Comm* comm, Parameter* param, void* m, int fmt)
 {
-  if (!&_t[0]) return sbSolveCG(comm, param, m, fmt, nullptr);
+  if (!&_t[0] || getenv("SB_NO_PROFILER_T")) return sbSolveCG(comm, param, m, fmt, nullptr);
   SbCGInfo info;
   memset(&info, 0, sizeof(info));
   info.flags = SB_CG_FUSED | SB_CG_PRINT | SB_CG_PROFILE;

@@ -85,18 +85,35 @@ struct CommExt {
   PutPlan* dPut = nullptr;
   WaitPlan* dWait = nullptr;
   unsigned long long haloSeq = 0, redEpoch = 0;
-  // registered halo vector (direct delivery)
+  // persistent halo vector (the CG's p): allocated, zeroed and mapped by every peer ONCE per partition
+  // (commAcquireHaloVector); solves only borrow it, the arrival counters keep running across solves
+  double* arena = nullptr;
+  size_t arenaSlots = 0;
+  uint32_t arenaRows = 0;
+  bool arenaBusy = false;
   std::vector<double*> peerVec;
+  PutPlan putDirect;               // host copy of *dPutDirect
   PutPlan* dPutDirect = nullptr;
   unsigned long long directSeq = 0;
-  bool attached = false;
-  FusedPut fused;                  // valid (ndest > 0) when the attached vector's sends fit kMaxFusedDests
+  // send list in solver numbering (SELL row permutation `elemsKey`) and the FusedPut maps derived from it
+  uint64_t elemsKey = 0;
+  int* dElemsSolver = nullptr;
+  bool fusedValid = false;
+  uint64_t fusedKey = 0;
+  FusedPut fused;                  // usable (ndest > 0) when the sends fit kMaxFusedDests
   std::vector<int*> fusedInv;      // device inverse maps owned by `fused`
 };
 
 static CommExt* g_world = nullptr;   // commReduction has no Comm* argument (it used MPI_COMM_WORLD, comm.c:653-662)
 
 static CommExt* ext(const Comm* c) { return c ? (CommExt*)c->communicator : nullptr; }
+
+static void freeHostLists(Comm* c)
+{
+  free(c->sources); free(c->recvCounts); free(c->rdispls);          // comm.c:896-903
+  free(c->destinations); free(c->sendCounts); free(c->sdispls);
+  free(c->elementsToSend);
+}
 
 static void resetLists(Comm* c)
 {
@@ -420,6 +437,8 @@ __global__ void renumberKernel(uint64_t n, Entry* __restrict__ e, uint32_t start
   }
 }
 
+static void releaseArena(Comm* c);
+
 // Releases the device-side state of the current partition (collective in peer mode: peers may still store into
 // the halo window until everybody has reached this point).
 static void uninstallPartition(Comm* c)
@@ -427,7 +446,9 @@ static void uninstallPartition(Comm* c)
   CommExt* e = ext(c);
   if (!e || !e->installed) return;
   SB_CUDA(cudaDeviceSynchronize());
-  commDetachHaloVector(c);
+  releaseArena(c);
+  sbFree(e->dElemsSolver); e->dElemsSolver = nullptr;
+  e->elemsKey = 0;
   if (e->mode == COMM_PEER) {
     ncclBarrier(e);
     std::vector<void*> peers(e->peerHalo.begin(), e->peerHalo.end());
@@ -542,28 +563,75 @@ void commHaloWait(Comm* c, uint32_t numRows, double* x, cudaStream_t s)
   }
 }
 
-bool commAttachHaloVector(Comm* c, double* x, uint32_t numRows, bool localOk, const int* elements)
+// All-reduce of one host double over the ranks of `e` (the body of commReduction).
+static void hostAllreduce(CommExt* e, double* v, int op)
+{
+  Context& c = ctx();
+  e->hScalar[0] = *v;
+  SB_CUDA(cudaMemcpyAsync(e->dScalar, e->hScalar, sizeof(double), cudaMemcpyHostToDevice, c.stream));
+  Comm tmp;
+  memset(&tmp, 0, sizeof(tmp));
+  tmp.communicator = e;
+  commAllreduceDevice(&tmp, e->dScalar, 1, op, c.stream);
+  SB_CUDA(cudaMemcpyAsync(e->hScalar, e->dScalar, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  SB_CUDA(cudaStreamSynchronize(c.stream));
+  *v = e->hScalar[0];
+}
+
+static void dropFusedMaps(CommExt* e)
+{
+  for (int* p : e->fusedInv) sbFree(p);
+  e->fusedInv.clear();
+  e->fused = FusedPut();
+  e->fusedValid = false;
+}
+
+// Collective. Frees the persistent halo vector: nobody may store into it any more when it goes.
+static void releaseArena(Comm* c)
 {
   CommExt* e = ext(c);
-  if (!e || e->mode != COMM_PEER) return false;
-  installPartition(c);
-  if (e->attached) commDetachHaloVector(c);
+  if (!e || !e->arena) return;
+  SB_CUDA(cudaDeviceSynchronize());
+  ncclBarrier(e);
+  std::vector<void*> peers(e->peerVec.begin(), e->peerVec.end());
+  unmapPeers(e, peers);
+  e->peerVec.clear();
+  ncclBarrier(e);
+  sbFree(e->arena);
+  e->arena = nullptr;
+  e->arenaSlots = 0;
+  e->arenaRows = 0;
+  e->arenaBusy = false;
+  sbFree(e->dPutDirect);
+  e->dPutDirect = nullptr;
+  dropFusedMaps(e);
+}
+
+// Collective. Allocates the persistent halo vector, lets every peer map it and builds the put plan: my boundary
+// values go straight behind destination d's local rows, at d's rdispl for me (comm.c:135).
+static bool registerArena(Comm* c, size_t slots, uint32_t numRows)
+{
+  CommExt* e = ext(c);
+  releaseArena(c);
   const int size = e->size, rank = e->rank;
-  int ok = (localOk && c->indegree <= kMaxGateSources) ? 1 : 0;   // collective decision: every rank must agree
-  std::vector<int> oks((size_t)size);
-  allGatherInts(e, &ok, 1, oks.data());
-  for (int r = 0; r < size; r++) ok &= oks[(size_t)r];
-  if (!ok) return false;
+  e->arena = (double*)allocate(256, sizeof(double) * slots);
+  SB_CUDA(cudaMemset(e->arena, 0, sizeof(double) * slots));
   SB_CUDA(cudaDeviceSynchronize());
   std::vector<void*> peers;
-  if (!mapPeers(e, x, peers)) return false;
+  if (!mapPeers(e, e->arena, peers)) {
+    sbFree(e->arena);
+    e->arena = nullptr;
+    return false;
+  }
+  e->arenaSlots = slots;
+  e->arenaRows = numRows;
   e->peerVec.resize((size_t)size);
   for (int r = 0; r < size; r++) e->peerVec[(size_t)r] = (double*)peers[(size_t)r];
   std::vector<int> rows((size_t)size);
   int mine = (int)numRows;
   allGatherInts(e, &mine, 1, rows.data());
   const int* W = e->wantMatrix.data();
-  PutPlan put;
+  PutPlan& put = e->putDirect;
   memset(&put, 0, sizeof(put));
   put.ndest = c->outdegree;
   for (int i = 0; i < c->outdegree; i++) {
@@ -578,11 +646,70 @@ bool commAttachHaloVector(Comm* c, double* x, uint32_t numRows, bool localOk, co
   put.sdispl[c->outdegree] = c->totalSendCount;
   e->dPutDirect = (PutPlan*)allocate(64, sizeof(PutPlan));
   sbCopyToDevice(e->dPutDirect, &put, sizeof(put));
-  // inverse maps for the delivery fused into the producing kernel: element -> position in the destination's halo
-  e->fused = FusedPut();
-  if (c->outdegree > 0 && c->outdegree <= kMaxFusedDests) {
+  // the arrival counters count elements since registration and keep running from solve to solve
+  e->directSeq = 0;
+  SB_CUDA(cudaMemset(e->ctrl->directFlag, 0, sizeof(e->ctrl->directFlag)));
+  SB_CUDA(cudaDeviceSynchronize());
+  ncclBarrier(e);
+  return true;
+}
+
+// Borrows the persistent halo vector for one solve (collective; one scalar all-reduce when nothing has to be
+// registered). Returns nullptr -- on every rank -- when some rank cannot run the gated SpMV or the windows cannot be
+// mapped; the caller then allocates its own vector and exchanges through commExchangeOnStream.
+// Why the halo part may be reused from solve to solve without any further synchronisation: a rank can only start
+// storing the next solve's first halo after it has collected the previous solve's last p.Ap, i.e. after every
+// rank's last SpMV -- the only reader of the halo -- has completed. The caller must not clear slots >= numRows.
+double* commAcquireHaloVector(Comm* c, uint32_t numRows, size_t slots, bool localOk)
+{
+  CommExt* e = ext(c);
+  if (!e || e->mode != COMM_PEER) return nullptr;
+  installPartition(c);
+  if (e->arenaBusy) SB_FATAL("commAcquireHaloVector: the halo vector is in use by another solver");
+  const bool fits = e->arena && e->arenaSlots >= slots && e->arenaRows == numRows;
+  const bool ok = localOk && c->indegree <= kMaxGateSources;
+  double v = (ok ? 1.0 : 0.0) + (fits ? 0.0 : 1024.0);       // both collective decisions in one sum
+  hostAllreduce(e, &v, SB_SUM);
+  const long long sum = (long long)(v + 0.5);
+  if (sum % 1024 != e->size) return nullptr;
+  if (sum / 1024 > 0 && !registerArena(c, slots > e->arenaSlots ? slots : e->arenaSlots, numRows)) return nullptr;
+  e->arenaBusy = true;
+  return e->arena;
+}
+
+void commReleaseHaloVector(Comm* c)
+{
+  CommExt* e = ext(c);
+  if (e) e->arenaBusy = false;
+}
+
+// Send list in the solver's row numbering: the CG keeps SELL vectors in permuted order, so it sends
+// p[oldToNew[element]]. Cached per permutation (`key`: unique id of the converted matrix, 0 = no permutation).
+const int* commSolverElements(Comm* c, uint64_t key, const uint32_t* oldToNew, cudaStream_t s)
+{
+  CommExt* e = ext(c);
+  if (!e) return nullptr;
+  installPartition(c);
+  if (key == 0 || !oldToNew || c->totalSendCount == 0) return e->dElementsToSend;
+  if (e->dElemsSolver && e->elemsKey == key) return e->dElemsSolver;
+  if (!e->dElemsSolver) e->dElemsSolver = (int*)allocate(64, sizeof(int) * (size_t)c->totalSendCount);
+  launchPermuteIndices((uint32_t)c->totalSendCount, oldToNew, e->dElementsToSend, e->dElemsSolver, s);
+  e->elemsKey = key;
+  return e->dElemsSolver;
+}
+
+// Inverse maps for the delivery fused into the producing kernel (FusedPut): element -> position in the
+// destination's halo. Local work, cached per permutation; false when there are too many destinations.
+bool commPrepareFusedPut(Comm* c, uint64_t key, const int* elements)
+{
+  CommExt* e = ext(c);
+  if (!e || !e->arena) return false;
+  if (c->outdegree > kMaxFusedDests) return false;
+  if (e->fusedValid && e->fusedKey == key) return true;
+  dropFusedMaps(e);
+  if (c->outdegree > 0) {
     std::vector<int> elems((size_t)c->totalSendCount);
-    if (elements) sbCopyToHost(elems.data(), elements, sizeof(int) * elems.size());
+    if (elements && elements != e->dElementsToSend) sbCopyToHost(elems.data(), elements, sizeof(int) * elems.size());
     else memcpy(elems.data(), c->elementsToSend, sizeof(int) * elems.size());
     e->fused.ndest = c->outdegree;
     for (int i = 0; i < c->outdegree; i++) {
@@ -600,47 +727,18 @@ bool commAttachHaloVector(Comm* c, double* x, uint32_t numRows, bool localOk, co
       e->fused.lo[i] = (uint32_t)lo;
       e->fused.hi[i] = (uint32_t)hi;
       e->fused.inv[i] = dInv;
-      e->fused.remote[i] = put.remote[0][i];
-      e->fused.remoteFlag[i] = put.remoteFlag[i];
+      e->fused.remote[i] = e->putDirect.remote[0][i];
+      e->fused.remoteFlag[i] = e->putDirect.remoteFlag[i];
     }
   }
-  e->directSeq = 0;
-  SB_CUDA(cudaMemset(e->ctrl->directFlag, 0, sizeof(e->ctrl->directFlag)));
-  SB_CUDA(cudaDeviceSynchronize());
-  ncclBarrier(e);
-  e->attached = true;
+  e->fusedValid = true;
+  e->fusedKey = key;
   return true;
 }
 
-void commDetachHaloVector(Comm* c)
+static HaloGate directGate(Comm* c, CommExt* e)
 {
-  CommExt* e = ext(c);
-  if (!e || !e->attached) return;
-  SB_CUDA(cudaDeviceSynchronize());
-  ncclBarrier(e);                                           // nobody stores into a vector that is about to go
-  std::vector<void*> peers(e->peerVec.begin(), e->peerVec.end());
-  unmapPeers(e, peers);
-  e->peerVec.clear();
-  sbFree(e->dPutDirect);
-  e->dPutDirect = nullptr;
-  for (int* p : e->fusedInv) sbFree(p);
-  e->fusedInv.clear();
-  e->fused = FusedPut();
-  ncclBarrier(e);
-  e->attached = false;
-}
-
-HaloGate commHaloPutDirect(Comm* c, const double* x, const int* elements, cudaStream_t s)
-{
-  CommExt* e = ext(c);
   HaloGate g;
-  if (!e || !e->attached) SB_FATAL("commHaloPutDirect: no registered halo vector");
-  e->directSeq++;
-  if (c->outdegree > 0) {
-    haloPutKernel<<<kPutBlocks, kHaloThreads, 0, s>>>(e->dPutDirect, elements ? elements : e->dElementsToSend, x, e->directSeq, true);
-    SB_CUDA(cudaGetLastError());
-    countLaunch();
-  }
   g.nsrc = c->indegree;
   for (int i = 0; i < c->indegree; i++) {
     g.flag[i] = &e->ctrl->directFlag[c->sources[i]];
@@ -649,10 +747,17 @@ HaloGate commHaloPutDirect(Comm* c, const double* x, const int* elements, cudaSt
   return g;
 }
 
-bool commFusedPutAvailable(const Comm* c)
+HaloGate commHaloPutDirect(Comm* c, const double* x, const int* elements, cudaStream_t s)
 {
   CommExt* e = ext(c);
-  return e && e->attached && (c->outdegree == 0 || e->fused.ndest > 0);
+  if (!e || !e->arenaBusy || x != e->arena) SB_FATAL("commHaloPutDirect: not the registered halo vector");
+  e->directSeq++;
+  if (c->outdegree > 0) {
+    haloPutKernel<<<kPutBlocks, kHaloThreads, 0, s>>>(e->dPutDirect, elements ? elements : e->dElementsToSend, x, e->directSeq, true);
+    SB_CUDA(cudaGetLastError());
+    countLaunch();
+  }
+  return directGate(c, e);
 }
 
 // The next exchange of the registered vector is performed by the caller's own kernel (FusedPut): returns what that
@@ -660,16 +765,10 @@ bool commFusedPutAvailable(const Comm* c)
 HaloGate commFusedPutBegin(Comm* c, FusedPut* fp)
 {
   CommExt* e = ext(c);
-  if (!e || !e->attached) SB_FATAL("commFusedPutBegin: no registered halo vector");
+  if (!e || !e->arenaBusy || !e->fusedValid) SB_FATAL("commFusedPutBegin: no registered halo vector");
   e->directSeq++;
   *fp = e->fused;
-  HaloGate g;
-  g.nsrc = c->indegree;
-  for (int i = 0; i < c->indegree; i++) {
-    g.flag[i] = &e->ctrl->directFlag[c->sources[i]];
-    g.target[i] = e->directSeq * (unsigned long long)c->recvCounts[i];
-  }
-  return g;
+  return directGate(c, e);
 }
 
 void commExchangeOnStream(Comm* c, uint32_t numRows, double* x, const int* elements, cudaStream_t s)
@@ -807,9 +906,7 @@ void commAbort(Comm* c, char* msg)
 
 void commFinalize(Comm* c)
 {
-  free(c->sources); free(c->recvCounts); free(c->rdispls);          // comm.c:896-903
-  free(c->destinations); free(c->sendCounts); free(c->sdispls);
-  free(c->elementsToSend);
+  freeHostLists(c);
   CommExt* e = ext(c);
   if (e) {
     SB_CUDA(cudaDeviceSynchronize());
@@ -834,17 +931,7 @@ void commFinalize(Comm* c)
 
 void commReduction(CG_FLOAT* v, int op)
 {
-  CommExt* e = g_world;
-  if (!e) return;                          // single rank: no-op (comm.c:655,661)
-  Context& c = ctx();
-  e->hScalar[0] = *v;
-  SB_CUDA(cudaMemcpyAsync(e->dScalar, e->hScalar, sizeof(double), cudaMemcpyHostToDevice, c.stream));
-  Comm tmp;
-  tmp.communicator = e;
-  commAllreduceDevice(&tmp, e->dScalar, 1, op, c.stream);
-  SB_CUDA(cudaMemcpyAsync(e->hScalar, e->dScalar, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
-  SB_CUDA(cudaStreamSynchronize(c.stream));
-  *v = e->hScalar[0];
+  if (g_world) hostAllreduce(g_world, v, op);   // single rank: no-op (comm.c:655,661)
 }
 
 void sbCommAllreduceDevice(Comm* c, CG_FLOAT* dev, int count, int op) { commAllreduceDevice(c, dev, count, op, ctx().stream); }
@@ -1013,6 +1100,7 @@ void sbPartitionFinish(SbPartitionPlan* P, Comm* c, const int* wantMatrix, const
     uninstallPartition(c);                                   // device state of a previous partition (collective)
     e->wantMatrix.assign(wantMatrix, wantMatrix + (size_t)c->size * c->size);
   }
+  freeHostLists(c);                                          // lists of a previous partition on this Comm
   c->externalCount = L.externalCount;
   c->totalSendCount = L.totalSendCount;
   c->indegree = (int)L.sources.size();
@@ -1029,6 +1117,7 @@ void commPartition(Comm* c, GMatrix* m)
   const int size = c->size, rank = c->rank;
   CommExt* e = ext(c);
   if (size <= 1) {   // one row block: every column is local already, all lists stay empty (startRow is 0)
+    freeHostLists(c);
     resetLists(c);
     c->sources = dupInts({}); c->recvCounts = dupInts({}); c->rdispls = dupInts({});
     c->destinations = dupInts({}); c->sendCounts = dupInts({}); c->sdispls = dupInts({});

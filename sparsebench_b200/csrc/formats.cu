@@ -5,6 +5,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <atomic>
 #include <mutex>
 #include <unordered_map>
 
@@ -20,7 +21,10 @@ ScsExt* scsExt(const void* key, bool create)
 {
   std::lock_guard<std::mutex> l(g_extMutex);
   auto it = g_scs.find(key);
-  if (it != g_scs.end()) return it->second;
+  if (it != g_scs.end()) {
+    if (create) *it->second = ScsExt();      // the key was freed behind our back and handed out again: start clean
+    return it->second;
+  }
   if (!create) return nullptr;
   return g_scs[key] = new ScsExt();
 }
@@ -28,7 +32,10 @@ CrsExt* crsExt(const void* key, bool create)
 {
   std::lock_guard<std::mutex> l(g_extMutex);
   auto it = g_crs.find(key);
-  if (it != g_crs.end()) return it->second;
+  if (it != g_crs.end()) {
+    if (create) *it->second = CrsExt();
+    return it->second;
+  }
   if (!create) return nullptr;
   return g_crs[key] = new CrsExt();
 }
@@ -207,7 +214,7 @@ Operator makeOperator(void* matrix, int fmt)
     A.rowLen = e->rowLenPerm;
     A.nnzTrue = e->nnzTrue;
     A.split = &e->split;
-    if (!e->identityPerm) { A.oldToNew = m->oldToNewPerm; A.newToOld = m->newToOldPerm; }
+    if (!e->identityPerm) { A.oldToNew = m->oldToNewPerm; A.newToOld = m->newToOldPerm; A.permKey = e->id; }
     A.sell = SellView { m->nChunks, m->nr, m->C, m->chunkPtr, m->chunkLens, e->identityPerm ? m->colInd : e->colPerm, m->val };
   } else {
     SB_FATAL("unknown matrix format id %d", fmt);
@@ -306,6 +313,8 @@ void sbSCS_convertMatrix(SbSCSMatrix* m, GMatrix* im)
   ext->rowLenPerm = (uint32_t*)allocate(64, sizeof(uint32_t) * np);
   ext->nnzTrue = in.stored;
   ext->nc = im->nc;
+  static std::atomic<uint64_t> nextId { 1 };
+  ext->id = nextId.fetch_add(1);
   SB_CUDA(cudaMemsetAsync(ext->rowLenPerm, 0, sizeof(uint32_t) * np, s));
   scsKeysKernel<<<gridFor(nrPadded, 256), 256, 0, s>>>(nr, nrPadded, sigma, in.rowPtr, keys, idx, ext->rowLenOrig);
   SB_CUDA(cudaGetLastError());

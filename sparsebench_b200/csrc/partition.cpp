@@ -7,6 +7,7 @@
 // are bit-identical to the reference's; its unbalanced binary search tree (bstree.c, O(ext^2) on stencil
 // input) is replaced by an open-addressing hash set with the same first-encounter ordinals.
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -64,17 +65,15 @@ void PartitionPlan::build(const uint32_t* extRefs, size_t nRefs, int rank_, int 
     owner[(size_t)i] = o;
     want[(size_t)o]++;
   }
-  // step 3 (comm.c:40-114): halo slots grouped by owner in order of first appearance. Equivalent to the
-  // reference's quadratic rescan: bucket the ordinals per owner, then emit owners by first appearance.
-  std::vector<int> firstSeen((size_t)size, -1), ownerOrder;
-  for (int i = 0; i < nExt; i++)
-    if (firstSeen[(size_t)owner[(size_t)i]] < 0) {
-      firstSeen[(size_t)owner[(size_t)i]] = i;
-      ownerOrder.push_back(owner[(size_t)i]);
-    }
+  // step 3 (comm.c:40-114): halo slots grouped by owner, first-encounter order inside a group. The reference emits
+  // the groups in order of first appearance but then ships and receives them as if they were in ASCENDING owner
+  // order (sources / rdispls of comm.c:522-580 and the slices of :148-158 are running sums over ascending ranks):
+  // whenever a higher owner is met before a lower one its lists address the wrong ranks. The groups are therefore
+  // laid out in ascending owner order here -- bit-identical to the reference in every case in which the reference
+  // is self-consistent (all generated stencils, row-sorted banded input), and correct in the others.
   std::vector<int> groupStart((size_t)size, 0);
   int cursor = 0;
-  for (int o : ownerOrder) {
+  for (int o = 0; o < size; o++) {
     groupStart[(size_t)o] = cursor;
     cursor += want[(size_t)o];
   }
@@ -116,14 +115,21 @@ void PartitionPlan::finish(CommLists& out, const int* wantMatrix, const int* rec
   }
   out.totalSendCount = sacc;
   out.elementsToSend.resize((size_t)sacc);
-  for (int i = 0; i < sacc; i++) out.elementsToSend[(size_t)i] = received[i] - (int)startRow;   // comm.c:164-166
+  for (int i = 0; i < sacc; i++) {
+    const long long local = (long long)received[i] - (long long)startRow;                        // comm.c:164-166
+    if (local < 0 || local >= (long long)nr) {   // would become a device gather index: never let a foreign row through
+      fprintf(stderr, "sparsebench_b200: commPartition: rank %d was asked for row %d, which it does not own (rows %u..%u)\n",
+          rank, received[i], startRow, startRow + nr - 1);
+      exit(EXIT_FAILURE);
+    }
+    out.elementsToSend[(size_t)i] = (int)local;
+  }
 }
 
 void PartitionPlan::requestSlice(const int* wantMatrix, int source, const int** ptr, int* count) const
 {
   // the slice shipped to `source` starts at my rdispls for it: a running sum over ascending sources
-  // (comm.c:148-158) -- NOT the owner-group offset; the two coincide whenever owners first appear in
-  // ascending order, which the reference silently assumes
+  // (comm.c:148-158) = the start of that owner's group (groups are laid out in ascending owner order)
   int off = 0;
   for (int s = 0; s < source; s++) off += wantMatrix[(size_t)rank * size + s];
   *ptr = requests.data() + off;

@@ -65,11 +65,24 @@ extern "C" {
 // the same nine vectors per solve (CGSolver.c:69-79 never frees, a library must). Released blocks are therefore
 // parked in a small exact-size cache and handed out again (contents undefined, exactly like fresh cudaMalloc memory).
 static std::mutex g_poolMutex;
-static std::unordered_map<void*, size_t> g_blockSize;               // every live or parked block
+struct Block {
+  size_t bytes;
+  bool parked;
+};
+static std::unordered_map<void*, Block> g_blockSize;                // every live or parked block
 static std::unordered_multimap<size_t, void*> g_parked;
 static size_t g_parkedBytes = 0;
-constexpr size_t kParkLimitBytes = (size_t)8 << 30;                 // total
 constexpr size_t kParkMaxBlock = (size_t)2 << 30;                   // per block
+// total; SB_POOL_MB overrides (0 disables parking). The parked bytes are invisible to other allocators in the
+// process (PyTorch, NCCL): sbTrimPool() hands them back.
+static size_t parkLimitBytes()
+{
+  static const size_t v = [] {
+    const char* e = getenv("SB_POOL_MB");
+    return e && *e ? (size_t)strtoull(e, nullptr, 10) << 20 : (size_t)8 << 30;
+  }();
+  return v;
+}
 
 static void releaseParked()
 {
@@ -97,6 +110,7 @@ void* allocate(size_t alignment, size_t bytesize)
     void* p = it->second;
     g_parked.erase(it);
     g_parkedBytes -= bytes;
+    g_blockSize[p].parked = false;
     return p;
   }
   void* p = nullptr;
@@ -111,8 +125,15 @@ void* allocate(size_t alignment, size_t bytesize)
         cudaGetErrorString(e));
     exit(EXIT_FAILURE);
   }
-  g_blockSize[p] = bytes;
+  g_blockSize[p] = Block { bytes, false };
   return p;
+}
+
+void sbTrimPool(void)
+{
+  std::lock_guard<std::mutex> lock(g_poolMutex);
+  if (g_ctx.stream) SB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+  releaseParked();
 }
 
 void sbFree(void* p)
@@ -124,10 +145,12 @@ void sbFree(void* p)
     SB_CUDA(cudaFree(p));
     return;
   }
-  const size_t bytes = it->second;
-  if (bytes <= kParkMaxBlock && g_parkedBytes + bytes <= kParkLimitBytes) {
+  if (it->second.parked) SB_FATAL("sbFree: block %p released twice", p);
+  const size_t bytes = it->second.bytes;
+  if (bytes <= kParkMaxBlock && g_parkedBytes + bytes <= parkLimitBytes()) {
     // work queued on the stream may still use the block: it may only be reused once that work has drained
     SB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    it->second.parked = true;
     g_parked.emplace(bytes, p);
     g_parkedBytes += bytes;
     return;

@@ -85,6 +85,7 @@ struct Operator {
   const uint32_t* rowLen = nullptr;        // SCS: row lengths in vector (permuted) order
   const uint32_t* oldToNew = nullptr;      // SCS with sigma>1: vectors live in permuted order
   const uint32_t* newToOld = nullptr;
+  uint64_t permKey = 0;                    // unique id of the row permutation (0: none); cache key of derived lists
   CrsView crs{};
   SellView sell{};                         // col = symmetric-permuted columns when oldToNew != nullptr
   CcrsView ccrs{};
@@ -158,11 +159,16 @@ struct FusedPut {
   double* remote[kMaxFusedDests] = {};
   unsigned long long* remoteFlag[kMaxFusedDests] = {};
 };
-// collective; false -> use commExchangeOnStream. `elements` overrides Comm.elementsToSend (device, solver numbering)
-bool commAttachHaloVector(Comm* c, double* x, uint32_t numRows, bool localOk, const int* elements);
-bool commFusedPutAvailable(const Comm* c);                           // few enough destinations for FusedPut
+// Collective. Borrows the Comm's persistent halo vector (>= slots doubles, zero-filled when first registered; peers
+// map it once per partition, not per solve) for one solver; nullptr (on every rank) -> allocate your own vector and
+// use commExchangeOnStream. The borrower must not clear slots >= numRows: a faster peer may already have stored the
+// next exchange's halo there.
+double* commAcquireHaloVector(Comm* c, uint32_t numRows, size_t slots, bool localOk);
+void commReleaseHaloVector(Comm* c);
+// send list in the solver's row numbering (device; SELL keeps vectors in permuted order), cached per permutation key
+const int* commSolverElements(Comm* c, uint64_t key, const uint32_t* oldToNew, cudaStream_t s);
+bool commPrepareFusedPut(Comm* c, uint64_t key, const int* elements);    // false: too many destinations for FusedPut
 HaloGate commFusedPutBegin(Comm* c, FusedPut* fp);                   // next exchange, performed by the caller's kernel
-void commDetachHaloVector(Comm* c);                                  // collective
 HaloGate commHaloPutDirect(Comm* c, const double* x, const int* elements, cudaStream_t s);   // returns the gate to wait on
 
 // ---- side tables keyed by the device array a Matrix struct points to
@@ -174,6 +180,7 @@ struct ScsExt {
   bool identityPerm = true;
   uint64_t nnzTrue = 0;
   uint32_t nc = 0;               // columns incl. halo (the reference's SCS struct drops it, matrix-SCS.c:38)
+  uint64_t id = 0;               // unique per conversion, never reused
 };
 struct CrsExt {
   HaloSplit split;

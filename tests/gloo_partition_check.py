@@ -16,9 +16,41 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from oracle import orc  # noqa: E402
 from sparsebench_b200 import api  # noqa: E402
+
+
+def partition_over_gloo(L, g, rank, world):
+    """commPartition in its three collective steps (comm.c:414-625 with gloo in place of MPI/NCCL)."""
+    # step 1: all-gather of the first rows (comm.c:496)
+    starts = [None] * world
+    dist.all_gather_object(starts, int(g.startRow))
+    starts = np.array(starts, np.uint32)
+    want = np.zeros(world, np.int32)
+    plan = L.sbPartitionLocal(C.byref(g), rank, world, starts.ctypes.data, want.ctypes.data)
+    # step 2: all-gather of the per-owner counts
+    wants = [None] * world
+    dist.all_gather_object(wants, want.tolist())
+    wm = np.array(wants, np.int32)                      # [requester][owner]
+    # step 3: request lists travel requester -> owner (comm.c:130-161)
+    mine = {}
+    for s in range(world):
+        cnt = C.c_int(0)
+        ptr = L.sbPartitionRequestSlice(plan, wm.ctypes.data, s, C.byref(cnt))
+        assert cnt.value == wm[rank, s]
+        mine[s] = [ptr[i] for i in range(cnt.value)]
+    allreq = [None] * world
+    dist.all_gather_object(allreq, mine)
+    received = []
+    for q in range(world):                              # ascending requester
+        received += allreq[q][rank]
+    received = np.array(received + [0], np.int32)
+    comm = api.Comm()
+    comm.rank, comm.size = rank, world
+    L.sbPartitionFinish(plan, C.byref(comm), wm.ctypes.data, received.ctypes.data)
+    return comm, starts
 
 
 def main():
@@ -29,32 +61,7 @@ def main():
     for (nx, ny, nz, use7) in [(3, 3, 2, False), (4, 5, 4, True), (8, 8, 3, False), (1, 4, 4, False)]:
         g = api.matrixGenerate(nx, ny, nz, rank, world, use7)
         n = nx * ny * nz
-        # step 1: all-gather of the first rows (comm.c:496)
-        starts = [None] * world
-        dist.all_gather_object(starts, int(g.startRow))
-        starts = np.array(starts, np.uint32)
-        want = np.zeros(world, np.int32)
-        plan = L.sbPartitionLocal(C.byref(g), rank, world, starts.ctypes.data, want.ctypes.data)
-        # step 2: all-gather of the per-owner counts
-        wants = [None] * world
-        dist.all_gather_object(wants, want.tolist())
-        wm = np.array(wants, np.int32)                      # [requester][owner]
-        # step 3: request lists travel requester -> owner (comm.c:130-161)
-        mine = {}
-        for s in range(world):
-            cnt = C.c_int(0)
-            ptr = L.sbPartitionRequestSlice(plan, wm.ctypes.data, s, C.byref(cnt))
-            assert cnt.value == wm[rank, s]
-            mine[s] = [ptr[i] for i in range(cnt.value)]
-        allreq = [None] * world
-        dist.all_gather_object(allreq, mine)
-        received = []
-        for q in range(world):                              # ascending requester
-            received += allreq[q][rank]
-        received = np.array(received + [0], np.int32)
-        comm = api.Comm()
-        comm.rank, comm.size = rank, world
-        L.sbPartitionFinish(plan, C.byref(comm), wm.ctypes.data, received.ctypes.data)
+        comm, _starts = partition_over_gloo(L, g, rank, world)
         # oracle: the reference algorithm for all ranks at once
         omats = [orc.generate(nx, ny, nz, r, world, use7) for r in range(world)]
         part = orc.Partition(omats)
@@ -84,6 +91,19 @@ def main():
             x[n + d["rdispls"][i]:n + d["rdispls"][i] + d["recvCounts"][i]] = vals
         if not np.array_equal(x[n:], np.asarray(o["externalsReordered"], np.float64)):
             bad.append("%s halo values" % tag)
+    # arrow matrix: every rank meets the last rank's column first (owners out of ascending order). The reference's
+    # lists are inconsistent there; the product's must deliver x[global id] into the slot of every external.
+    import matrices
+    N = 12 * world + 5
+    lo, rp, col, val = matrices.arrow_blocks(N, world)[rank]
+    g = api.gmatrix_from_csr(rp, col.copy(), val, startRow=lo, totalNr=N)
+    comm, starts = partition_over_gloo(L, g, rank, world)
+    everything = [None] * world
+    dist.all_gather_object(everything, (len(rp) - 1, col.tolist(), api.gmatrix_arrays(g)[1].tolist(), comm.lists()))
+    if rank == 0:
+        sem = matrices.check_partition_semantics(starts.astype(np.int64), [e[0] for e in everything], [e[1] for e in everything],
+                                                 [e[2] for e in everything], [e[3] for e in everything])
+        bad += ["arrow: " + m for m in sem]
     for b in bad:
         print("[rank %d] FAIL %s" % (rank, b), flush=True)
     print("[rank %d] gloo_partition_check: %s" % (rank, "PASS" if not bad else "FAIL"), flush=True)

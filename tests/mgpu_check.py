@@ -46,28 +46,33 @@ def main():
         omats = [orc.generate(nx, ny, nz, r, world) for r in range(world)]
         part = orc.Partition(omats)
         n = nx * ny * nz
+        # ONE partition per case, shared by every format and every solve below: the Comm's peer-mapped halo vector
+        # is registered by the first gated solve and only borrowed by the later ones (different matrices, different
+        # row permutations, the non-overlapped and call-by-call paths in between)
+        g = api.matrixGenerate(nx, ny, nz, rank, world, device=True)
+        L.commPartition(C.byref(comm), C.byref(g))
+        tag = "%dx%dx%d" % (nx, ny, nz)
+        d, o = comm.lists(), part.ranks[rank]
+        for f in ("externalCount", "totalSendCount"):
+            check(d[f] == o[f], "%s: %s %r != %r" % (tag, f, d[f], o[f]), failures)
+        for f in ("sources", "recvCounts", "rdispls", "destinations", "sendCounts", "sdispls", "elementsToSend"):
+            check(np.array_equal(d[f], o[f]), "%s: list %s differs" % (tag, f), failures)
+        check(np.array_equal(api.gmatrix_arrays(g)[1], omats[rank].col), "%s: renumbered columns differ" % tag, failures)
+        # halo exchange through the drop-in entry point (comm.c:627-651): x = global row id
+        nc = n + comm.externalCount
+        xs = np.zeros(nc)
+        xs[:n] = rank * n + np.arange(n)
+        xd = api.to_device(xs)
+        for _ in range(3):                                   # slot parity + acknowledge path
+            L.commExchange(C.byref(comm), n, xd.ptr)
+        got = api.to_host(xd, np.float64, nc)
+        check(np.array_equal(got[n:], np.array(part.ranks[rank]["externalsReordered"], np.float64)), "%s: halo values differ" % tag, failures)
+        mats = []
         for fmt, sigma in fmts:
             tag = "%dx%dx%d fmt=%s sigma=%d" % (nx, ny, nz, api.FMT_NAMES[fmt], sigma)
-            g = api.matrixGenerate(nx, ny, nz, rank, world, device=True)
-            L.commPartition(C.byref(comm), C.byref(g))
-            d, o = comm.lists(), part.ranks[rank]
-            for f in ("externalCount", "totalSendCount"):
-                check(d[f] == o[f], "%s: %s %r != %r" % (tag, f, d[f], o[f]), failures)
-            for f in ("sources", "recvCounts", "rdispls", "destinations", "sendCounts", "sdispls", "elementsToSend"):
-                check(np.array_equal(d[f], o[f]), "%s: list %s differs" % (tag, f), failures)
-            check(np.array_equal(api.gmatrix_arrays(g)[1], omats[rank].col), "%s: renumbered columns differ" % tag, failures)
-            # halo exchange through the drop-in entry point (comm.c:627-651): x = global row id
-            nc = n + comm.externalCount
-            xs = np.zeros(nc)
-            xs[:n] = rank * n + np.arange(n)
-            xd = api.to_device(xs)
-            L.commExchange(C.byref(comm), n, xd.ptr)
-            got = api.to_host(xd, np.float64, nc)
-            want = np.array(part.ranks[rank]["externalsReordered"], np.float64) if "externalsReordered" in part.ranks[rank] else None
-            if want is not None:
-                check(np.array_equal(got[n:], want), "%s: halo values differ" % tag, failures)
             A = api.convertMatrix(fmt, g, 32, sigma)
-            for flags in (api.CG_FUSED, api.CG_FUSED | api.CG_NO_OVERLAP, 0):
+            mats.append(A)
+            for flags in (api.CG_FUSED, api.CG_FUSED, api.CG_FUSED | api.CG_NO_OVERLAP, 0, api.CG_FUSED):
                 k, hist, x, info = api.solveCG(A, itermax, eps, comm=comm, flags=flags, want_x=True)
                 check(k == kref, "%s flags=%d: k %d != %d" % (tag, flags, k, kref), failures)
                 if len(hist) == len(href):
@@ -78,9 +83,14 @@ def main():
                     check(False, "%s flags=%d: history length %d != %d" % (tag, flags, len(hist), len(href)), failures)
                 xe = float(np.max(np.abs(x - xref[rank * n:(rank + 1) * n])))
                 check(xe <= 1e-9 * max(1.0, float(np.max(np.abs(xref)))), "%s flags=%d: solution error %.3e" % (tag, flags, xe), failures)
+        # interleaved: one fused solve per matrix again, now that every permutation has been seen once
+        for A, (fmt, sigma) in zip(mats, fmts):
+            k, hist, _, _ = api.solveCG(A, itermax, eps, comm=comm, flags=api.CG_FUSED)
+            ok = k == kref and len(hist) == len(href) and float(np.max(np.abs(hist - href) / np.maximum(href, 1e-10 * href[0]))) <= CG_TOL
+            check(ok, "%dx%dx%d fmt=%s sigma=%d: interleaved re-solve k=%d/%d" % (nx, ny, nz, api.FMT_NAMES[fmt], sigma, k, kref), failures)
+        for A in mats:
             api.destroyMatrix(A)
-            if fmt != api.FMT_CCRS:
-                L.sbFreeGMatrix(C.byref(g))
+        L.sbFreeGMatrix(C.byref(g))
     # MatrixMarket path over the ranks (main.c:64-71, comm.c:311-402): rank 0 reads, row blocks are scattered
     nxm, nym, nzm = 7, 6, 3 * world + 1                      # row count not divisible by the rank count
     mg = orc.generate(nxm, nym, nzm)

@@ -10,6 +10,7 @@ import pytest
 
 from oracle import orc
 from sparsebench_b200 import _lib, api
+import matrices
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -112,16 +113,15 @@ def test_partition_lists_bit_exact_vs_unmodified_comm_c(golden, P, nx, ny, nz, u
         assert np.array_equal(golden[cfg + "r%d_rowPtr" % r], rp)
 
 
-def test_partition_matches_oracle_on_irregular_matrix():
-    """A banded + random-long-range matrix split over 5 ranks of unequal size (owners first met out of order)."""
+def _irregular_blocks(sort_cols):
     rng = np.random.default_rng(11)
     N, P = 300, 5
     rows = []
     for i in range(N):
         cols = {i, max(i - 1, 0), min(i + 1, N - 1), int(rng.integers(0, N)), int(rng.integers(0, N))}
-        rows.append(sorted(cols, key=lambda c: (c * 7919) % N))      # scrambled order inside the row
+        rows.append(sorted(cols) if sort_cols else sorted(cols, key=lambda c: (c * 7919) % N))
     bounds = [0, 50, 120, 130, 220, 300]
-    omats, gmats = [], []
+    blocks = []
     for r in range(P):
         lo, hi = bounds[r], bounds[r + 1]
         rp = np.zeros(hi - lo + 1, np.uint32)
@@ -129,20 +129,61 @@ def test_partition_matches_oracle_on_irregular_matrix():
         for i in range(lo, hi):
             col += rows[i]
             rp[i - lo + 1] = len(col)
-        col = np.array(col, np.uint32)
-        val = rng.standard_normal(len(col))
-        omats.append(orc.Csr(rp, col.copy(), val, startRow=lo, totalNr=N))
-        gmats.append(api.gmatrix_from_csr(rp, col.copy(), val, startRow=lo, totalNr=N))
+        blocks.append((lo, rp, np.array(col, np.uint32), rng.standard_normal(len(col))))
+    return N, blocks
+
+
+def _partition_blocks(N, blocks):
+    omats = [orc.Csr(rp, col.copy(), val, startRow=lo, totalNr=N) for lo, rp, col, val in blocks]
+    gmats = [api.gmatrix_from_csr(rp, col.copy(), val, startRow=lo, totalNr=N) for lo, rp, col, val in blocks]
     part = orc.Partition(omats)
     comms = partition_serial(gmats)
-    for r in range(P):
-        d = comms[r].lists()
+    starts = [lo for lo, _, _, _ in blocks]
+    nrs = [len(rp) - 1 for _, rp, _, _ in blocks]
+    new_cols = [api.gmatrix_arrays(g)[1] for g in gmats]
+    lists = [c.lists() for c in comms]
+    bad = matrices.check_partition_semantics(starts, nrs, [b[2] for b in blocks], new_cols, lists)
+    assert not bad, bad
+    return part, omats, starts, new_cols, lists
+
+
+@pytest.mark.parametrize("sort_cols", [True, False])
+def test_partition_on_irregular_matrix(sort_cols):
+    """A banded + random-long-range matrix split over 5 ranks of unequal size. The lists must be self-consistent
+    (tests/matrices.py:check_partition_semantics) and equal the reference's (oracle restatement of comm.c:414-625)
+    on every rank on which the reference itself is self-consistent, i.e. meets its owners in ascending order."""
+    N, blocks = _irregular_blocks(sort_cols)
+    part, omats, starts, new_cols, lists = _partition_blocks(N, blocks)
+    compared = 0
+    for r in range(len(blocks)):
         o = part.ranks[r]
-        for f in ("externalCount", "totalSendCount"):
-            assert d[f] == o[f]
-        for f in ("sources", "recvCounts", "rdispls", "destinations", "sendCounts", "sdispls", "elementsToSend"):
-            assert np.array_equal(d[f], o[f]), (r, f)
-        assert np.array_equal(api.gmatrix_arrays(gmats[r])[1], omats[r].col)
+        assert lists[r]["externalCount"] == o["externalCount"]
+        for f in ("sources", "recvCounts", "rdispls", "destinations", "sendCounts", "sdispls"):
+            assert np.array_equal(lists[r][f], o[f]), (r, f)          # counts and topology never depend on the order
+        if matrices.owners_ascending(starts, o["externalsReordered"]):
+            assert np.array_equal(new_cols[r], omats[r].col), r
+            compared += 1
+        # what I send to d is defined by d's halo layout: equal to the reference's when d's layout is the reference's
+        for i, d in enumerate(lists[r]["destinations"]):
+            if matrices.owners_ascending(starts, part.ranks[int(d)]["externalsReordered"]):
+                lo, cnt = int(lists[r]["sdispls"][i]), int(lists[r]["sendCounts"][i])
+                assert np.array_equal(lists[r]["elementsToSend"][lo:lo + cnt], o["elementsToSend"][lo:lo + cnt]), (r, int(d))
+    assert compared >= (1 if sort_cols else 0)
+
+
+@pytest.mark.parametrize("P", [3, 4])
+def test_partition_arrow_matrix_owners_out_of_order(P):
+    """Arrow matrix: every rank meets the LAST rank's column first. The reference then addresses the wrong ranks
+    (its elementsToSend leave the local row range); the product lays the halo groups out in ascending owner order
+    and must be self-consistent."""
+    N = 40
+    blocks = matrices.arrow_blocks(N, P)
+    part, omats, starts, new_cols, lists = _partition_blocks(N, blocks)
+    # the reference's own lists are inconsistent here: some rank is asked for rows it does not own
+    broken = any(len(part.ranks[r]["elementsToSend"]) and
+                 (part.ranks[r]["elementsToSend"].min() < 0 or part.ranks[r]["elementsToSend"].max() >= len(blocks[r][1]) - 1)
+                 for r in range(P))
+    assert broken, "the arrow matrix no longer exercises the out-of-order case"
 
 
 # ------------------------------------------------------------------------------------------- MatrixMarket path

@@ -18,18 +18,19 @@ def test_reference_arm_prints_one_json_line(workload, world):
         env.pop(k, None)
     if world > 1:
         env.update(RANK="0", WORLD_SIZE=str(world), LOCAL_RANK="0")
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", str(world), "--steps", "1",
-                        "--warmup", "3", "--ref-planes", "2", "--workload", workload], capture_output=True, text=True, timeout=300, env=env)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", str(world), "--steps", "6",
+                        "--warmup", "3", "--ref-planes", "8", "--workload", workload], capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = r.stdout.strip().splitlines()
     assert len(lines) == 1, r.stdout
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "cg_gflops" and d["unit"] == "GFLOP/s" and d["higher_is_better"] is True
-    assert d["n_gpus"] == world and d["steps"] == 1 and d["warmup"] == 3 and d["value"] > 0
+    assert d["n_gpus"] == world and d["steps"] == 6 and d["warmup"] == 3 and d["value"] > 0
     assert d["scaling"] == ("strong" if workload.startswith("strong") else "weak")
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] == 2 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and d["vs_baseline"] is None and d["dtype"] == "f64"
+    assert d["cpu_baseline"]["same_config"] is False and 0 < d["cpu_baseline"]["sampled_fraction"] < 1      # --ref-planes: a labelled sample
 
 
 def test_reference_arm_other_ranks_exit_quietly():
