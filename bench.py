@@ -120,11 +120,12 @@ class ClockSampler:
                 if self._record:
                     self.samples.append(mhz)
                     self.bits |= bits
-                    try:
-                        self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
-                    except Exception:
-                        pass
-                time.sleep(0.002 if self._record else 0.02)
+                    if len(self.samples) % 8 == 1:      # every NVML query costs milliseconds: power only now and then
+                        try:
+                            self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                        except Exception:
+                            pass
+                time.sleep(0.001 if self._record else 0.02)
         except Exception as e:
             self.error = repr(e)
             self._ready.set()
