@@ -169,6 +169,22 @@ def ddot(x, y):
     return lib().orc_ddot(len(x), np.ascontiguousarray(x), np.ascontiguousarray(y))
 
 
+class dot_threads:
+    """`with orc.dot_threads(16): ...` -- dot products summed like the reference's OpenMP build with that many
+    threads (solver.c:46-61, static schedule); 1 = sequential (default); 0 = long double yardstick."""
+
+    def __init__(self, t):
+        self.t = t
+
+    def __enter__(self):
+        self.old = lib().orc_get_dot_threads()
+        lib().orc_set_dot_threads(self.t)
+
+    def __exit__(self, *exc):
+        lib().orc_set_dot_threads(self.old)
+        return False
+
+
 def cg_crs(m, b, x0, itermax, eps):
     """CGSolver.c:62-141. Returns (k, history, x): history[0] initial residual, history[k] = normr of iteration k."""
     x = np.array(x0, np.float64)

@@ -171,11 +171,33 @@ void orc_waxpby(uint32_t n, double alpha, const double* x, double beta, const do
   else                   for (uint32_t i = 0; i < n; i++) w[i] = alpha * x[i] + beta * y[i];
 }
 
+/* solver.c:46-61: `#pragma omp parallel for reduction(+ : sum) schedule(static)`. The summation order depends on the
+ * thread count T of the run: every thread sums one contiguous chunk left to right (libgomp's static schedule: n / T
+ * elements each, the first n % T threads one more), the partial sums are combined afterwards (thread order here; OpenMP
+ * leaves it open). T = 1 is the sequential loop of the strict single-thread build. T = 0 is not a reference mode: it
+ * accumulates in long double and serves as the rounding-free yardstick when two summation orders are compared. */
+static int g_dot_threads = 1;
+void orc_set_dot_threads(int t) { g_dot_threads = t < 0 ? 1 : t; }
+int orc_get_dot_threads(void) { return g_dot_threads; }
+
 double orc_ddot(uint32_t n, const double* x, const double* y)
-{ /* solver.c:46-61 (single thread: left to right) */
-  double s = 0.0;
-  for (uint32_t i = 0; i < n; i++) s += x[i] * y[i];
-  return s;
+{
+  if (g_dot_threads == 0) {
+    long double s = 0.0L;
+    for (uint32_t i = 0; i < n; i++) s += (long double)x[i] * (long double)y[i];
+    return (double)s;
+  }
+  const uint32_t T = (uint32_t)g_dot_threads;
+  double total = 0.0;
+  uint32_t at = 0;
+  for (uint32_t t = 0; t < T; t++) {
+    const uint32_t len = n / T + (t < n % T ? 1u : 0u);
+    double s = 0.0;
+    for (uint32_t i = at; i < at + len; i++) s += x[i] * y[i];
+    total = (t == 0) ? s : total + s;
+    at += len;
+  }
+  return total;
 }
 
 /* ------------------------------------------------------------------ CG: CGSolver.c:62-141 */

@@ -39,6 +39,10 @@ void orc_spmv_scs(uint32_t nChunks, uint32_t C, const uint32_t* chunkPtr, const 
 /* solver.c:16-39, :41-62 */
 void orc_waxpby(uint32_t n, double alpha, const double* x, double beta, const double* y, double* w);
 double orc_ddot(uint32_t n, const double* x, const double* y);
+/* summation order of orc_ddot: T >= 1 = the reference's OpenMP static schedule with T threads (1 = sequential, the
+ * default); 0 = long double accumulation (yardstick, not a reference mode) */
+void orc_set_dot_threads(int t);
+int orc_get_dot_threads(void);
 /* CGSolver.c:62-141 (single rank, CRS operator) */
 int orc_cg_crs(uint32_t nr, uint32_t nc, const uint32_t* rowPtr, const uint32_t* col, const double* val,
     const double* b, double* x, int itermax, double eps, double* hist, int* nhist);

@@ -41,8 +41,16 @@ def stencil128():
     yref = orc.spmv_crs(m, x)
     scale = orc.spmv_crs(orc.Csr(m.rowPtr, m.col, np.abs(m.val)), np.abs(x))
     x0, b, _ = orc.init_vectors(m)
-    kref, href, xref = orc.cg_crs(m, b, x0, 31, 0.0)
-    return dict(m=m, x=x, yref=yref, scale=scale, kref=kref, href=href, xref=xref)
+    # The reference's ddot is an OpenMP reduction (solver.c:46-61): its summation order depends on the thread count.
+    # Over 2.1 M mostly IDENTICAL terms (the interior of the stencil is translation invariant) a sequential sum rounds
+    # in the same direction again and again and drifts by ~1e-10 relative -- measured below against a long double
+    # accumulation -- so the history is pinned against three orders: 16 threads (the bench host), 1 thread, and the
+    # rounding-free yardstick.
+    hists = {}
+    for t in (1, 16, 0):
+        with orc.dot_threads(t):
+            kref, hists[t], xref = orc.cg_crs(m, b, x0, 31, 0.0)
+    return dict(m=m, x=x, yref=yref, scale=scale, kref=kref, hists=hists, xref=xref)
 
 
 @pytest.mark.parametrize("fmt", [api.FMT_CRS, api.FMT_CCRS, api.FMT_SCS])
@@ -71,8 +79,12 @@ def test_128_cubed_against_the_oracle(stencil128, fmt):
         err = np.abs(y - s["yref"])
         assert np.all(err <= SPMV_TOL * s["scale"]), float(np.max(err / s["scale"]))
     k, hist, x, info = api.solveCG(A, 31, 0.0, want_x=True)
-    assert k == s["kref"] and len(hist) == len(s["href"])
-    assert float(np.max(np.abs(hist - s["href"]) / s["href"])) <= CG_TOL
+    assert k == s["kref"]
+    dev = {t: float(np.max(np.abs(hist - h) / h)) for t, h in s["hists"].items() if len(h) == len(hist)}
+    assert len(dev) == 3
+    seq_rounding = float(np.max(np.abs(s["hists"][1] - s["hists"][0]) / s["hists"][0]))   # what a sequential sum loses
+    assert dev[0] <= CG_TOL and dev[16] <= CG_TOL, dev          # vs exactly-summed dots, vs the 16-thread reference order
+    assert dev[1] <= CG_TOL + 2 * seq_rounding, (dev, seq_rounding)  # vs the 1-thread order: its own drift on top
     assert float(np.max(np.abs(x - s["xref"]))) <= 1e-9
     api.destroyMatrix(A)
     if fmt == api.FMT_CCRS:
