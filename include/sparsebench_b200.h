@@ -189,6 +189,9 @@ void sbCCRS_spMVM(SbCCRSMatrix* m, const CG_FLOAT* x, CG_FLOAT* y);           /*
  * afterwards: the kernel the multi-GPU CG uses to overlap the halo exchange, here without a
  * halo to wait for. Returns 0 if the matrix has no pipelined kernel (then nothing was launched). */
 int sbSpmvOrdered(void* matrix, int fmt, const CG_FLOAT* x, CG_FLOAT* y, CG_UINT intLo, CG_UINT intHi);
+/* y = A x fused with *dDot = x . y (dDot: device scalar) -- spMVM + ddot of CGSolver.c:123-125 in one pass, asynchronous.
+ * Vectors in solver order (SCS with sigma > 1: permuted row order for x and y, as inside sbSolveCG). */
+void sbSpmvDot(void* matrix, int fmt, const CG_FLOAT* x, CG_FLOAT* y, CG_FLOAT* dDot);
 void sbCRS_destroyMatrix(SbCRSMatrix* m);
 void sbSCS_destroyMatrix(SbSCSMatrix* m);
 void sbCCRS_destroyMatrix(SbCCRSMatrix* m);

@@ -116,6 +116,8 @@ def lib():
             getattr(L, "sb%s_solveCG" % f).restype = C.c_int
         L.sbSpmvOrdered.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, U, U]
         L.sbSpmvOrdered.restype = C.c_int
+        L.sbSpmvDot.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sbTrimPool.argtypes = []
         L.waxpby.argtypes = [U, C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
         L.ddot.argtypes = [U, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
         L.sbSolveCG.argtypes = [C.POINTER(Comm), C.POINTER(Parameter), C.c_void_p, C.c_int, C.POINTER(CGInfo)]

@@ -20,7 +20,8 @@ namespace sb {
 
 namespace {
 
-constexpr int kEventRing = 8;
+// hRho[j] holds this bit pattern (a NaN no arithmetic produces) until the device has stored the global rho[j] there
+constexpr unsigned long long kRhoPending = 0xffffffffffffffffull;
 enum Region { R_UPDATE_P = 0, R_EXCHANGE, R_SPMV, R_ALLREDUCE, R_UPDATE_XR, R_HALO_WAIT, R_SPMV_BOUNDARY, R_COUNT };
 
 bool commActive(const Comm* c) { return c && c->size > 1; }
@@ -43,8 +44,7 @@ struct CgSolver {
   // vectors (CGSolver.c:69-79), solver order (SELL: permuted)
   double *r = nullptr, *p = nullptr, *Ap = nullptr, *x = nullptr, *b = nullptr, *tmp = nullptr;
   double *rho = nullptr, *pAp = nullptr;   // device scalars indexed by iteration: rho[j] = r_j.r_j, pAp[k] = p_k.Ap_k
-  double* hRho = nullptr;                  // pinned mirror of rho
-  cudaEvent_t ring[kEventRing];
+  double* hRho = nullptr;                  // mapped pinned mirror of rho: written by the kernels themselves, polled by the host
   std::vector<double> hist;
   double normr = 0.0, rtrans = 0.0, oldrtrans = 0.0;
   int k = 1;
@@ -78,6 +78,29 @@ struct CgSolver {
     if (evUsed == kProfEvents) drainMarks();
     SB_CUDA(cudaEventRecord(evPool[(size_t)evUsed], s));
     evRegion[evUsed++] = region;
+  }
+
+  // Blocks until the device has published the global rho[j]. No copy and no event sits in the stream for this: the
+  // kernel that completes the sum stores it into mapped host memory (gridSum's mirror / the p update's collect).
+  double waitRho(int j)
+  {
+    volatile unsigned long long* slot = reinterpret_cast<volatile unsigned long long*>(hRho + j);
+    for (unsigned long spins = 1;; spins++) {
+      const unsigned long long bits = *slot;
+      if (bits != kRhoPending) {
+        double v;
+        memcpy(&v, &bits, sizeof(v));
+        return v;
+      }
+      if ((spins & 0x3fff) == 0) {             // a failed or finished stream must not leave the host spinning
+        const cudaError_t e = cudaStreamQuery(s);
+        if (e == cudaSuccess) {
+          if (*slot == kRhoPending) SB_FATAL("CG: the stream drained but rho[%d] never arrived", j);
+        } else if (e != cudaErrorNotReady) {
+          SB_CUDA(e);
+        }
+      }
+    }
   }
 
   void allreduce(double* d, int op)
@@ -194,7 +217,6 @@ struct CgSolver {
     SB_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * rowSlots, s));
     SB_CUDA(cudaMemsetAsync(rho, 0, sizeof(double) * nScal, s));
     SB_CUDA(cudaMemsetAsync(pAp, 0, sizeof(double) * nScal, s));
-    for (int i = 0; i < kEventRing; i++) SB_CUDA(cudaEventCreateWithFlags(&ring[i], cudaEventDisableTiming));
     if (profile) {
       evPool.resize(kProfEvents);
       for (cudaEvent_t& e : evPool) SB_CUDA(cudaEventCreate(&e));
@@ -235,6 +257,7 @@ struct CgSolver {
     SB_CUDA(cudaMemcpyAsync(hRho, rho, sizeof(double), cudaMemcpyDeviceToHost, s));
     SB_CUDA(cudaStreamSynchronize(s));
     rtrans = hRho[0];
+    for (int j = 1; j < nScal; j++) memcpy(hRho + j, &kRhoPending, sizeof(double));
     normr = sqrt(rtrans);
     hist.push_back(normr);
     if (print) printf("Initial Residual = %E\n", normr);      // :102
@@ -258,10 +281,7 @@ struct CgSolver {
       // the normr tested before iteration k is sqrt(rho[max(k-2,0)]) -- the reference's lagging test (:107,:116)
       for (; k < stopK; k++) {
         if ((int)hist.size() < k) {                            // hist[k-1] = normr of iteration k-1 = sqrt(rho[k-2])
-          if (k >= 3) {
-            SB_CUDA(cudaEventSynchronize(ring[(k - 2) % kEventRing]));
-            normr = sqrt(hRho[k - 2]);
-          }
+          if (k >= 3) normr = sqrt(waitRho(k - 2));
           hist.push_back(normr);
           printIteration(k - 1, normr);
         }
@@ -274,30 +294,30 @@ struct CgSolver {
           FusedPut fp;
           HaloGate gate;
           if (fusedPut) gate = commFusedPutBegin(comm, &fp);    // the halo exchange (:122) rides on the p update
-          launchCgUpdateP(n, k, rho, r, p, pendingRho.size ? &pendingRho : nullptr, fusedPut ? &fp : nullptr, s);   // :109 / :111-114
+          // the p update completes the global rho[k-1] and stores it to the host mirror itself
+          launchCgUpdateP(n, k, rho, r, p, pendingRho.size ? &pendingRho : nullptr, fusedPut ? &fp : nullptr, hRho, s);   // :109 / :111-114
           mark(R_UPDATE_P);
-          if (k >= 2) {                                         // the global rho[k-1] exists now: send it to the host
-            SB_CUDA(cudaMemcpyAsync(hRho + k - 1, rho + k - 1, sizeof(double), cudaMemcpyDeviceToHost, s));
-            SB_CUDA(cudaEventRecord(ring[(k - 1) % kEventRing], s));
-          }
           const PeerReduce prPAp = commBeginReduce(comm);
           DotArgs d { pAp + k, false, 1, &prPAp };
           spmvWithHalo(&d, fusedPut ? &gate : nullptr);         // :122-125
           pendingRho = commBeginReduce(comm);
-          launchCgUpdateXR(n, k, rho, pAp, x, r, p, Ap, 2, &prPAp, &pendingRho, s);       // :126-128 (+ :112 of iteration k+1)
+          launchCgUpdateXR(n, k, rho, pAp, x, r, p, Ap, 2, &prPAp, &pendingRho, nullptr, s);   // :126-128 (+ :112 of iteration k+1)
           mark(R_UPDATE_XR);
           continue;
         }
-        launchCgUpdateP(n, k, rho, r, p, nullptr, nullptr, s); // :109 / :111-114
+        launchCgUpdateP(n, k, rho, r, p, nullptr, nullptr, nullptr, s); // :109 / :111-114
         mark(R_UPDATE_P);
         DotArgs d { pAp + k, false, 1 };
         spmvWithHalo(&d);                                      // :122-125
         allreduce(pAp + k, SB_SUM);
-        launchCgUpdateXR(n, k, rho, pAp, x, r, p, Ap, 2, nullptr, nullptr, s);   // :126-128 (+ :112 of iteration k+1)
+        // one GPU: the x/r update's grid reduction stores rho[k] to the host mirror; several GPUs with stand-alone
+        // all-reduce kernels: the global value only exists after the all-reduce, copy it from there
+        launchCgUpdateXR(n, k, rho, pAp, x, r, p, Ap, 2, nullptr, nullptr, commActive(comm) ? nullptr : hRho, s);   // :126-128 (+ :112 of iteration k+1)
         mark(R_UPDATE_XR);
-        allreduce(rho + k, SB_SUM);
-        SB_CUDA(cudaMemcpyAsync(hRho + k, rho + k, sizeof(double), cudaMemcpyDeviceToHost, s));
-        SB_CUDA(cudaEventRecord(ring[k % kEventRing], s));
+        if (commActive(comm)) {
+          allreduce(rho + k, SB_SUM);
+          SB_CUDA(cudaMemcpyAsync(hRho + k, rho + k, sizeof(double), cudaMemcpyDeviceToHost, s));
+        }
       }
     } else {
       // the reference's call sequence through the drop-in entry points (host scalars, 5 kernels + 2 syncs / iteration)
@@ -364,7 +384,6 @@ struct CgSolver {
       }
     }
     for (cudaEvent_t e : evPool) cudaEventDestroy(e);
-    for (int i = 0; i < kEventRing; i++) SB_CUDA(cudaEventDestroy(ring[i]));
     sbFree(r); sbFree(Ap); sbFree(x); sbFree(b); sbFree(tmp); sbFree(rho); sbFree(pAp);
     if (!pBorrowed) sbFree(p);
     sbFreeHost(hRho);

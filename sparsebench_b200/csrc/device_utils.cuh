@@ -63,8 +63,10 @@ __device__ __forceinline__ double blockSum(double v, double* scratch)
 // With `push` (multi-GPU) the last block additionally stores the sum into slot [rank] of every peer's control
 // window -- the first half of an all-reduce whose second half (peerCollect) runs in the prologue of the kernel
 // that consumes the scalar, so no separate all-reduce launch sits between the two.
+// `mirror` (optional): a second place the final value is stored to -- the solver passes mapped pinned host memory, so
+// the host sees rho[k] without a copy or an event in the stream.
 __device__ __forceinline__ void gridSum(double blockPartial, double* partials, unsigned int* ticket, double* out,
-    bool accumulate, double* scratch, const PeerReduce* push = nullptr)
+    bool accumulate, double* scratch, const PeerReduce* push = nullptr, double* mirror = nullptr)
 {
   __shared__ bool amLast;
   if (threadIdx.x == 0) {
@@ -82,6 +84,7 @@ __device__ __forceinline__ void gridSum(double blockPartial, double* partials, u
     if (threadIdx.x == 0) {
       v = accumulate ? (*out + v) : v;
       *out = v;
+      if (mirror) *(volatile double*)mirror = v;
       scratch[0] = v;
     }
     if (push && push->size > 0) {
@@ -121,6 +124,14 @@ __device__ __forceinline__ double peerCollect(const PeerReduce& pr, double* vals
   __syncthreads();
   return acc;
 }
+
+// ---- programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor in the stream is still draining. Everything it does before griddepWait() must touch
+// only data no kernel ever writes (the matrix arrays, its own shared memory); griddepWait() returns when the
+// predecessor has completed and its writes are visible. Every kernel of a PDL chain executes both calls, so the order
+// is transitive. Without the launch attribute both are no-ops.
+__device__ __forceinline__ void griddepLaunchDependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddepWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- mbarrier + 1-D bulk copy (TMA, SASS UBLKCP): asynchronous global -> shared streaming of the matrix
 __device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -166,6 +177,14 @@ __device__ __forceinline__ void bulkLoad(void* smemDst, const void* gmemSrc, uin
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
                    smemAddr(smemDst)),
                "l"(gmemSrc), "r"(bytes), "r"(smemAddr(bar)), "l"(l2EvictFirstPolicy())
+               : "memory");
+}
+
+// the same copy without the evict-first hint: for data that is used again (vector entries)
+__device__ __forceinline__ void bulkLoadKeep(void* smemDst, const void* gmemSrc, uint32_t bytes, uint64_t* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(smemDst)),
+               "l"(gmemSrc), "r"(bytes), "r"(smemAddr(bar))
                : "memory");
 }
 

@@ -43,6 +43,12 @@ Context& ctx()
   return g_ctx;
 }
 
+bool pdlEnabled()
+{
+  static const bool on = getenv("SB_NO_PDL") == nullptr;
+  return on;
+}
+
 bool isDevicePointer(const void* p)
 {
   if (!p) return false;

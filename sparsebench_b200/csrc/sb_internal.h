@@ -49,6 +49,25 @@ inline void countLaunch(int n = 1) { ctx().launches += (size_t)n; }
 
 bool isDevicePointer(const void* p);
 
+// Kernel launch with the programmatic-dependent-launch attribute (device_utils.cuh: griddepWait). SB_NO_PDL=1 turns
+// the attribute off (plain stream order) for A/B measurements.
+bool pdlEnabled();
+template <typename... KArgs, typename... Args>
+inline void launchPdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdlEnabled() ? 1 : 0;
+  SB_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+
 // ---- sparse formats: device-side views the kernels take
 struct CrsView {
   uint32_t nr;
@@ -120,10 +139,12 @@ void launchDot(uint32_t n, const double* x, const double* y, double* dResult, in
 // fused CG passes: rho[j] = r_j.r_j, pAp[k] = p_k.Ap_k live on the device, k is the 1-based iteration
 // collect*: the scalar this kernel needs (rho[k-1] resp. pAp[k]) is still spread over the peer window and is summed
 // in the kernel's prologue; pushRho: rho[k] is pushed to the peers instead of being all-reduced by a separate kernel
+// hostRho: mapped pinned mirror of rho[] -- the kernel that produces the GLOBAL rho[j] also stores it there
 void launchCgUpdateP(uint32_t n, int k, double* rho, const double* r, double* p, const PeerReduce* collectRho,
-    const FusedPut* put, cudaStream_t s);
+    const FusedPut* put, double* hostRho, cudaStream_t s);
 void launchCgUpdateXR(uint32_t n, int k, double* rho, double* pAp, double* x, double* r, const double* p,
-    const double* Ap, int slot, const PeerReduce* collectPAp, const PeerReduce* pushRho, cudaStream_t s);
+    const double* Ap, int slot, const PeerReduce* collectPAp, const PeerReduce* pushRho, double* hostRho, cudaStream_t s);
+
 void launchInitVectors(uint32_t n, const uint32_t* rowPtr, const uint32_t* rowLen, bool generated, double* x, double* b,
     cudaStream_t s);
 void launchScatter(uint32_t n, const uint32_t* map, const double* in, double* out, cudaStream_t s);   // out[map[i]] = in[i]

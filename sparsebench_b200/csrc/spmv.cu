@@ -109,6 +109,7 @@ spmvSell32TmaKernel(SellView A, const double* __restrict__ x, double* __restrict
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char* mine = ring + (size_t)warp * S * kStageBytes;
   uint64_t* bar = bars + warp * S;
+  griddepLaunchDependents();
   if (GATED && threadIdx.x == 0) gateStore(gateSmem, gate);
   if (lane == 0) {
 #pragma unroll
@@ -163,6 +164,8 @@ spmvSell32TmaKernel(SellView A, const double* __restrict__ x, double* __restrict
   };
 #pragma unroll
   for (int s = 0; s < S; s++) produce(s);
+  // up to here only the matrix has been touched: the rings are filling while the previous kernel drains
+  griddepWait();
 
   int cs = 0;
   uint32_t phases = 0;
@@ -251,13 +254,12 @@ static void launchSell32TmaCfg(const SellView& A, const double* x, double* y, ui
   const uint32_t rot = g ? g->rot : 0u, nInt = g ? g->nInterior : 0u;
   const HaloGate gate = g ? g->gate : HaloGate();
   if (dot)
-    spmvSell32TmaKernel<true, WARPS, J, S, U, LOCKSTEP, GATED><<<(int)blocks, WARPS * 32, smem, s>>>(A, x, y, lo, hi,
-        c.partials + (size_t)dot->slot * kMaxPartials, c.tickets + dot->slot, dot->out, dot->accumulate, rot, nInt, gate,
+    launchPdl(spmvSell32TmaKernel<true, WARPS, J, S, U, LOCKSTEP, GATED>, dim3((unsigned)blocks), dim3(WARPS * 32), smem, s, A, x, y, lo,
+        hi, c.partials + (size_t)dot->slot * kMaxPartials, c.tickets + dot->slot, dot->out, dot->accumulate, rot, nInt, gate,
         dot->push ? *dot->push : PeerReduce());
   else
-    spmvSell32TmaKernel<false, WARPS, J, S, U, LOCKSTEP, GATED><<<(int)blocks, WARPS * 32, smem, s>>>(A, x, y, lo, hi,
-        nullptr, nullptr, nullptr, false, rot, nInt, gate, PeerReduce());
-  SB_CUDA(cudaGetLastError());
+    launchPdl(spmvSell32TmaKernel<false, WARPS, J, S, U, LOCKSTEP, GATED>, dim3((unsigned)blocks), dim3(WARPS * 32), smem, s, A, x, y, lo,
+        hi, (double*)nullptr, (unsigned int*)nullptr, (double*)nullptr, false, rot, nInt, gate, PeerReduce());
   countLaunch();
 }
 
@@ -376,6 +378,9 @@ spmvSellAnyCKernel(SellView A, const double* __restrict__ x, double* __restrict_
 // touch rowPtr/col/val in global memory, and the number of consumer warps is independent of the bytes in
 // flight. Tiles whose non-zeros do not fit a stage are read straight from global memory by the same lanes.
 constexpr uint32_t kPipeMaxRows = 768;                  // row pointers per stage
+constexpr int kRowsVar = 12;                            // default VAR of spmvRowsPipeKernel (see there; sweep in profiles/README.md)
+// fused dot: the tile's own x entries are staged behind the ring, one slot of kPipeXBytes per stage
+constexpr uint32_t kPipeXBytes = (kPipeMaxRows + 8) * 8;
 
 template <int WARPS, uint32_t CAP, uint32_t STAGES>
 struct CrsPipe {                                        // stage: val[CAP+8] | col[CAP+8] | rowPtr[kPipeMaxRows+8]
@@ -453,7 +458,17 @@ struct CcrsPipe {                                       // stage: {col, pad, val
 // GATED launches cover all rows in one go as three runs of tiles: the interior rows [intLo, intHi) first, then the
 // rows above and below, which reference halo columns; a consumer warp waits on the gate before its first tile of
 // those (x gathers of a gated kernel are coherent loads: the peers store the halo while this kernel is running).
-template <bool DOT, int LPR, typename L, bool GATED>
+// VAR (bit mask; measured on the 27-point stencil, profiles/README.md):
+//   1  the row's own x for the fused dot is requested BEFORE the gathers of the pass (no gain: not latency)
+//   2  a row's lanes start at the row start rounded up to LPR elements -- their shared-memory reads then fall into one
+//      aligned LPR*8-byte window per step, rows of a half-warp into different bank groups -- and the 0..LPR-1 leading
+//      elements take one extra predicated slot (removes the bank conflicts, but no faster: not the limiter)
+//   4  7 instead of 8 elements per lane and batch: lanes per row = avg/7, so one batch is a whole row (-1..2 %)
+//   8  fused dot: the tile's own x entries arrive with the tile through the bulk-copy engine (one more 16-byte
+//      granular copy per tile into a slot behind the ring) instead of through one more global load per row:
+//      fused-dot cost +2.0 % -> +1.0 % at 256^3, +3.3 % -> +1.7 % at 128^3
+// Default: 12.
+template <bool DOT, int LPR, typename L, bool GATED, int VAR>
 __global__ void __launch_bounds__((L::kWarps + 1) * 32, 1)
 spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __restrict__ x, double* __restrict__ y,
     uint32_t lo, uint32_t hi, uint32_t tileRows, double* partials, unsigned int* ticket, double* dotOut, bool accumulate,
@@ -465,9 +480,12 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
   __shared__ GateSmem gateSmem;
   constexpr uint32_t S = L::kStages;
   constexpr int kPipeWarps = L::kWarps;
-  constexpr int UN = 8;                                  // elements per lane per batch
+  constexpr bool EARLYX = (VAR & 1) != 0, ALIGN = (VAR & 2) != 0, XSMEM = (VAR & 8) != 0;
+  constexpr int UN = (VAR & 4) ? 7 : 8;                  // slots per lane per batch
+  constexpr int HEAD = ALIGN ? 1 : 0;                    // slot 0 of a row's first batch: its unaligned leading elements
   constexpr int GPW = 32 / LPR;                          // rows per warp per pass
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  griddepLaunchDependents();
   if (threadIdx.x == 0) {
     if (GATED) gateStore(gateSmem, gate);
     for (uint32_t s = 0; s < S; s++) {
@@ -501,11 +519,26 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
 
   double dotAcc = 0.0;
   if (warp == kPipeWarps) {
-    // ---- producer: one thread keeps the ring full
+    // ---- producer: one thread keeps the ring full. The first S tiles are requested before griddepWait(): only the
+    // matrix is touched, so the ring fills while the previous kernel drains; their x entries (fused dot) follow it.
     if (lane == 0) {
       uint32_t i = 0;
+      bool waited = false;
       for (uint64_t t = blockIdx.x; t < nTiles; t += gridDim.x, i++) {
         const uint32_t s = i % S, k = i / S;
+        if (k > 0 && !waited) {
+          griddepWait();
+          waited = true;
+          if (DOT && XSMEM) {                                  // x entries of the tiles requested so far
+            uint32_t j = 0;
+            for (uint64_t t2 = blockIdx.x; j < S && t2 < nTiles; t2 += gridDim.x, j++) {
+              uint64_t q0, q1;
+              tileRange(t2, q0, q1);
+              const uint64_t ax = q0 & ~1ull;
+              bulkLoadKeep(ring + (size_t)S * L::kBytes + (size_t)j * kPipeXBytes, x + ax, (uint32_t)((q1 - ax + 1) & ~1ull) * 8, fullBar + j);
+            }
+          }
+        }
         uint64_t r0, r1;
         tileRange(t, r0, r1);
         const uint64_t bs = __ldg(rowPtr + r0), be = __ldg(rowPtr + r1);
@@ -514,13 +547,30 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
         const bool fits = be > bs && be - L::origin(bs) <= L::kCap;
         if (k > 0) mbarWait(emptyBar + s, (k - 1) & 1u);
         unsigned char* dst = ring + (size_t)s * L::kBytes;
-        mbarExpectTx(fullBar + s, nrp * 4 + (fits ? L::bytes(bs, be) : 0u));
+        // fused dot: the tile's own x entries ride along (16-byte granularity: from the even row at or below r0)
+        const uint64_t ax = r0 & ~1ull;
+        const uint32_t nxr = DOT && XSMEM ? (uint32_t)((r1 - ax + 1) & ~1ull) : 0u;
+        mbarExpectTx(fullBar + s, nrp * 4 + nxr * 8 + (fits ? L::bytes(bs, be) : 0u));
         bulkLoad(dst + L::kRpOff, rowPtr + a, nrp * 4, fullBar + s);
+        if (DOT && XSMEM && waited) bulkLoadKeep(ring + (size_t)S * L::kBytes + (size_t)s * kPipeXBytes, x + ax, nxr * 8, fullBar + s);
         if (fits) acc.request(dst, bs, be, fullBar + s);
+      }
+      if (!waited) {                                           // fewer than S + 1 tiles: nothing was waited for yet
+        griddepWait();
+        if (DOT && XSMEM) {
+          uint32_t j = 0;
+          for (uint64_t t2 = blockIdx.x; j < S && t2 < nTiles; t2 += gridDim.x, j++) {
+            uint64_t q0, q1;
+            tileRange(t2, q0, q1);
+            const uint64_t ax = q0 & ~1ull;
+            bulkLoadKeep(ring + (size_t)S * L::kBytes + (size_t)j * kPipeXBytes, x + ax, (uint32_t)((q1 - ax + 1) & ~1ull) * 8, fullBar + j);
+          }
+        }
       }
     }
   } else {
     // ---- consumers
+    griddepWait();                                             // x (and y) belong to the previous kernels
     const int sub = lane % LPR, grp = lane / LPR;
     bool gatePassed = false;
     uint32_t i = 0;
@@ -537,6 +587,7 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
       mbarWait(fullBar + s, k & 1u);
       const unsigned char* st = ring + (size_t)s * L::kBytes;
       const uint32_t* rp = reinterpret_cast<const uint32_t*>(st + L::kRpOff) + (uint32_t)(r0 & 3ull);
+      const double* xrow = reinterpret_cast<const double*>(ring + (size_t)S * L::kBytes + (size_t)s * kPipeXBytes) + (uint32_t)(r0 & 1ull);   // x[r0 + i] (DOT && XSMEM only)
       const uint64_t bs = rp[0], be = rp[nrows];
       const uint64_t org = L::origin(bs);
       const bool fits = be > bs && be - org <= L::kCap;
@@ -544,34 +595,44 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
         const uint32_t g = g0 + grp;
         const bool live = g < nrows;
         const uint32_t rs = live ? rp[g] : 0u, re = live ? rp[g + 1] : 0u;
-        double sum = 0.0;
+        double sum = 0.0, xr = 0.0;
+        if (DOT && EARLYX && live && sub == 0) xr = gatherX<GATED>(x + r0 + g);   // in flight together with the gathers below
         if (fits) {
           // lanes without a row get an empty range (0 - org would wrap and alias real entries)
-          uint32_t idx = live ? rs - (uint32_t)org + sub : 0u;
+          const uint32_t first = live ? rs - (uint32_t)org : 0u;
           const uint32_t end = live ? re - (uint32_t)org : 0u;
-          while (__any_sync(0xffffffffu, idx < end)) {
+          const uint32_t start = ALIGN ? min((first + (uint32_t)LPR - 1u) & ~((uint32_t)LPR - 1u), end) : first;
+          uint32_t idx = start + sub;
+          bool head = ALIGN && first + sub < start;     // this lane owns one of the leading elements
+          do {
             double vv[UN], xx[UN];
             if constexpr (L::kSplitFetch) {
+              if (HEAD && head) xx[0] = gatherX<GATED>(x + L::fetchCol(st, first + sub));
 #pragma unroll
-              for (int u = 0; u < UN; u++)
-                if (idx + u * LPR < end) xx[u] = gatherX<GATED>(x + L::fetchCol(st, idx + u * LPR));
+              for (int u = HEAD; u < UN; u++)
+                if (idx + (u - HEAD) * LPR < end) xx[u] = gatherX<GATED>(x + L::fetchCol(st, idx + (u - HEAD) * LPR));
+              if (HEAD && head) vv[0] = L::fetchVal(st, first + sub);
 #pragma unroll
-              for (int u = 0; u < UN; u++)
-                if (idx + u * LPR < end) vv[u] = L::fetchVal(st, idx + u * LPR);
+              for (int u = HEAD; u < UN; u++)
+                if (idx + (u - HEAD) * LPR < end) vv[u] = L::fetchVal(st, idx + (u - HEAD) * LPR);
             } else {
               uint32_t cc[UN];
+              if (HEAD && head) L::fetch(st, first + sub, cc[0], vv[0]);
 #pragma unroll
-              for (int u = 0; u < UN; u++)
-                if (idx + u * LPR < end) L::fetch(st, idx + u * LPR, cc[u], vv[u]);
+              for (int u = HEAD; u < UN; u++)
+                if (idx + (u - HEAD) * LPR < end) L::fetch(st, idx + (u - HEAD) * LPR, cc[u], vv[u]);
+              if (HEAD && head) xx[0] = gatherX<GATED>(x + cc[0]);
 #pragma unroll
-              for (int u = 0; u < UN; u++)
-                if (idx + u * LPR < end) xx[u] = gatherX<GATED>(x + cc[u]);
+              for (int u = HEAD; u < UN; u++)
+                if (idx + (u - HEAD) * LPR < end) xx[u] = gatherX<GATED>(x + cc[u]);
             }
+            if (HEAD && head) sum = mulAdd(sum, vv[0], xx[0]);
 #pragma unroll
-            for (int u = 0; u < UN; u++)
-              if (idx + u * LPR < end) sum = mulAdd(sum, vv[u], xx[u]);
-            idx += UN * LPR;
-          }
+            for (int u = HEAD; u < UN; u++)
+              if (idx + (u - HEAD) * LPR < end) sum = mulAdd(sum, vv[u], xx[u]);
+            idx += (UN - HEAD) * LPR;
+            head = false;
+          } while (__any_sync(0xffffffffu, idx < end));
         } else {
           for (uint64_t j = (uint64_t)rs + sub; j < re; j += LPR) {   // oversized tile: straight from global memory
             uint32_t c;
@@ -584,7 +645,7 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
         for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         if (live && sub == 0) {
           y[r0 + g] = sum;
-          if (DOT) dotAcc = fma(sum, __ldg(x + r0 + g), dotAcc);   // L1 hit: the row's own diagonal was just gathered
+          if (DOT) dotAcc = fma(sum, XSMEM ? xrow[g] : EARLYX ? xr : gatherX<GATED>(x + r0 + g), dotAcc);
         }
       }
       __syncwarp();
@@ -602,16 +663,18 @@ struct RowsGate {                                     // extra arguments of a ga
   HaloGate gate;
 };
 
-template <int LPR, typename L, bool GATED>
+template <int LPR, typename L, bool GATED, int VAR>
 static void launchRowsPipe(L acc, const uint32_t* rowPtr, const double* x, double* y, uint32_t lo, uint32_t hi,
     uint32_t tileRows, const DotArgs* dot, const RowsGate* g, cudaStream_t s)
 {
   Context& c = ctx();
-  const size_t smem = (size_t)L::kStages * L::kBytes;
+  const size_t smemPlain = (size_t)L::kStages * L::kBytes;
+  const size_t smemDot = smemPlain + ((VAR & 8) ? (size_t)L::kStages * kPipeXBytes : 0);
+  const size_t smem = dot ? smemDot : smemPlain;
   static bool configured = false;
   if (!configured) {
-    allowLargeSmem(spmvRowsPipeKernel<true, LPR, L, GATED>, smem);
-    allowLargeSmem(spmvRowsPipeKernel<false, LPR, L, GATED>, smem);
+    allowLargeSmem(spmvRowsPipeKernel<true, LPR, L, GATED, VAR>, smemDot);
+    allowLargeSmem(spmvRowsPipeKernel<false, LPR, L, GATED, VAR>, smemPlain);
     configured = true;
   }
   uint64_t blocks = ((uint64_t)(hi - lo) + tileRows - 1) / tileRows + (GATED ? 2 : 0);
@@ -620,13 +683,12 @@ static void launchRowsPipe(L acc, const uint32_t* rowPtr, const double* x, doubl
   const uint32_t intLo = g ? g->intLo : 0u, intHi = g ? g->intHi : 0u;
   const HaloGate gate = g ? g->gate : HaloGate();
   if (dot)
-    spmvRowsPipeKernel<true, LPR, L, GATED><<<(int)blocks, threads, smem, s>>>(acc, rowPtr, x, y, lo, hi, tileRows,
-        c.partials + (size_t)dot->slot * kMaxPartials, c.tickets + dot->slot, dot->out, dot->accumulate, intLo, intHi, gate,
+    launchPdl(spmvRowsPipeKernel<true, LPR, L, GATED, VAR>, dim3((unsigned)blocks), dim3(threads), smem, s, acc, rowPtr, x, y, lo, hi,
+        tileRows, c.partials + (size_t)dot->slot * kMaxPartials, c.tickets + dot->slot, dot->out, dot->accumulate, intLo, intHi, gate,
         dot->push ? *dot->push : PeerReduce());
   else
-    spmvRowsPipeKernel<false, LPR, L, GATED><<<(int)blocks, threads, smem, s>>>(acc, rowPtr, x, y, lo, hi, tileRows, nullptr,
-        nullptr, nullptr, false, intLo, intHi, gate, PeerReduce());
-  SB_CUDA(cudaGetLastError());
+    launchPdl(spmvRowsPipeKernel<false, LPR, L, GATED, VAR>, dim3((unsigned)blocks), dim3(threads), smem, s, acc, rowPtr, x, y, lo, hi,
+        tileRows, (double*)nullptr, (unsigned int*)nullptr, (double*)nullptr, false, intLo, intHi, gate, PeerReduce());
   countLaunch();
 }
 
@@ -637,7 +699,7 @@ struct CrsAccess {
   const double* val;
   template <int W, uint32_t CAP, uint32_t S> using Pipe = CrsPipe<W, CAP, S>;
   template <typename P> P pipe() const { return P { col, val }; }
-  static constexpr uint32_t kStagesFor3584 = 5, kStagesFor5376 = 3;
+  static constexpr uint32_t kStagesFor3584 = 4, kStagesFor5376 = 3;   // 4 x 46 KB + the x slots of the fused dot
   static constexpr int kDefaultCfg = 0;                 // 23 consumer warps (+1 producer = 6 warps per scheduler, 80 registers), 3 stages of 66 KB
   __device__ __forceinline__ void load(uint64_t j, uint32_t& c, double& v) const
   {
@@ -741,19 +803,34 @@ static bool tryRowsPipe(Access acc, const uint32_t* rowPtr, double avg, const do
   if (tileRows > kPipeMaxRows) tileRows = (kPipeMaxRows / rowsPerPass) * rowsPerPass;
   if (tileRows < rowsPerPass) return false;
   if (probeOnly) return true;
-#define SB_PIPE(LPRV)                                                                                            \
-  do {                                                                                                           \
-    if (g) launchRowsPipe<LPRV, P, true>(acc.template pipe<P>(), rowPtr, x, y, lo, hi, tileRows, dot, g, s);     \
-    else launchRowsPipe<LPRV, P, false>(acc.template pipe<P>(), rowPtr, x, y, lo, hi, tileRows, dot, nullptr, s); \
+#define SB_PIPE_V(LPRV, V)                                                                                          \
+  do {                                                                                                              \
+    if (g) launchRowsPipe<LPRV, P, true, V>(acc.template pipe<P>(), rowPtr, x, y, lo, hi, tileRows, dot, g, s);      \
+    else launchRowsPipe<LPRV, P, false, V>(acc.template pipe<P>(), rowPtr, x, y, lo, hi, tileRows, dot, nullptr, s); \
   } while (0)
+#define SB_PIPE(LPRV) SB_PIPE_V(LPRV, kRowsVar)
+  static const int var = envInt("SB_ROWS_VAR", kRowsVar);       // tuning knob for the 4-lanes-per-row case (the stencil)
   switch (lpr) {
   case 1: SB_PIPE(1); break;
   case 2: SB_PIPE(2); break;
-  case 4: SB_PIPE(4); break;
+  case 4:
+    switch (var) {
+    case 0: SB_PIPE_V(4, 0); break;
+    case 1: SB_PIPE_V(4, 1); break;
+    case 2: SB_PIPE_V(4, 2); break;
+    case 3: SB_PIPE_V(4, 3); break;
+    case 4: SB_PIPE_V(4, 4); break;
+    case 5: SB_PIPE_V(4, 5); break;
+    case 8: SB_PIPE_V(4, 8); break;
+    case 12: SB_PIPE_V(4, 12); break;
+    default: SB_PIPE(4); break;
+    }
+    break;
   case 8: SB_PIPE(8); break;
   case 16: SB_PIPE(16); break;
   default: SB_PIPE(32); break;
   }
+#undef SB_PIPE_V
 #undef SB_PIPE
   return true;
 }
@@ -937,6 +1014,15 @@ int sbSpmvOrdered(void* matrix, int fmt, const CG_FLOAT* x, CG_FLOAT* y, CG_UINT
   if (!spmvGatedAvailable(A)) return 0;
   launchSpmvGated(A, x, y, intLo, intHi, HaloGate(), nullptr, ctx().stream);
   return 1;
+}
+
+void sbSpmvDot(void* matrix, int fmt, const CG_FLOAT* x, CG_FLOAT* y, CG_FLOAT* dDot)
+{
+  // y = A x fused with *dDot = sum_i x[i] y[i] (device scalar; CGSolver.c:123-125 in one pass), the kernel the CG
+  // loop runs. Vectors in solver order: for SCS with sigma > 1 that is the permuted row order for x AND y.
+  Operator A = makeOperator(matrix, fmt);
+  DotArgs d { dDot, false, 1 };
+  launchSpmv(A, x, y, 0, spmvUnits(A), &d, ctx().stream);
 }
 
 void sbSCS_spMVM(SbSCSMatrix* m, const CG_FLOAT* x, CG_FLOAT* y)

@@ -129,13 +129,49 @@ void launchDot(uint32_t n, const double* x, const double* y, double* dResult, in
 // vector is one pass of the grid, so the kernels are a single DRAM/L2 round trip instead of a dependent chain.
 constexpr int kVecUnroll = 4;
 
+// KEEP: when all CG vectors together fit the 126 MB L2 (small problems), their lines are tagged evict_last, so that
+// the matrix stream of the SpMV in between (tagged evict_first by the bulk copies) cannot push them out and the
+// vector kernels run out of L2 instead of HBM.
+__device__ __forceinline__ uint64_t l2EvictLastPolicy()
+{
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+  return policy;
+}
+template <bool KEEP>
+__device__ __forceinline__ double2 ldVec(const double2* p, uint64_t policy)
+{
+  if (!KEEP) return *p;
+  double2 v;
+  asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(policy) : "memory");
+  return v;
+}
+template <bool KEEP>
+__device__ __forceinline__ void stVec(double2* p, double2 v, uint64_t policy)
+{
+  if (!KEEP) {
+    *p = v;
+    return;
+  }
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(policy) : "memory");
+}
+// all CG vectors (r, p, Ap, x, b) of this size fit L2 with room for the stream
+static inline bool vectorsFitL2(uint32_t n)
+{
+  static const int knob = getenv("SB_VEC_KEEP") ? atoi(getenv("SB_VEC_KEEP")) : 1;
+  return knob != 0 && (uint64_t)n * 8 * 5 <= ((uint64_t)96 << 20);
+}
+
 // p = r + beta*p with beta = rho[k-1]/rho[k-2]  (CGSolver.c:111-114); k == 1: p = r + 0*r (:109).
+template <bool KEEP>
 __global__ void __launch_bounds__(kVecThreads)
 cgUpdatePKernel(uint32_t n, int k, double* rho, const double* __restrict__ r, double* __restrict__ p, PeerReduce collectRho,
-    FusedPut put)
+    FusedPut put, double* hostRho)
 {
   __shared__ double peerVals[kMaxRanks];
   __shared__ unsigned int delivered[kMaxFusedDests];     // halo elements this block stored at each neighbour
+  griddepLaunchDependents();
+  griddepWait();
   if (put.ndest > 0 && threadIdx.x < kMaxFusedDests) delivered[threadIdx.x] = 0;
   // multi-GPU: a freshly computed p[e] that a neighbour needs goes straight behind that neighbour's local rows
   auto deliver = [&](uint32_t e, double v) {
@@ -154,13 +190,17 @@ cgUpdatePKernel(uint32_t n, int k, double* rho, const double* __restrict__ r, do
   const uint64_t n2 = n / 2;
   const double2* r2 = reinterpret_cast<const double2*>(r);
   double2* p2 = reinterpret_cast<double2*>(p);
+  const uint64_t keep = KEEP ? l2EvictLastPolicy() : 0;
   // multi-GPU: rho[k-1] was pushed to the peer windows by the previous x/r update; sum it here (every block gets
   // the same bits) and let one thread store the global value for the host's convergence test
   double rtrans = 0.0;
   if (k > 1) {
     if (collectRho.size > 0) {
       rtrans = peerCollect(collectRho, peerVals);
-      if (tid == 0) rho[k - 1] = rtrans;
+      if (tid == 0) {
+        rho[k - 1] = rtrans;
+        if (hostRho) *(volatile double*)(hostRho + k - 1) = rtrans;   // the global value, for the host's convergence test
+      }
     } else {
       rtrans = rho[k - 1];
     }
@@ -172,8 +212,8 @@ cgUpdatePKernel(uint32_t n, int k, double* rho, const double* __restrict__ r, do
 #pragma unroll
     for (int u = 0; u < kVecUnroll; u++)
       if (i0 + u * stride < n2) {
-        a[u] = r2[i0 + u * stride];
-        b[u] = k == 1 ? a[u] : p2[i0 + u * stride];
+        a[u] = ldVec<KEEP>(r2 + i0 + u * stride, keep);
+        b[u] = k == 1 ? a[u] : ldVec<KEEP>(p2 + i0 + u * stride, keep);
       }
 #pragma unroll
     for (int u = 0; u < kVecUnroll; u++)
@@ -181,7 +221,7 @@ cgUpdatePKernel(uint32_t n, int k, double* rho, const double* __restrict__ r, do
         double2 o;
         o.x = __dadd_rn(a[u].x, __dmul_rn(beta, b[u].x));
         o.y = __dadd_rn(a[u].y, __dmul_rn(beta, b[u].y));
-        p2[i0 + u * stride] = o;
+        stVec<KEEP>(p2 + i0 + u * stride, o, keep);
         if (put.ndest > 0) {
           const uint32_t e = (uint32_t)(2 * (i0 + u * stride));
           deliver(e, o.x);
@@ -206,13 +246,16 @@ cgUpdatePKernel(uint32_t n, int k, double* rho, const double* __restrict__ r, do
 
 // alpha = rho[k-1]/pAp[k]; x += alpha*p; r += (-alpha)*Ap; rho[k] = r.r   (CGSolver.c:126-128 + :112 of the
 // next iteration, which reads the same r)
+template <bool KEEP>
 __global__ void __launch_bounds__(kVecThreads)
 cgUpdateXRKernel(uint32_t n, int k, double* rho, double* pAp, double* __restrict__ x,
     double* __restrict__ r, const double* __restrict__ p, const double* __restrict__ Ap, double* partials,
-    unsigned int* ticket, PeerReduce collectPAp, PeerReduce pushRho)
+    unsigned int* ticket, PeerReduce collectPAp, PeerReduce pushRho, double* hostRho)
 {
   __shared__ double scratch[32];
   __shared__ double peerVals[kMaxRanks];
+  griddepLaunchDependents();
+  griddepWait();
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   double pApK;
@@ -229,16 +272,17 @@ cgUpdateXRKernel(uint32_t n, int k, double* rho, double* pAp, double* __restrict
   double2* r2 = reinterpret_cast<double2*>(r);
   const double2* p2 = reinterpret_cast<const double2*>(p);
   const double2* q2 = reinterpret_cast<const double2*>(Ap);
+  const uint64_t keep = KEEP ? l2EvictLastPolicy() : 0;
   double a0 = 0.0, a1 = 0.0;
   for (uint64_t i0 = tid; i0 < n2; i0 += 2 * stride) {
     double2 xv[2], pv[2], rv[2], qv[2];
 #pragma unroll
     for (int u = 0; u < 2; u++)
       if (i0 + u * stride < n2) {
-        xv[u] = x2[i0 + u * stride];
-        pv[u] = p2[i0 + u * stride];
-        rv[u] = r2[i0 + u * stride];
-        qv[u] = q2[i0 + u * stride];
+        xv[u] = ldVec<KEEP>(x2 + i0 + u * stride, keep);
+        pv[u] = ldVec<KEEP>(p2 + i0 + u * stride, keep);
+        rv[u] = ldVec<KEEP>(r2 + i0 + u * stride, keep);
+        qv[u] = ldVec<KEEP>(q2 + i0 + u * stride, keep);
       }
 #pragma unroll
     for (int u = 0; u < 2; u++)
@@ -248,8 +292,8 @@ cgUpdateXRKernel(uint32_t n, int k, double* rho, double* pAp, double* __restrict
         xo.y = __dadd_rn(xv[u].y, __dmul_rn(alpha, pv[u].y));
         ro.x = __dadd_rn(rv[u].x, __dmul_rn(nalpha, qv[u].x));
         ro.y = __dadd_rn(rv[u].y, __dmul_rn(nalpha, qv[u].y));
-        x2[i0 + u * stride] = xo;
-        r2[i0 + u * stride] = ro;
+        stVec<KEEP>(x2 + i0 + u * stride, xo, keep);
+        stVec<KEEP>(r2 + i0 + u * stride, ro, keep);
         a0 = fma(ro.x, ro.x, a0);
         a1 = fma(ro.y, ro.y, a1);
       }
@@ -263,31 +307,33 @@ cgUpdateXRKernel(uint32_t n, int k, double* rho, double* pAp, double* __restrict
     acc = fma(ro, ro, acc);
   }
   const double b = blockSum(acc, scratch);
-  gridSum(b, partials, ticket, rho + k, false, scratch, pushRho.size ? &pushRho : nullptr);
+  gridSum(b, partials, ticket, rho + k, false, scratch, pushRho.size ? &pushRho : nullptr, hostRho ? hostRho + k : nullptr);
 }
 
 void launchCgUpdateP(uint32_t n, int k, double* rho, const double* r, double* p, const PeerReduce* collectRho,
-    const FusedPut* put, cudaStream_t s)
+    const FusedPut* put, double* hostRho, cudaStream_t s)
 {
   if (n == 0 && !collectRho) return;
-  cgUpdatePKernel<<<vecGrid(n, 2 * kVecUnroll), kVecThreads, 0, s>>>(n, k, rho, r, p, collectRho ? *collectRho : PeerReduce(),
-      put ? *put : FusedPut());
-  SB_CUDA(cudaGetLastError());
+  launchPdl(vectorsFitL2(n) ? cgUpdatePKernel<true> : cgUpdatePKernel<false>, dim3((unsigned)vecGrid(n, 2 * kVecUnroll)),
+      dim3(kVecThreads), 0, s, n, k, rho, r, p, collectRho ? *collectRho : PeerReduce(), put ? *put : FusedPut(),
+      collectRho ? hostRho : (double*)nullptr);
   countLaunch();
 }
 
 void launchCgUpdateXR(uint32_t n, int k, double* rho, double* pAp, double* x, double* r, const double* p,
-    const double* Ap, int slot, const PeerReduce* collectPAp, const PeerReduce* pushRho, cudaStream_t s)
+    const double* Ap, int slot, const PeerReduce* collectPAp, const PeerReduce* pushRho, double* hostRho, cudaStream_t s)
 {
   Context& c = ctx();
   if (n == 0 && !collectPAp && !pushRho) {
     SB_CUDA(cudaMemsetAsync(rho + k, 0, sizeof(double), s));
+    if (hostRho) SB_CUDA(cudaMemcpyAsync(hostRho + k, rho + k, sizeof(double), cudaMemcpyDeviceToHost, s));
     return;
   }
-  cgUpdateXRKernel<<<vecGrid(n, 4), kVecThreads, 0, s>>>(n, k, rho, pAp, x, r, p, Ap,
+  // with pushRho the local sum is not the global one yet: the next p update publishes that
+  launchPdl(vectorsFitL2(n) ? cgUpdateXRKernel<true> : cgUpdateXRKernel<false>, dim3((unsigned)vecGrid(n, 4)), dim3(kVecThreads), 0,
+      s, n, k, rho, pAp, x, r, p, Ap,
       c.partials + (size_t)slot * kMaxPartials, c.tickets + slot, collectPAp ? *collectPAp : PeerReduce(),
-      pushRho ? *pushRho : PeerReduce());
-  SB_CUDA(cudaGetLastError());
+      pushRho ? *pushRho : PeerReduce(), pushRho ? (double*)nullptr : hostRho);
   countLaunch();
 }
 

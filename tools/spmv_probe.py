@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--dirty", action="store_true")
     ap.add_argument("--ordered", action="store_true")
+    ap.add_argument("--dot", action="store_true", help="also time the fused SpMV + dot kernel (sbSpmvDot)")
     ap.add_argument("--cg", type=int, default=0, help="also run this many fused CG iterations")
     a = ap.parse_args()
     L = api.lib()
@@ -51,6 +52,28 @@ def main():
     ms, med = min(times), sorted(times)[len(times) // 2]
     print("spmv %s %d^2x%d: min %.4f ms (%.1f GB/s, %.1f GFLOP/s)  median %.4f  back-to-back %.4f ms (%.1f GB/s)  first %.4f"
           % (a.fmt, n, nz, ms, B / ms / 1e6, 2 * nnz / ms / 1e6, med, blk, B / blk / 1e6, times[0]))
+    if a.dot:
+        # the fused kernel of the CG loop: y = A x with x . y in the epilogue
+        d = api.DeviceBuffer(64)
+        times = []
+        for i in range(a.reps):
+            t.start()
+            L.sbSpmvDot(C.byref(A), fmt, x.ptr, y.ptr, d.ptr)
+            times.append(t.stop_ms())
+        # interleaved blocks (plain, fused, plain, fused, ...) so that clock / temperature drift hits both alike
+        plain_b, fused_b = [], []
+        for rnd in range(6):
+            t.start()
+            for i in range(a.reps):
+                api.spMVM(A, x, y)
+            plain_b.append(t.stop_ms() / a.reps)
+            t.start()
+            for i in range(a.reps):
+                L.sbSpmvDot(C.byref(A), fmt, x.ptr, y.ptr, d.ptr)
+            fused_b.append(t.stop_ms() / a.reps)
+        pb, fb = sorted(plain_b)[len(plain_b) // 2], sorted(fused_b)[len(fused_b) // 2]
+        print("spmv+dot %s: isolated min %.4f median %.4f | interleaved back-to-back blocks: plain %.4f ms, fused %.4f ms (%.1f GB/s)"
+              "  -> fused-dot cost %+.2f %%" % (a.fmt, min(times), sorted(times)[len(times) // 2], pb, fb, B / fb / 1e6, 100.0 * (fb / pb - 1.0)))
     if a.ordered:
         units = A.nChunks if a.fmt == "SCS" else A.nr
         plane = (n * n) // (32 if a.fmt == "SCS" else 1)
