@@ -143,8 +143,15 @@ typedef struct {                /* comm.h:27-46, the _MPI member set is always p
 } Comm;
 
 /* ---------------------------------------------------------------- runtime (allocate.c, timing.c) */
-/* allocate.h:9 -- device allocation (alignment honoured up to 512 B); exits on failure */
+/* allocate.h:9 -- what a reference caller gets for its vectors: UNIFIED memory, so host code that fills the array with
+ * plain stores (main.c:208-211, `-t spmv`) keeps working; spMVM / waxpby / ddot / commExchange move such a block to the
+ * GPU once, before the first kernel that touches it, after which it is device-resident. Alignment honoured up to 256 B;
+ * exits on failure (allocate.c:19-33). */
 void* allocate(size_t alignment, size_t bytesize);
+/* plain device memory (cudaMalloc, parked-block cache): what the library uses for itself and what a caller that never
+ * dereferences the pointer on the host should use */
+void* sbAllocateDevice(size_t alignment, size_t bytesize);
+int sbPrefetchManaged(const void* p);                /* allocate()d block containing p -> GPU now; returns 1 if p is in one */
 void sbFree(void* devPtr);                           /* released blocks are parked for reuse (SB_POOL_MB caps the cache, default 8192) */
 void sbTrimPool(void);                               /* returns every parked block to the driver (before handing the GPU to another allocator) */
 void* sbAllocateHost(size_t bytesize);               /* pinned host memory for staging */

@@ -85,6 +85,10 @@ def lib():
     if not _configured:
         L.allocate.restype = C.c_void_p
         L.allocate.argtypes = [C.c_size_t, C.c_size_t]
+        L.sbAllocateDevice.restype = C.c_void_p
+        L.sbAllocateDevice.argtypes = [C.c_size_t, C.c_size_t]
+        L.sbPrefetchManaged.argtypes = [C.c_void_p]
+        L.sbPrefetchManaged.restype = C.c_int
         L.sbFree.argtypes = [C.c_void_p]
         L.sbAllocateHost.restype = C.c_void_p
         L.sbAllocateHost.argtypes = [C.c_size_t]
@@ -146,11 +150,11 @@ def lib():
 
 # ------------------------------------------------------------------ device memory (allocate.c)
 class DeviceBuffer:
-    """What allocate() returns: a device pointer plus its size."""
+    """Plain device memory (sbAllocateDevice): a device pointer plus its size."""
 
     def __init__(self, nbytes):
         self.nbytes = int(nbytes)
-        self.ptr = lib().allocate(64, self.nbytes)
+        self.ptr = lib().sbAllocateDevice(64, self.nbytes)
 
     def free(self):
         if self.ptr:
@@ -164,9 +168,22 @@ class DeviceBuffer:
             pass
 
 
+class UnifiedBuffer(DeviceBuffer):
+    """What the reference-ABI allocate() returns (allocate.h:9): unified memory the host may write with plain stores;
+    `host(dtype)` is a numpy view of it. The entry points move it to the GPU before their first kernel."""
+
+    def __init__(self, nbytes):
+        self.nbytes = int(nbytes)
+        self.ptr = lib().allocate(64, self.nbytes)
+
+    def host(self, dtype=np.float64):
+        n = self.nbytes // np.dtype(dtype).itemsize
+        return np.ctypeslib.as_array(C.cast(self.ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dtype))), (n,))
+
+
 def allocate(alignment, bytesize):
     assert alignment <= 256
-    return DeviceBuffer(bytesize)
+    return UnifiedBuffer(bytesize)
 
 
 def to_device(a, slots=None):

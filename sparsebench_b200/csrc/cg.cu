@@ -138,6 +138,7 @@ struct CgSolver {
   {
     const size_t bytes = sizeof(double) * n;
     const bool dev = isDevicePointer(src);
+    if (dev) ensureOnDevice(src);
     if (!A.oldToNew) {
       SB_CUDA(cudaMemcpyAsync(dst, src, bytes, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
     } else {
@@ -202,17 +203,17 @@ struct CgSolver {
         fusedPut = fusedReduce && getenv("SB_NO_FUSED_PUT") == nullptr && commPrepareFusedPut(comm, A.permKey, elems);
       }
     }
-    r = (double*)allocate(64, sizeof(double) * rowSlots);
+    r = (double*)sbAllocateDevice(64, sizeof(double) * rowSlots);
     if (!p) {
-      p = (double*)allocate(64, sizeof(double) * colSlots);
+      p = (double*)sbAllocateDevice(64, sizeof(double) * colSlots);
       SB_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * colSlots, s));
     }
-    Ap = (double*)allocate(64, sizeof(double) * rowSlots);
-    x = (double*)allocate(64, sizeof(double) * rowSlots);
-    b = (double*)allocate(64, sizeof(double) * rowSlots);
-    tmp = (double*)allocate(64, sizeof(double) * rowSlots);
-    rho = (double*)allocate(64, sizeof(double) * nScal);
-    pAp = (double*)allocate(64, sizeof(double) * nScal);
+    Ap = (double*)sbAllocateDevice(64, sizeof(double) * rowSlots);
+    x = (double*)sbAllocateDevice(64, sizeof(double) * rowSlots);
+    b = (double*)sbAllocateDevice(64, sizeof(double) * rowSlots);
+    tmp = (double*)sbAllocateDevice(64, sizeof(double) * rowSlots);
+    rho = (double*)sbAllocateDevice(64, sizeof(double) * nScal);
+    pAp = (double*)sbAllocateDevice(64, sizeof(double) * nScal);
     hRho = (double*)sbAllocateHost(sizeof(double) * nScal);
     SB_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * rowSlots, s));
     SB_CUDA(cudaMemsetAsync(rho, 0, sizeof(double) * nScal, s));

@@ -128,7 +128,7 @@ static void resetLists(Comm* c)
 static void allGatherBytes(CommExt* e, const void* mine, size_t bytes, void* all)
 {
   Context& c = ctx();
-  char* d = (char*)allocate(64, bytes * (size_t)(e->size + 1));
+  char* d = (char*)sbAllocateDevice(64, bytes * (size_t)(e->size + 1));
   SB_CUDA(cudaMemcpyAsync(d, mine, bytes, cudaMemcpyHostToDevice, c.stream));
   SB_NCCL(ncclAllGather(d, d + bytes, bytes, ncclChar, e->nccl, c.stream));
   SB_CUDA(cudaMemcpyAsync(all, d + bytes, bytes * (size_t)e->size, cudaMemcpyDeviceToHost, c.stream));
@@ -206,7 +206,7 @@ static void attach(Comm* c, int rank, int size, int device, const ncclUniqueId* 
   e->rank = rank;
   e->size = size;
   SB_NCCL(ncclCommInitRank(&e->nccl, size, *id, rank));
-  e->dScalar = (double*)allocate(64, sizeof(double) * 8);
+  e->dScalar = (double*)sbAllocateDevice(64, sizeof(double) * 8);
   e->hScalar = (double*)sbAllocateHost(sizeof(double) * 8);
   c->communicator = e;
   g_world = e;
@@ -214,14 +214,14 @@ static void attach(Comm* c, int rank, int size, int device, const ncclUniqueId* 
   const char* modeEnv = getenv("SB_COMM");
   const bool wantPeer = !(modeEnv && strcmp(modeEnv, "nccl") == 0);
   if (wantPeer) {
-    e->ctrl = (CtrlWindow*)allocate(256, sizeof(CtrlWindow));
+    e->ctrl = (CtrlWindow*)sbAllocateDevice(256, sizeof(CtrlWindow));
     SB_CUDA(cudaMemset(e->ctrl, 0, sizeof(CtrlWindow)));
     SB_CUDA(cudaDeviceSynchronize());
     std::vector<void*> peers;
     if (mapPeers(e, e->ctrl, peers)) {
       e->peerCtrl.resize((size_t)size);
       for (int r = 0; r < size; r++) e->peerCtrl[(size_t)r] = (CtrlWindow*)peers[(size_t)r];
-      e->dPeerCtrl = (CtrlWindow**)allocate(64, sizeof(CtrlWindow*) * (size_t)size);
+      e->dPeerCtrl = (CtrlWindow**)sbAllocateDevice(64, sizeof(CtrlWindow*) * (size_t)size);
       sbCopyToDevice(e->dPeerCtrl, e->peerCtrl.data(), sizeof(CtrlWindow*) * (size_t)size);
       e->mode = COMM_PEER;
     } else {
@@ -471,15 +471,15 @@ static void installPartition(Comm* c)
   if (!e || e->installed) return;
   const int size = e->size, rank = e->rank;
   if (c->totalSendCount > 0) {
-    e->dElementsToSend = (int*)allocate(64, sizeof(int) * (size_t)c->totalSendCount);
+    e->dElementsToSend = (int*)sbAllocateDevice(64, sizeof(int) * (size_t)c->totalSendCount);
     sbCopyToDevice(e->dElementsToSend, c->elementsToSend, sizeof(int) * (size_t)c->totalSendCount);
-    c->sendBuffer = (CG_FLOAT*)allocate(64, sizeof(CG_FLOAT) * (size_t)c->totalSendCount);   // comm.c:124-125
+    c->sendBuffer = (CG_FLOAT*)sbAllocateDevice(64, sizeof(CG_FLOAT) * (size_t)c->totalSendCount);   // comm.c:124-125
   }
   if (e->mode == COMM_PEER) {
     if ((int)e->wantMatrix.size() != size * size) SB_FATAL("commPartition: missing halo count matrix");
     const int* W = e->wantMatrix.data();
     const size_t ext0 = (size_t)c->externalCount;
-    e->halo = (double*)allocate(256, sizeof(double) * (2 * ext0 + 2));
+    e->halo = (double*)sbAllocateDevice(256, sizeof(double) * (2 * ext0 + 2));
     SB_CUDA(cudaMemset(e->halo, 0, sizeof(double) * (2 * ext0 + 2)));
     SB_CUDA(cudaDeviceSynchronize());
     std::vector<void*> peers;
@@ -521,8 +521,8 @@ static void installPartition(Comm* c)
     SB_CUDA(cudaMemset(e->ctrl->haloFlag, 0, sizeof(e->ctrl->haloFlag)));
     SB_CUDA(cudaMemset(e->ctrl->haloAck, 0, sizeof(e->ctrl->haloAck)));
     SB_CUDA(cudaDeviceSynchronize());
-    e->dPut = (PutPlan*)allocate(64, sizeof(PutPlan));
-    e->dWait = (WaitPlan*)allocate(64, sizeof(WaitPlan));
+    e->dPut = (PutPlan*)sbAllocateDevice(64, sizeof(PutPlan));
+    e->dWait = (WaitPlan*)sbAllocateDevice(64, sizeof(WaitPlan));
     sbCopyToDevice(e->dPut, &put, sizeof(put));
     sbCopyToDevice(e->dWait, &wait, sizeof(wait));
     ncclBarrier(e);
@@ -614,7 +614,7 @@ static bool registerArena(Comm* c, size_t slots, uint32_t numRows)
   CommExt* e = ext(c);
   releaseArena(c);
   const int size = e->size, rank = e->rank;
-  e->arena = (double*)allocate(256, sizeof(double) * slots);
+  e->arena = (double*)sbAllocateDevice(256, sizeof(double) * slots);
   SB_CUDA(cudaMemset(e->arena, 0, sizeof(double) * slots));
   SB_CUDA(cudaDeviceSynchronize());
   std::vector<void*> peers;
@@ -644,7 +644,7 @@ static bool registerArena(Comm* c, size_t slots, uint32_t numRows)
     put.ack[i] = nullptr;
   }
   put.sdispl[c->outdegree] = c->totalSendCount;
-  e->dPutDirect = (PutPlan*)allocate(64, sizeof(PutPlan));
+  e->dPutDirect = (PutPlan*)sbAllocateDevice(64, sizeof(PutPlan));
   sbCopyToDevice(e->dPutDirect, &put, sizeof(put));
   // the arrival counters count elements since registration and keep running from solve to solve
   e->directSeq = 0;
@@ -692,7 +692,7 @@ const int* commSolverElements(Comm* c, uint64_t key, const uint32_t* oldToNew, c
   installPartition(c);
   if (key == 0 || !oldToNew || c->totalSendCount == 0) return e->dElementsToSend;
   if (e->dElemsSolver && e->elemsKey == key) return e->dElemsSolver;
-  if (!e->dElemsSolver) e->dElemsSolver = (int*)allocate(64, sizeof(int) * (size_t)c->totalSendCount);
+  if (!e->dElemsSolver) e->dElemsSolver = (int*)sbAllocateDevice(64, sizeof(int) * (size_t)c->totalSendCount);
   launchPermuteIndices((uint32_t)c->totalSendCount, oldToNew, e->dElementsToSend, e->dElemsSolver, s);
   e->elemsKey = key;
   return e->dElemsSolver;
@@ -721,7 +721,7 @@ bool commPrepareFusedPut(Comm* c, uint64_t key, const int* elements)
       }
       std::vector<int> inv((size_t)(hi - lo + 1), -1);
       for (int j = 0; j < cnt; j++) inv[(size_t)(elems[(size_t)(b + j)] - lo)] = j;
-      int* dInv = (int*)allocate(64, sizeof(int) * inv.size());
+      int* dInv = (int*)sbAllocateDevice(64, sizeof(int) * inv.size());
       sbCopyToDevice(dInv, inv.data(), sizeof(int) * inv.size());
       e->fusedInv.push_back(dInv);
       e->fused.lo[i] = (uint32_t)lo;
@@ -936,7 +936,11 @@ void commReduction(CG_FLOAT* v, int op)
 
 void sbCommAllreduceDevice(Comm* c, CG_FLOAT* dev, int count, int op) { commAllreduceDevice(c, dev, count, op, ctx().stream); }
 
-void commExchange(Comm* c, CG_UINT numRows, CG_FLOAT* x) { commExchangeOnStream(c, numRows, x, nullptr, ctx().stream); }
+void commExchange(Comm* c, CG_UINT numRows, CG_FLOAT* x)
+{
+  ensureOnDevice(x);
+  commExchangeOnStream(c, numRows, x, nullptr, ctx().stream);
+}
 
 void commDistributeMatrix(Comm* c, MMMatrix* m, MMMatrix* mLocal)
 {
@@ -973,7 +977,7 @@ void commDistributeMatrix(Comm* c, MMMatrix* m, MMMatrix* mLocal)
       printf("Rank %d count %d displ %d start %d stop %d\n", i, (int)(at - begin), (int)begin, stopRow - numRows + 1, stopRow);
     }
   }
-  int* dTable = (int*)allocate(64, sizeof(int) * table.size());
+  int* dTable = (int*)sbAllocateDevice(64, sizeof(int) * table.size());
   if (rank == 0) SB_CUDA(cudaMemcpyAsync(dTable, table.data(), sizeof(int) * table.size(), cudaMemcpyHostToDevice, cx.stream));
   SB_NCCL(ncclBroadcast(dTable, dTable, table.size(), ncclInt32, 0, e->nccl, cx.stream));
   SB_CUDA(cudaMemcpyAsync(table.data(), dTable, sizeof(int) * table.size(), cudaMemcpyDeviceToHost, cx.stream));
@@ -988,8 +992,8 @@ void commDistributeMatrix(Comm* c, MMMatrix* m, MMMatrix* mLocal)
   mLocal->entries = (MMEntry*)host;
   // MPI_Scatterv (comm.c:373-381)
   const size_t allBytes = rank == 0 ? sizeof(MMEntry) * m->count : 0;
-  char* dAll = rank == 0 ? (char*)allocate(64, allBytes) : nullptr;
-  char* dMine = (char*)allocate(64, sizeof(MMEntry) * (size_t)(count ? count : 1));
+  char* dAll = rank == 0 ? (char*)sbAllocateDevice(64, allBytes) : nullptr;
+  char* dMine = (char*)sbAllocateDevice(64, sizeof(MMEntry) * (size_t)(count ? count : 1));
   if (rank == 0) SB_CUDA(cudaMemcpyAsync(dAll, m->entries, allBytes, cudaMemcpyHostToDevice, cx.stream));
   SB_NCCL(ncclGroupStart());
   if (rank == 0)
@@ -1029,17 +1033,17 @@ SbPartitionPlan* sbPartitionLocal(GMatrix* m, int rank, int size, const CG_UINT*
     SB_CUDA(cudaMemcpyAsync(&stored, m->rowPtr + nr, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     SB_CUDA(cudaStreamSynchronize(s));
     const uint64_t n = stored;
-    unsigned char* flag = (unsigned char*)allocate(64, n ? n : 1);
-    uint32_t* col = (uint32_t*)allocate(64, sizeof(uint32_t) * (n ? n : 1));
-    uint32_t* sel = (uint32_t*)allocate(64, sizeof(uint32_t) * (n ? n : 1));
-    int* dCount = (int*)allocate(64, sizeof(int));
+    unsigned char* flag = (unsigned char*)sbAllocateDevice(64, n ? n : 1);
+    uint32_t* col = (uint32_t*)sbAllocateDevice(64, sizeof(uint32_t) * (n ? n : 1));
+    uint32_t* sel = (uint32_t*)sbAllocateDevice(64, sizeof(uint32_t) * (n ? n : 1));
+    int* dCount = (int*)sbAllocateDevice(64, sizeof(int));
     const int threads = 256;
     const int blocks = (int)std::min<uint64_t>((n + threads - 1) / threads + 1, (uint64_t)c.numSMs * 16);
     flagExternalKernel<<<blocks, threads, 0, s>>>(n, m->entries, startRow, stopRow, flag, col);
     SB_CUDA(cudaGetLastError());
     size_t tmpBytes = 0;
     SB_CUDA(cub::DeviceSelect::Flagged(nullptr, tmpBytes, col, flag, sel, dCount, (long long)n, s));
-    void* tmp = allocate(64, tmpBytes);
+    void* tmp = sbAllocateDevice(64, tmpBytes);
     SB_CUDA(cub::DeviceSelect::Flagged(tmp, tmpBytes, col, flag, sel, dCount, (long long)n, s));   // stable: entry order kept
     int nRefs = 0;
     SB_CUDA(cudaMemcpyAsync(&nRefs, dCount, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -1053,8 +1057,8 @@ SbPartitionPlan* sbPartitionLocal(GMatrix* m, int rank, int size, const CG_UINT*
     std::sort(table.begin(), table.end());
     std::vector<uint32_t> g((size_t)nExt), l((size_t)nExt);
     for (int i = 0; i < nExt; i++) { g[(size_t)i] = table[(size_t)i].first; l[(size_t)i] = table[(size_t)i].second; }
-    uint32_t* dg = (uint32_t*)allocate(64, sizeof(uint32_t) * (size_t)(nExt ? nExt : 1));
-    uint32_t* dl = (uint32_t*)allocate(64, sizeof(uint32_t) * (size_t)(nExt ? nExt : 1));
+    uint32_t* dg = (uint32_t*)sbAllocateDevice(64, sizeof(uint32_t) * (size_t)(nExt ? nExt : 1));
+    uint32_t* dl = (uint32_t*)sbAllocateDevice(64, sizeof(uint32_t) * (size_t)(nExt ? nExt : 1));
     if (nExt) {
       sbCopyToDevice(dg, g.data(), sizeof(uint32_t) * (size_t)nExt);
       sbCopyToDevice(dl, l.data(), sizeof(uint32_t) * (size_t)nExt);
@@ -1150,8 +1154,8 @@ void commPartition(Comm* c, GMatrix* m)
     Context& cx = ctx();
     int nReq = 0;
     for (int s = 0; s < size; s++) nReq += wantMatrix[(size_t)rank * size + s];
-    int* dSend = (int*)allocate(64, sizeof(int) * (size_t)(nReq ? nReq : 1));
-    int* dRecv = (int*)allocate(64, sizeof(int) * (size_t)(total ? total : 1));
+    int* dSend = (int*)sbAllocateDevice(64, sizeof(int) * (size_t)(nReq ? nReq : 1));
+    int* dRecv = (int*)sbAllocateDevice(64, sizeof(int) * (size_t)(total ? total : 1));
     if (nReq) sbCopyToDevice(dSend, P->plan.requests.data(), sizeof(int) * (size_t)nReq);
     SB_NCCL(ncclGroupStart());
     for (int s = 0; s < size; s++) {

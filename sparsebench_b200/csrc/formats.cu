@@ -75,8 +75,8 @@ static DeviceInput stageInput(const GMatrix* im)
     in.stored = last;
   } else {
     in.stored = im->rowPtr[nr];
-    uint32_t* rp = (uint32_t*)allocate(64, sizeof(uint32_t) * (nr + 1 + 8));   // +8: bulk-copy granularity (CCRS shares it)
-    Entry* en = (Entry*)allocate(64, sizeof(Entry) * (in.stored ? in.stored : 1));
+    uint32_t* rp = (uint32_t*)sbAllocateDevice(64, sizeof(uint32_t) * (nr + 1 + 8));   // +8: bulk-copy granularity (CCRS shares it)
+    Entry* en = (Entry*)sbAllocateDevice(64, sizeof(Entry) * (in.stored ? in.stored : 1));
     SB_CUDA(cudaMemcpyAsync(rp, im->rowPtr, sizeof(uint32_t) * (nr + 1), cudaMemcpyHostToDevice, c.stream));
     SB_CUDA(cudaMemcpyAsync(en, im->entries, sizeof(Entry) * in.stored, cudaMemcpyHostToDevice, c.stream));
     SB_CUDA(cudaStreamSynchronize(c.stream));
@@ -241,10 +241,10 @@ void sbCRS_convertMatrix(SbCRSMatrix* m, GMatrix* im)
   copyHeader(&m->nr, im);
   DeviceInput in = stageInput(im);
   const size_t nr = im->nr;
-  m->rowPtr = (CG_UINT*)allocate(64, sizeof(CG_UINT) * (nr + 1 + 8));   // +8: 16-byte granularity of the bulk copies
+  m->rowPtr = (CG_UINT*)sbAllocateDevice(64, sizeof(CG_UINT) * (nr + 1 + 8));   // +8: 16-byte granularity of the bulk copies
   // +8: the staged SpMV kernel widens its bulk copies to 16-byte granularity (up to 3 elements past the end)
-  m->colInd = (CG_UINT*)allocate(64, sizeof(CG_UINT) * (in.stored + 8));
-  m->val = (CG_FLOAT*)allocate(64, sizeof(CG_FLOAT) * (in.stored + 8));
+  m->colInd = (CG_UINT*)sbAllocateDevice(64, sizeof(CG_UINT) * (in.stored + 8));
+  m->val = (CG_FLOAT*)sbAllocateDevice(64, sizeof(CG_FLOAT) * (in.stored + 8));
   SB_CUDA(cudaMemsetAsync(m->colInd + in.stored, 0, sizeof(CG_UINT) * 8, c.stream));
   SB_CUDA(cudaMemsetAsync(m->val + in.stored, 0, sizeof(CG_FLOAT) * 8, c.stream));
   SB_CUDA(cudaMemcpyAsync(m->rowPtr, in.rowPtr, sizeof(CG_UINT) * (nr + 1), cudaMemcpyDeviceToDevice, c.stream));
@@ -304,13 +304,13 @@ void sbSCS_convertMatrix(SbSCSMatrix* m, GMatrix* im)
   DeviceInput in = stageInput(im);
 
   const size_t np = nrPadded ? nrPadded : 1;
-  uint64_t* keys = (uint64_t*)allocate(64, sizeof(uint64_t) * np);
-  uint64_t* keysSorted = (uint64_t*)allocate(64, sizeof(uint64_t) * np);
-  uint32_t* idx = (uint32_t*)allocate(64, sizeof(uint32_t) * np);
-  uint32_t* idxSorted = (uint32_t*)allocate(64, sizeof(uint32_t) * np);
+  uint64_t* keys = (uint64_t*)sbAllocateDevice(64, sizeof(uint64_t) * np);
+  uint64_t* keysSorted = (uint64_t*)sbAllocateDevice(64, sizeof(uint64_t) * np);
+  uint32_t* idx = (uint32_t*)sbAllocateDevice(64, sizeof(uint32_t) * np);
+  uint32_t* idxSorted = (uint32_t*)sbAllocateDevice(64, sizeof(uint32_t) * np);
   ScsExt* ext = new ScsExt();
-  ext->rowLenOrig = (uint32_t*)allocate(64, sizeof(uint32_t) * np);
-  ext->rowLenPerm = (uint32_t*)allocate(64, sizeof(uint32_t) * np);
+  ext->rowLenOrig = (uint32_t*)sbAllocateDevice(64, sizeof(uint32_t) * np);
+  ext->rowLenPerm = (uint32_t*)sbAllocateDevice(64, sizeof(uint32_t) * np);
   ext->nnzTrue = in.stored;
   ext->nc = im->nc;
   static std::atomic<uint64_t> nextId { 1 };
@@ -321,7 +321,7 @@ void sbSCS_convertMatrix(SbSCSMatrix* m, GMatrix* im)
   if (sigma > 1 && nrPadded > 1) {
     size_t tmpBytes = 0;
     SB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keys, keysSorted, idx, idxSorted, (long long)nrPadded, 0, 64, s));
-    void* tmp = allocate(64, tmpBytes);
+    void* tmp = sbAllocateDevice(64, tmpBytes);
     SB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, keys, keysSorted, idx, idxSorted, (long long)nrPadded, 0, 64, s));
     SB_CUDA(cudaStreamSynchronize(s));
     sbFree(tmp);
@@ -330,10 +330,10 @@ void sbSCS_convertMatrix(SbSCSMatrix* m, GMatrix* im)
     SB_CUDA(cudaMemcpyAsync(idxSorted, idx, sizeof(uint32_t) * np, cudaMemcpyDeviceToDevice, s));
   }
 
-  m->chunkLens = (CG_UINT*)allocate(64, sizeof(CG_UINT) * (nChunks ? nChunks : 1));
-  m->chunkPtr = (CG_UINT*)allocate(64, sizeof(CG_UINT) * ((size_t)nChunks + 1));
-  uint64_t* chunkElems = (uint64_t*)allocate(64, sizeof(uint64_t) * ((size_t)nChunks + 1));
-  uint64_t* chunkPtr64 = (uint64_t*)allocate(64, sizeof(uint64_t) * ((size_t)nChunks + 1));
+  m->chunkLens = (CG_UINT*)sbAllocateDevice(64, sizeof(CG_UINT) * (nChunks ? nChunks : 1));
+  m->chunkPtr = (CG_UINT*)sbAllocateDevice(64, sizeof(CG_UINT) * ((size_t)nChunks + 1));
+  uint64_t* chunkElems = (uint64_t*)sbAllocateDevice(64, sizeof(uint64_t) * ((size_t)nChunks + 1));
+  uint64_t* chunkPtr64 = (uint64_t*)sbAllocateDevice(64, sizeof(uint64_t) * ((size_t)nChunks + 1));
   SB_CUDA(cudaMemsetAsync(chunkElems, 0, sizeof(uint64_t) * ((size_t)nChunks + 1), s));
   if (nChunks) {
     scsChunkLenKernel<<<gridFor(nChunks, 128), 128, 0, s>>>(nChunks, C, keysSorted, m->chunkLens, chunkElems);
@@ -342,7 +342,7 @@ void sbSCS_convertMatrix(SbSCSMatrix* m, GMatrix* im)
   {
     size_t tmpBytes = 0;
     SB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, chunkElems, chunkPtr64, (long long)nChunks + 1, s));
-    void* tmp = allocate(64, tmpBytes);
+    void* tmp = sbAllocateDevice(64, tmpBytes);
     SB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmpBytes, chunkElems, chunkPtr64, (long long)nChunks + 1, s));
     SB_CUDA(cudaStreamSynchronize(s));
     sbFree(tmp);
@@ -355,9 +355,9 @@ void sbSCS_convertMatrix(SbSCSMatrix* m, GMatrix* im)
   scsNarrowKernel<<<gridFor((uint64_t)nChunks + 1, 256), 256, 0, s>>>(nChunks + 1, chunkPtr64, m->chunkPtr);
   SB_CUDA(cudaGetLastError());
 
-  m->oldToNewPerm = (CG_UINT*)allocate(64, sizeof(CG_UINT) * (nr ? nr : 1));
-  m->newToOldPerm = (CG_UINT*)allocate(64, sizeof(CG_UINT) * (nr ? nr : 1));
-  unsigned int* notIdentity = (unsigned int*)allocate(64, sizeof(unsigned int));
+  m->oldToNewPerm = (CG_UINT*)sbAllocateDevice(64, sizeof(CG_UINT) * (nr ? nr : 1));
+  m->newToOldPerm = (CG_UINT*)sbAllocateDevice(64, sizeof(CG_UINT) * (nr ? nr : 1));
+  unsigned int* notIdentity = (unsigned int*)sbAllocateDevice(64, sizeof(unsigned int));
   SB_CUDA(cudaMemsetAsync(notIdentity, 0, sizeof(unsigned int), s));
   if (nrPadded) {
     scsPermKernel<<<gridFor(nrPadded, 256), 256, 0, s>>>(nr, nrPadded, idxSorted, m->oldToNewPerm, m->newToOldPerm, notIdentity);
@@ -365,9 +365,9 @@ void sbSCS_convertMatrix(SbSCSMatrix* m, GMatrix* im)
   }
 
   const size_t ne = nElems ? nElems : 1;
-  m->colInd = (CG_UINT*)allocate(64, sizeof(CG_UINT) * ne);
-  m->val = (CG_FLOAT*)allocate(64, sizeof(CG_FLOAT) * ne);
-  ext->colPerm = (uint32_t*)allocate(64, sizeof(uint32_t) * ne);
+  m->colInd = (CG_UINT*)sbAllocateDevice(64, sizeof(CG_UINT) * ne);
+  m->val = (CG_FLOAT*)sbAllocateDevice(64, sizeof(CG_FLOAT) * ne);
+  ext->colPerm = (uint32_t*)sbAllocateDevice(64, sizeof(uint32_t) * ne);
   SB_CUDA(cudaMemsetAsync(m->colInd, 0, sizeof(CG_UINT) * ne, s));      // :150-155
   SB_CUDA(cudaMemsetAsync(m->val, 0, sizeof(CG_FLOAT) * ne, s));
   SB_CUDA(cudaMemsetAsync(ext->colPerm, 0xff, sizeof(uint32_t) * ne, s));

@@ -132,8 +132,8 @@ void sbGenerateDevice(GMatrix* m, Parameter* p, int rank, int size, bool use_7pt
   checkSizes(g);
   sb::Context& c = sb::ctx();
   const size_t n = (size_t)g.localRows;
-  uint32_t* len = (uint32_t*)allocate(64, sizeof(uint32_t) * n);
-  m->rowPtr = (CG_UINT*)allocate(64, sizeof(CG_UINT) * (n + 1 + 8));   // +8: bulk-copy granularity of the SpMV kernels (CCRS shares this array)
+  uint32_t* len = (uint32_t*)sbAllocateDevice(64, sizeof(uint32_t) * n);
+  m->rowPtr = (CG_UINT*)sbAllocateDevice(64, sizeof(CG_UINT) * (n + 1 + 8));   // +8: bulk-copy granularity of the SpMV kernels (CCRS shares this array)
   const int threads = 256;
   const int blocks = (int)((n + threads - 1) / threads < (size_t)c.numSMs * 16 ? (n + threads - 1) / threads : (size_t)c.numSMs * 16);
   rowLengthKernel<<<blocks, threads, 0, c.stream>>>(g, len);
@@ -141,14 +141,14 @@ void sbGenerateDevice(GMatrix* m, Parameter* p, int rank, int size, bool use_7pt
   SB_CUDA(cudaMemsetAsync(m->rowPtr, 0, sizeof(CG_UINT), c.stream));
   size_t tmpBytes = 0;
   SB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmpBytes, len, m->rowPtr + 1, (long long)n, c.stream));
-  void* tmp = allocate(64, tmpBytes);
+  void* tmp = sbAllocateDevice(64, tmpBytes);
   SB_CUDA(cub::DeviceScan::InclusiveSum(tmp, tmpBytes, len, m->rowPtr + 1, (long long)n, c.stream));
   CG_UINT stored = 0;
   SB_CUDA(cudaMemcpyAsync(&stored, m->rowPtr + n, sizeof(CG_UINT), cudaMemcpyDeviceToHost, c.stream));
   SB_CUDA(cudaStreamSynchronize(c.stream));
   // the reference allocates 27 entries per row (matrix.c:35,54); only rowPtr[nr] are ever valid, so the
   // device copy keeps just those
-  m->entries = (Entry*)allocate(64, sizeof(Entry) * (size_t)(stored ? stored : 1));
+  m->entries = (Entry*)sbAllocateDevice(64, sizeof(Entry) * (size_t)(stored ? stored : 1));
   SB_CUDA(cudaMemsetAsync(m->entries, 0, sizeof(Entry) * (size_t)stored, c.stream));   // defined padding bytes
   fillKernel<<<blocks, threads, 0, c.stream>>>(g, m->rowPtr, m->entries);
   SB_CUDA(cudaGetLastError());

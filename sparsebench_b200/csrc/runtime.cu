@@ -2,6 +2,7 @@
 // timing.c:8-20 / the PROFILE macro's time source, profiler.h:18-21) and the per-process device context.
 #include <time.h>
 
+#include <map>
 #include <mutex>
 #include <unordered_map>
 
@@ -10,6 +11,7 @@
 namespace sb {
 
 static Context g_ctx;
+static std::mutex g_poolMutex;
 static std::once_flag g_once;
 static int g_requestedDevice = -1;
 
@@ -43,6 +45,14 @@ Context& ctx()
   return g_ctx;
 }
 
+} // namespace sb
+extern "C" int sbPrefetchManaged(const void* p);
+namespace sb {
+void ensureOnDevice(const void* p)
+{
+  if (p) sbPrefetchManaged(p);
+}
+
 bool pdlEnabled()
 {
   static const bool on = getenv("SB_NO_PDL") == nullptr;
@@ -70,7 +80,6 @@ extern "C" {
 // cudaMalloc / cudaFree synchronise the device and cost up to milliseconds each; a solver allocates and releases
 // the same nine vectors per solve (CGSolver.c:69-79 never frees, a library must). Released blocks are therefore
 // parked in a small exact-size cache and handed out again (contents undefined, exactly like fresh cudaMalloc memory).
-static std::mutex g_poolMutex;
 struct Block {
   size_t bytes;
   bool parked;
@@ -100,14 +109,49 @@ static void releaseParked()
   g_parkedBytes = 0;
 }
 
-void* allocate(size_t alignment, size_t bytesize)
+static void checkAlignment(size_t alignment)
 {
-  // cudaMalloc returns >= 256-byte aligned blocks; the reference only ever asks for 64 (ARRAY_ALIGNMENT).
+  // cudaMalloc / cudaMallocManaged return >= 256-byte aligned blocks; the reference only ever asks for 64 (ARRAY_ALIGNMENT).
   if (alignment == 0 || (alignment & (alignment - 1)) != 0) {
-    fprintf(stderr, "Error: Alignment parameter is not a power of two\n");
+    fprintf(stderr, "Error: Alignment parameter is not a power of two\n");          // allocate.c:19-22
     exit(EXIT_FAILURE);
   }
   if (alignment > 256) SB_FATAL("allocate: alignment %zu > 256 not supported on the device", alignment);
+}
+
+// allocate() of the reference's ABI (allocate.h:9). Its callers are host programs that go on to WRITE the array with
+// plain stores (main.c:208-211 fills x and y of `-t spmv` that way) and then hand it to spMVM / waxpby / ddot: the
+// block is unified (managed) memory. The entry points that receive such a vector move it to the GPU once, before the
+// first kernel that uses it (sb::ensureOnDevice), after which it behaves like device memory. Everything the library
+// allocates for itself -- matrices, solver vectors, the peer-mapped windows, which CUDA IPC could not export from
+// managed memory -- comes from sbAllocateDevice (cudaMalloc).
+struct ManagedBlock {
+  size_t bytes;
+  bool onDevice;          // prefetched since it was allocated (a later host write migrates pages back: still correct)
+};
+static std::map<uintptr_t, ManagedBlock> g_managed;
+
+void* allocate(size_t alignment, size_t bytesize)
+{
+  checkAlignment(alignment);
+  ctx();
+  // + 256: matrix-SCS.c:224-226 stores nrPadded entries into a y the caller sized with nr (main.c:206)
+  const size_t bytes = (((bytesize ? bytesize : 1) + 255) & ~(size_t)255) + 256;
+  void* p = nullptr;
+  cudaError_t e = cudaMallocManaged(&p, bytes, cudaMemAttachGlobal);
+  if (e != cudaSuccess || p == nullptr) {
+    fprintf(stderr, "Error: Insufficient memory to fulfill the request (%zu bytes of unified memory: %s)\n", bytesize,
+        cudaGetErrorString(e));                                                        // allocate.c:24-33
+    exit(EXIT_FAILURE);
+  }
+  std::lock_guard<std::mutex> lock(g_poolMutex);
+  g_managed[(uintptr_t)p] = ManagedBlock { bytes, false };
+  return p;
+}
+
+void* sbAllocateDevice(size_t alignment, size_t bytesize)
+{
+  checkAlignment(alignment);
   ctx();
   const size_t bytes = ((bytesize ? bytesize : 1) + 255) & ~(size_t)255;
   std::lock_guard<std::mutex> lock(g_poolMutex);
@@ -135,6 +179,23 @@ void* allocate(size_t alignment, size_t bytesize)
   return p;
 }
 
+// A vector from allocate() (unified memory) that the host has filled: bring the whole block to the GPU before the first
+// kernel touches it instead of paying for page faults there. Returns 1 if `p` lies in such a block.
+int sbPrefetchManaged(const void* p)
+{
+  std::lock_guard<std::mutex> lock(g_poolMutex);
+  if (g_managed.empty()) return 0;
+  auto it = g_managed.upper_bound((uintptr_t)p);
+  if (it == g_managed.begin()) return 0;
+  --it;
+  if ((uintptr_t)p >= it->first + it->second.bytes) return 0;
+  if (!it->second.onDevice) {
+    SB_CUDA(cudaMemPrefetchAsync((const void*)it->first, it->second.bytes, g_ctx.device, g_ctx.stream));
+    it->second.onDevice = true;
+  }
+  return 1;
+}
+
 void sbTrimPool(void)
 {
   std::lock_guard<std::mutex> lock(g_poolMutex);
@@ -146,6 +207,13 @@ void sbFree(void* p)
 {
   if (!p) return;
   std::lock_guard<std::mutex> lock(g_poolMutex);
+  auto mit = g_managed.find((uintptr_t)p);
+  if (mit != g_managed.end()) {
+    g_managed.erase(mit);
+    SB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    SB_CUDA(cudaFree(p));
+    return;
+  }
   auto it = g_blockSize.find(p);
   if (it == g_blockSize.end()) {           // not ours (or already released): plain free
     SB_CUDA(cudaFree(p));

@@ -48,6 +48,8 @@ Context& ctx();                      // lazily initialised on first use; exits i
 inline void countLaunch(int n = 1) { ctx().launches += (size_t)n; }
 
 bool isDevicePointer(const void* p);
+// `p` may be unified memory from the ABI-level allocate() that the host has just filled: moved to the GPU once
+void ensureOnDevice(const void* p);
 
 // Kernel launch with the programmatic-dependent-launch attribute (device_utils.cuh: griddepWait). SB_NO_PDL=1 turns
 // the attribute off (plain stream order) for A/B measurements.

@@ -898,7 +898,7 @@ void spmvInteriorUnits(const Operator& A, uint32_t* lo, uint32_t* hi, cudaStream
   const uint32_t units = spmvUnits(A);
   uint32_t h[2] = { 0u, units };
   if (units > 0) {
-    uint32_t* d = (uint32_t*)allocate(64, 2 * sizeof(uint32_t));
+    uint32_t* d = (uint32_t*)sbAllocateDevice(64, 2 * sizeof(uint32_t));
     SB_CUDA(cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, s));
     haloTouchKernel<<<ctx().numSMs * 8, 256, 0, s>>>(A, units, d);
     SB_CUDA(cudaGetLastError());
@@ -996,12 +996,16 @@ extern "C" {
 void sbCRS_spMVM(SbCRSMatrix* m, const CG_FLOAT* x, CG_FLOAT* y)
 {
   Operator A = makeOperator(m, SB_FMT_CRS);
+  ensureOnDevice(x);
+  ensureOnDevice(y);
   launchSpmv(A, x, y, 0, A.nr, nullptr, ctx().stream);
 }
 
 void sbCCRS_spMVM(SbCCRSMatrix* m, const CG_FLOAT* x, CG_FLOAT* y)
 {
   Operator A = makeOperator(m, SB_FMT_CCRS);
+  ensureOnDevice(x);
+  ensureOnDevice(y);
   launchSpmv(A, x, y, 0, A.nr, nullptr, ctx().stream);
 }
 
@@ -1012,6 +1016,8 @@ int sbSpmvOrdered(void* matrix, int fmt, const CG_FLOAT* x, CG_FLOAT* y, CG_UINT
   Operator A = makeOperator(matrix, fmt);
   if (fmt == SB_FMT_SCS) A.sell.col = ((SbSCSMatrix*)matrix)->colInd;   // reference semantics, like sbSCS_spMVM
   if (!spmvGatedAvailable(A)) return 0;
+  ensureOnDevice(x);
+  ensureOnDevice(y);
   launchSpmvGated(A, x, y, intLo, intHi, HaloGate(), nullptr, ctx().stream);
   return 1;
 }
@@ -1022,6 +1028,9 @@ void sbSpmvDot(void* matrix, int fmt, const CG_FLOAT* x, CG_FLOAT* y, CG_FLOAT* 
   // loop runs. Vectors in solver order: for SCS with sigma > 1 that is the permuted row order for x AND y.
   Operator A = makeOperator(matrix, fmt);
   DotArgs d { dDot, false, 1 };
+  ensureOnDevice(x);
+  ensureOnDevice(y);
+  ensureOnDevice(dDot);
   launchSpmv(A, x, y, 0, spmvUnits(A), &d, ctx().stream);
 }
 
@@ -1031,6 +1040,8 @@ void sbSCS_spMVM(SbSCSMatrix* m, const CG_FLOAT* x, CG_FLOAT* y)
   // written in permuted row order and needs nrPadded slots.
   Operator A = makeOperator(m, SB_FMT_SCS);
   A.sell.col = m->colInd;
+  ensureOnDevice(x);
+  ensureOnDevice(y);
   launchSpmv(A, x, y, 0, A.sell.nChunks, nullptr, ctx().stream);
 }
 

@@ -437,12 +437,17 @@ extern "C" {
 void waxpby(const CG_UINT n, const CG_FLOAT alpha, const CG_FLOAT* x, const CG_FLOAT beta, const CG_FLOAT* y,
     CG_FLOAT* w)
 {
+  ensureOnDevice(x);
+  ensureOnDevice(y);
+  ensureOnDevice(w);
   launchWaxpby(n, alpha, x, beta, y, w, ctx().stream);
 }
 
 void ddot(const CG_UINT n, const CG_FLOAT* x, const CG_FLOAT* y, CG_FLOAT* result)
 {
   Context& c = ctx();
+  ensureOnDevice(x);
+  ensureOnDevice(y);
   launchDot(n, x, y, c.dScalar, 0, c.stream);
   SB_CUDA(cudaMemcpyAsync(c.hScalar, c.dScalar, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
   SB_CUDA(cudaStreamSynchronize(c.stream));

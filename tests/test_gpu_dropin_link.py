@@ -72,3 +72,66 @@ def test_reference_driver_bmx_round_trip(tmp_path):
     lines = [re.sub(r"and took .*", "and took", ln) for ln in r.stdout.splitlines() if KEEP.match(ln)]
     gold = GOLD["klein"]["lines"]
     assert len(lines) == len(gold) and all(close_lines(a, b) for a, b in zip(lines, gold)), (lines, gold)
+
+
+SPMV_LINE = re.compile(r"^spMVM:\s+([-+\d.eE]+|inf|nan)\s+([-+\d.eE]+|inf|nan)\s+([-+\d.eE]+)", re.M)
+
+
+def _run_spmv_mode(exe, n, iters):
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    r = subprocess.run([exe, "-t", "spmv", "-x", str(n), "-y", str(n), "-z", str(n), "-i", str(iters)], capture_output=True, text=True,
+                       timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "Test type: SPMVM" in r.stdout and "Function   Rate(MB/s)  Rate(MFlop/s)  Walltime(s)" in r.stdout
+    m = SPMV_LINE.search(r.stdout)
+    assert m, r.stdout[-1500:]
+    mflops, wall = float(m.group(2)), float(m.group(3))
+    # the reference's accounting (main.c:183-189, profiler.c:127-139): 2 flop per ALLOCATED non-zero (27 per row), k = itermax
+    assert abs(mflops - 1e-6 * 2 * 27 * n ** 3 * iters / wall) <= 1e-3 * mflops + 1.0
+    return wall
+
+
+@pytest.mark.parametrize("fmt,n", [("SCS", 256), ("CRS", 128), ("CCRS", 128)])
+def test_reference_driver_spmv_mode(fmt, n):
+    """`-t spmv` of the UNMODIFIED main.c (main.c:200-216): it allocate()s x and y, fills them with plain host stores
+    (:208-211) and calls spMVM itermax-1 times inside PROFILE(); the reference's profilerPrint reports the rate. Works
+    because the ABI-level allocate() hands out unified memory that spMVM moves to the GPU once (that one-time move is
+    inside the first PROFILE region; two runs with different iteration counts separate it from the steady state).
+    SELL at 256^3: the steady-state time per call the driver reports is within 3 % (+ 15 us: PROFILE's getTimeStamp
+    pair drains the device around every call) of the same kernel launched back to back through the API here."""
+    import ctypes as C
+
+    import numpy as np
+
+    from sparsebench_b200 import api
+    exe = os.path.join(ROOT, "integration", "_build", "sparseBench-%s-B200" % fmt)
+    if not os.path.exists(exe):
+        pytest.skip("integration/_build not built")
+    short, long_ = 31, 131
+    w1 = _run_spmv_mode(exe, n, short)
+    w2 = _run_spmv_mode(exe, n, long_)
+    per_call_ms = (w2 - w1) / (long_ - short) * 1e3
+    first_call_extra_ms = w1 * 1e3 - (short - 1) * per_call_ms
+    # the same kernel through the API, x = 1, back to back
+    g = api.matrixGenerate(n, n, n, device=True)
+    fmt_id = {"CRS": api.FMT_CRS, "SCS": api.FMT_SCS, "CCRS": api.FMT_CCRS}[fmt]
+    A = api.convertMatrix(fmt_id, g, 32, 256)
+    if fmt != "CCRS":
+        api.lib().sbFreeGMatrix(C.byref(g))
+    x, y = api.to_device(np.ones(n ** 3)), api.DeviceBuffer(8 * (n ** 3 + 64))
+    t = api.EventTimer()
+    for _ in range(3):
+        api.spMVM(A, x, y)
+    t.start()
+    for _ in range(100):
+        api.spMVM(A, x, y)
+    direct_ms = t.stop_ms() / 100
+    api.destroyMatrix(A)
+    if fmt == "CCRS":
+        api.lib().sbFreeGMatrix(C.byref(g))
+    print("%s %d^3 -t spmv: %.4f ms per call reported by the reference driver (steady state; one-time move of x, y to the GPU "
+          "%.2f ms), %.4f ms back to back through the API" % (fmt, n, per_call_ms, first_call_extra_ms, direct_ms))
+    assert per_call_ms <= 1.03 * direct_ms + 0.015, (per_call_ms, direct_ms)
+    assert per_call_ms >= 0.9 * direct_ms, (per_call_ms, direct_ms)          # and it really ran the kernel

@@ -344,6 +344,45 @@ def test_cg_itermax_edge_cases():
         assert np.allclose(hist, href, rtol=1e-12)
 
 
+# ------------------------------------------------------------------------------------------- allocate(): host-writable
+@pytest.mark.parametrize("fmt", [api.FMT_CRS, api.FMT_SCS, api.FMT_CCRS])
+def test_abi_allocate_is_host_writable_and_feeds_the_kernels(fmt):
+    """allocate.h:9 through the C ABI: the reference's callers fill what it returns with plain host stores
+    (main.c:208-211) and hand it to spMVM / waxpby / ddot. Unified memory: written on the host, multiplied on the GPU
+    (moved there once by the entry point), read back on the host."""
+    L = api.lib()
+    m = orc.generate(11, 9, 7)
+    g = api.matrixGenerate(11, 9, 7, device=True)
+    A = make_matrix(fmt, g, 4)
+    slots = A.nrPadded if fmt == api.FMT_SCS else m.nr
+    x, y, w = api.allocate(64, 8 * m.nr), api.allocate(64, 8 * slots), api.allocate(64, 8 * m.nr)
+    xv = 1.0 + 0.01 * np.arange(m.nr)
+    x.host()[:m.nr] = xv                                    # plain host stores into what allocate() returned
+    y.host()[:slots] = 1.0
+    assert L.sbPrefetchManaged(x.ptr) == 1 and L.sbPrefetchManaged(api.to_device(xv).ptr) == 0
+    api.spMVM(A, x, y)
+    L.sbDeviceSynchronize()
+    got = np.array(y.host()[:slots])
+    if fmt == api.FMT_SCS:
+        s = orc.scs_convert(m, 32, 4)
+        assert np.array_equal(got, orc.spmv_scs(s, xv))
+    else:
+        assert_spmv_close(got, orc.spmv_crs(m, xv), m, xv)
+    api.waxpby(m.nr, 2.0, x, -1.0, x, w)                    # w = 2x - x
+    d = api.ddot(m.nr, x, w)
+    L.sbDeviceSynchronize()
+    assert np.array_equal(np.array(w.host()[:m.nr]), orc.waxpby(2.0, xv, -1.0, xv))
+    assert abs(d - float(np.dot(xv, xv))) <= 1e-12 * float(np.dot(xv, xv))
+    x.host()[:m.nr] = 2.0 * xv                              # the host writes again: pages come back, results stay right
+    api.spMVM(A, x, y)
+    L.sbDeviceSynchronize()
+    got2 = np.array(y.host()[:slots])
+    assert np.allclose(got2, 2.0 * got, rtol=1e-13, atol=0)
+    for b in (x, y, w):
+        b.free()
+    api.destroyMatrix(A)
+
+
 # ------------------------------------------------------------------------------------------- drop-in shims
 def test_link_time_dropin_names():
     """libsparsebench_b200_CRS.so: the reference's bare symbols convertMatrix / spMVM / solveCG (Makefile:32-34)"""
