@@ -26,6 +26,10 @@ static void initContext()
     const char* lr = getenv("LOCAL_RANK");   // one process per GPU under torchrun
     if (lr) dev = atoi(lr) % n;
   }
+  // getTimeStamp() drains the device around every PROFILE()d call of the reference's drivers: let those waits spin
+  // instead of sleeping (tens of microseconds less per call). Refused when another library already created the
+  // context with other flags: not an error.
+  if (cudaSetDeviceFlags(cudaDeviceScheduleSpin) != cudaSuccess) cudaGetLastError();
   SB_CUDA(cudaSetDevice(dev));
   g_ctx.device = dev;
   SB_CUDA(cudaDeviceGetAttribute(&g_ctx.numSMs, cudaDevAttrMultiProcessorCount, dev));
@@ -190,7 +194,22 @@ int sbPrefetchManaged(const void* p)
   --it;
   if ((uintptr_t)p >= it->first + it->second.bytes) return 0;
   if (!it->second.onDevice) {
+    static const int mode = getenv("SB_MANAGED_MODE") ? atoi(getenv("SB_MANAGED_MODE")) : 0;
+    if (mode & 1) {
+      SB_CUDA(cudaMemAdvise((const void*)it->first, it->second.bytes, cudaMemAdviseSetPreferredLocation, g_ctx.device));
+      SB_CUDA(cudaMemAdvise((const void*)it->first, it->second.bytes, cudaMemAdviseSetAccessedBy, g_ctx.device));
+    }
+    if (mode & 2) SB_CUDA(cudaStreamAttachMemAsync(g_ctx.stream, (void*)it->first, 0, cudaMemAttachSingle));
+    static const bool trace = getenv("SB_TRACE_MANAGED") != nullptr;
+    struct timespec t0, t1;
+    if (trace) clock_gettime(CLOCK_MONOTONIC, &t0);
     SB_CUDA(cudaMemPrefetchAsync((const void*)it->first, it->second.bytes, g_ctx.device, g_ctx.stream));
+    if (trace) {
+      SB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+      clock_gettime(CLOCK_MONOTONIC, &t1);
+      fprintf(stderr, "[sbPrefetchManaged] %zu bytes -> GPU in %.2f ms\n", it->second.bytes,
+          (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6);
+    }
     it->second.onDevice = true;
   }
   return 1;
