@@ -41,13 +41,19 @@ static struct {
 
 static __thread int t_rank = 0;
 
+#define SHIM_MAX_TYPES 64
+static size_t g_usertype[SHIM_MAX_TYPES];      /* extent of struct datatypes, MPI_SHIM_USERTYPE + i */
+static int g_nusertypes = 0;
+
 static size_t tsize(MPI_Datatype t)
 {
   switch (t) {
   case MPI_INT: case MPI_UNSIGNED: case MPI_FLOAT: return 4;
   case MPI_UNSIGNED_LONG_LONG: case MPI_DOUBLE: return 8;
-  case MPI_BYTE: return 1;
-  default: fprintf(stderr, "mpi_shim: unsupported datatype %d\n", t); abort();
+  case MPI_BYTE: case MPI_CHAR: return 1;
+  default:
+    if (t >= MPI_SHIM_USERTYPE && t < MPI_SHIM_USERTYPE + g_nusertypes) return g_usertype[t - MPI_SHIM_USERTYPE];
+    fprintf(stderr, "mpi_shim: unsupported datatype %d\n", t); abort();
   }
 }
 
@@ -214,16 +220,131 @@ int MPI_Neighbor_alltoallv(const void* sb, const int sc[], const int sd[], MPI_D
 }
 
 #define STUB(name) { fprintf(stderr, "mpi_shim: " name " is a link-only stub\n"); abort(); return 0; }
-int MPI_Bcast(void* b, int n, MPI_Datatype t, int root, MPI_Comm c) STUB("MPI_Bcast")
 int MPI_Get_address(const void* p, MPI_Aint* a) { *a = (MPI_Aint)p; return 0; }
 MPI_Aint MPI_Aint_diff(MPI_Aint a, MPI_Aint b) { return a - b; }
-int MPI_Type_create_struct(int n, const int bl[], const MPI_Aint d[], const MPI_Datatype t[], MPI_Datatype* nt) STUB("MPI_Type_create_struct")
-int MPI_Type_commit(MPI_Datatype* t) STUB("MPI_Type_commit")
-int MPI_Type_free(MPI_Datatype* t) STUB("MPI_Type_free")
-int MPI_Scatter(const void* sb, int sc, MPI_Datatype st, void* rb, int rc, MPI_Datatype rt, int root, MPI_Comm c) STUB("MPI_Scatter")
-int MPI_Scatterv(const void* sb, const int sc[], const int sd[], MPI_Datatype st, void* rb, int rc, MPI_Datatype rt, int root, MPI_Comm c) STUB("MPI_Scatterv")
+
+/* struct datatype = its extent: last member's end, rounded up to the widest member (C layout of the structs the
+   reference describes: MMEntry {int,int,double} = 16, FEntry {unsigned,float} = 8) */
+int MPI_Type_create_struct(int n, const int bl[], const MPI_Aint d[], const MPI_Datatype t[], MPI_Datatype* nt)
+{
+  size_t end = 0, align = 1;
+  for (int i = 0; i < n; i++) {
+    size_t sz = tsize(t[i]);
+    if ((size_t)d[i] + sz * (size_t)bl[i] > end) end = (size_t)d[i] + sz * (size_t)bl[i];
+    if (sz > align) align = sz;
+  }
+  end = (end + align - 1) / align * align;
+  pthread_mutex_lock(&W.mtx);
+  if (g_nusertypes >= SHIM_MAX_TYPES) g_nusertypes = 0;          /* test code: recycle */
+  g_usertype[g_nusertypes] = end;
+  *nt = MPI_SHIM_USERTYPE + g_nusertypes++;
+  pthread_mutex_unlock(&W.mtx);
+  return 0;
+}
+int MPI_Type_commit(MPI_Datatype* t) { (void)t; return 0; }
+int MPI_Type_free(MPI_Datatype* t) { (void)t; return 0; }
+
+/* rooted collectives: the root publishes its buffers, everybody copies its share */
+int MPI_Bcast(void* b, int n, MPI_Datatype t, int root, MPI_Comm c)
+{
+  (void)c;
+  W.slot[t_rank] = b;
+  bar();
+  if (t_rank != root) memcpy(b, W.slot[root], (size_t)n * tsize(t));
+  bar();
+  return 0;
+}
+int MPI_Scatter(const void* sb, int sc, MPI_Datatype st, void* rb, int rc, MPI_Datatype rt, int root, MPI_Comm c)
+{
+  (void)c; (void)rc; (void)rt;
+  W.slot[t_rank] = sb;
+  bar();
+  memcpy(rb, (const char*)W.slot[root] + (size_t)t_rank * (size_t)sc * tsize(st), (size_t)sc * tsize(st));
+  bar();
+  return 0;
+}
+int MPI_Scatterv(const void* sb, const int sc[], const int sd[], MPI_Datatype st, void* rb, int rc, MPI_Datatype rt, int root, MPI_Comm c)
+{
+  (void)c; (void)rt;
+  W.slot[t_rank] = sb; W.slot_cnt[t_rank] = sc; W.slot_dsp[t_rank] = sd;
+  bar();
+  if (W.slot_cnt[root][t_rank] != rc) { fprintf(stderr, "mpi_shim: Scatterv count mismatch\n"); abort(); }
+  memcpy(rb, (const char*)W.slot[root] + (size_t)W.slot_dsp[root][t_rank] * tsize(st), (size_t)rc * tsize(st));
+  bar();
+  return 0;
+}
 int MPI_Gather(const void* sb, int sc, MPI_Datatype st, void* rb, int rc, MPI_Datatype rt, int root, MPI_Comm c) STUB("MPI_Gather")
 int MPI_Reduce(const void* sb, void* rb, int n, MPI_Datatype t, MPI_Op op, int root, MPI_Comm c) STUB("MPI_Reduce")
+
+/* ---- MPI-IO subset on POSIX files. A view is (byte displacement, element type); the individual file pointer counts
+   elements of that type from the displacement (MPI-3.1 section 13.3, 13.4.3), which is all matrixBinfile.c relies on. */
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#define SHIM_MAX_FILES 256
+static struct { int fd; long long disp; size_t esize; long long pos; } g_file[SHIM_MAX_FILES];
+static int g_nfiles = 0;
+
+int MPI_File_open(MPI_Comm c, const char* filename, int amode, MPI_Info info, MPI_File* fh)
+{
+  (void)c; (void)info;
+  int flags = (amode & MPI_MODE_WRONLY) ? O_WRONLY : O_RDONLY;
+  if (amode & MPI_MODE_CREATE) flags |= O_CREAT;
+  int fd = open(filename, flags, 0644);
+  if (fd < 0) { fprintf(stderr, "mpi_shim: cannot open %s\n", filename); abort(); }
+  pthread_mutex_lock(&W.mtx);
+  if (g_nfiles >= SHIM_MAX_FILES) g_nfiles = 0;
+  int id = g_nfiles++;
+  g_file[id].fd = fd; g_file[id].disp = 0; g_file[id].esize = 1; g_file[id].pos = 0;
+  pthread_mutex_unlock(&W.mtx);
+  *fh = id;
+  return 0;
+}
+int MPI_File_close(MPI_File* fh) { close(g_file[*fh].fd); g_file[*fh].fd = -1; return 0; }
+int MPI_File_set_view(MPI_File fh, MPI_Offset disp, MPI_Datatype etype, MPI_Datatype filetype, const char* datarep, MPI_Info info)
+{
+  (void)filetype; (void)datarep; (void)info;
+  g_file[fh].disp = disp; g_file[fh].esize = tsize(etype); g_file[fh].pos = 0;
+  return 0;
+}
+int MPI_File_write(MPI_File fh, const void* buf, int count, MPI_Datatype t, MPI_Status* st)
+{
+  size_t bytes = (size_t)count * tsize(t);
+  ssize_t w = pwrite(g_file[fh].fd, buf, bytes, (off_t)(g_file[fh].disp + g_file[fh].pos * (long long)g_file[fh].esize));
+  if (w != (ssize_t)bytes) { fprintf(stderr, "mpi_shim: short write\n"); abort(); }
+  g_file[fh].pos += (long long)(bytes / g_file[fh].esize);
+  if (st) st->shim_bytes = (long long)w;
+  return 0;
+}
+int MPI_File_read(MPI_File fh, void* buf, int count, MPI_Datatype t, MPI_Status* st)
+{
+  size_t bytes = (size_t)count * tsize(t);
+  ssize_t r = pread(g_file[fh].fd, buf, bytes, (off_t)(g_file[fh].disp + g_file[fh].pos * (long long)g_file[fh].esize));
+  if (r < 0) r = 0;
+  g_file[fh].pos += (long long)((size_t)r / g_file[fh].esize);
+  if (st) st->shim_bytes = (long long)r;
+  return 0;
+}
+int MPI_Get_count(const MPI_Status* st, MPI_Datatype t, int* count) { *count = (int)((size_t)st->shim_bytes / tsize(t)); return 0; }
+int MPI_File_sync(MPI_File fh) { fsync(g_file[fh].fd); return 0; }
+int MPI_File_get_size(MPI_File fh, MPI_Offset* size)
+{
+  struct stat sb;
+  fstat(g_file[fh].fd, &sb);
+  *size = (MPI_Offset)sb.st_size;
+  return 0;
+}
+int MPI_File_get_position(MPI_File fh, MPI_Offset* offset) { *offset = g_file[fh].pos; return 0; }
+int MPI_File_get_byte_offset(MPI_File fh, MPI_Offset offset, MPI_Offset* disp)
+{
+  *disp = g_file[fh].disp + offset * (long long)g_file[fh].esize;
+  return 0;
+}
+int MPI_File_seek(MPI_File fh, MPI_Offset offset, int whence)
+{
+  g_file[fh].pos = (whence == MPI_SEEK_CUR) ? g_file[fh].pos + offset : offset;
+  return 0;
+}
 
 typedef struct { int rank, size; shim_rank_fn fn; void* arg; } shim_thread_arg;
 

@@ -16,6 +16,7 @@
 #include "allocate.h"
 #include "comm.h"
 #include "matrix.h"
+#include "matrixBinfile.h"
 #include "parameter.h"
 #include "solver.h"
 
@@ -158,4 +159,71 @@ void refdrv_free(int P, RefRankOut* out)
     free(o->elementsToSend); free(o->rowPtr); free(o->cols); free(o->vals);
     free(o->haloProbe); free(o->hist); free(o->x);
   }
+}
+
+
+/* ---- file input paths of main.c on P shim ranks: MatrixMarket (main.c:64-71, comm.c:311-402) and .bmx
+ * (main.c:36-47, :72-76, matrixBinfile.c:38-236). Hands every rank's GMatrix back. */
+typedef struct {
+  int nr, nc, nnz, totalNr, totalNnz, startRow, stopRow;
+  unsigned int* rowPtr;   /* nr+1 */
+  unsigned int* cols;     /* rowPtr[nr] */
+  double* vals;
+} RefGmOut;
+
+typedef struct { const char* path; const char* path2; RefGmOut* out; int mode; } FileArgs;
+
+static void keep_gm(const GMatrix* m, RefGmOut* o)
+{
+  o->nr = (int)m->nr; o->nc = (int)m->nc; o->nnz = (int)m->nnz; o->totalNr = (int)m->totalNr; o->totalNnz = (int)m->totalNnz;
+  o->startRow = (int)m->startRow; o->stopRow = (int)m->stopRow;
+  size_t stored = m->rowPtr[m->nr];
+  o->rowPtr = (unsigned int*)malloc(sizeof(unsigned int) * (m->nr + 1));
+  memcpy(o->rowPtr, m->rowPtr, sizeof(unsigned int) * (m->nr + 1));
+  o->cols = (unsigned int*)malloc(sizeof(unsigned int) * (stored ? stored : 1));
+  o->vals = (double*)malloc(sizeof(double) * (stored ? stored : 1));
+  for (size_t j = 0; j < stored; j++) { o->cols[j] = m->entries[j].col; o->vals[j] = m->entries[j].val; }
+}
+
+static void file_rank_main(int rank, int size, void* argp)
+{
+  FileArgs* a = (FileArgs*)argp;
+  Comm c;
+  memset(&c, 0, sizeof(c));
+  commInit(&c, 0, NULL);
+  GMatrix m;
+  if (a->mode == 0 || a->mode == 1) {          /* MatrixMarket: main.c:64-71 (and :36-47 for mode 1) */
+    MMMatrix mm, mmLocal;
+    if (commIsMaster(&c)) MMMatrixRead(&mm, (char*)a->path);
+    commDistributeMatrix(&c, &mm, &mmLocal);
+    matrixConvertfromMM(&mmLocal, &m);
+    if (a->mode == 1) matrixBinWrite(&m, &c, (char*)a->path2);
+  } else {                                      /* .bmx: main.c:72-76 */
+    matrixBinRead(&m, &c, (char*)a->path);
+  }
+  keep_gm(&m, &a->out[rank]);
+  fflush(stdout);
+}
+
+void refdrv_mm_read(int P, const char* mtx, RefGmOut* out)
+{
+  FileArgs a = { mtx, NULL, out, 0 };
+  shim_run(P, file_rank_main, &a);
+}
+
+void refdrv_bmx_write(const char* mtx, const char* bmx, RefGmOut* out)
+{
+  FileArgs a = { mtx, bmx, out, 1 };
+  shim_run(1, file_rank_main, &a);
+}
+
+void refdrv_bmx_read(int P, const char* bmx, RefGmOut* out)
+{
+  FileArgs a = { bmx, NULL, out, 2 };
+  shim_run(P, file_rank_main, &a);
+}
+
+void refdrv_gm_free(int P, RefGmOut* out)
+{
+  for (int r = 0; r < P; r++) { free(out[r].rowPtr); free(out[r].cols); free(out[r].vals); }
 }

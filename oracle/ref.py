@@ -246,3 +246,50 @@ def mpi_run(P, nx, ny, nz, use7pt=False, itermax=10, eps=0.0, do_cg=True):
         res.append(d)
     L.refdrv_free(P, out)
     return res, cap.text
+
+
+class RefGmOut(C.Structure):  # oracle/mpi_shim/ref_driver.c
+    _fields_ = [("nr", C.c_int), ("nc", C.c_int), ("nnz", C.c_int), ("totalNr", C.c_int), ("totalNnz", C.c_int),
+                ("startRow", C.c_int), ("stopRow", C.c_int), ("rowPtr", C.POINTER(C.c_uint32)),
+                ("cols", C.POINTER(C.c_uint32)), ("vals", C.POINTER(C.c_double))]
+
+
+def _gm_list(L, P, out):
+    res = []
+    for r in range(P):
+        o = out[r]
+        stored = int(o.rowPtr[o.nr])
+        res.append(dict(nr=o.nr, nc=o.nc, nnz=o.nnz, totalNr=o.totalNr, totalNnz=o.totalNnz, startRow=o.startRow, stopRow=o.stopRow,
+                        rowPtr=np.ctypeslib.as_array(o.rowPtr, (o.nr + 1,)).copy(),
+                        cols=np.ctypeslib.as_array(o.cols, (max(stored, 1),))[:stored].copy(),
+                        vals=np.ctypeslib.as_array(o.vals, (max(stored, 1),))[:stored].copy()))
+    L.refdrv_gm_free(P, out)
+    return res
+
+
+def mpi_mm_read(P, mtx):
+    """main.c:64-71 on P shim ranks of the unmodified sources: MMMatrixRead on the master, commDistributeMatrix
+    (comm.c:311-402, MPI branch), matrixConvertfromMM. Returns every rank's GMatrix as a dict."""
+    L = load("mpi_CRS")
+    out = (RefGmOut * P)()
+    with capture_stdout():
+        L.refdrv_mm_read(P, mtx.encode(), out)
+    return _gm_list(L, P, out)
+
+
+def mpi_bmx_write(mtx, bmx):
+    """main.c:36-47 (`-c file.mtx`): the reference's own matrixBinWrite (matrixBinfile.c:38-105) on one shim rank."""
+    L = load("mpi_CRS")
+    out = (RefGmOut * 1)()
+    with capture_stdout():
+        L.refdrv_bmx_write(mtx.encode(), bmx.encode(), out)
+    return _gm_list(L, 1, out)[0]
+
+
+def mpi_bmx_read(P, bmx):
+    """the reference's own matrixBinRead (matrixBinfile.c:107-236) on P shim ranks."""
+    L = load("mpi_CRS")
+    out = (RefGmOut * P)()
+    with capture_stdout():
+        L.refdrv_bmx_read(P, bmx.encode(), out)
+    return _gm_list(L, P, out)

@@ -136,8 +136,9 @@ void matrixConvertfromMM(MMMatrix* mm, GMatrix* m)
 // rowPtr[totalNr+1] (global entry offsets, :75-82), then totalNnz records {u32 col; f32 val} (:19-35, :92-103).
 // Values are float32 on disk. Every rank reads its own row block with plain POSIX I/O: rows split like sizeOfRank
 // (:14-17, :157-164), row pointers made local by subtracting the block's first entry offset (:189-205). Host arrays.
-// Parity note: the reference implementation needs an MPI library to compile, which this image does not have; these
-// two functions are pinned by the layout above (tests parse the file independently), not by a reference run.
+// Parity: pinned by the reference itself -- its matrixBinfile.c compiled against the test-only MPI shim (whose MPI-IO
+// subset runs on POSIX files) wrote tests/golden/reference_fixtures/klein_ref.bmx and read it back on 1, 2, 3 and 7
+// ranks (tests/golden/make_file_golden.py); the file written here is byte-identical, the row blocks read here equal.
 namespace {
 
 constexpr size_t kBmxHeader = 24;

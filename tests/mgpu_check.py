@@ -123,6 +123,18 @@ def main():
     if rank == 0:
         os.unlink(path)
 
+    # the reference's OWN multi-rank distribution of the klein file (unmodified comm.c:311-402 on shim ranks,
+    # tests/golden/ref_files.npz): this rank's block must be identical
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "ref_files.npz"))
+    key = "mm_matrix_band_klein_P%d_r%d_" % (world, rank)
+    if key + "scalars" in gold:
+        gk = api.matrixRead(os.path.join(ROOT, "tests", "golden", "reference_fixtures", "matrix_band_klein.mtx"), comm)
+        check([gk.nr, gk.nc, gk.nnz, gk.totalNr, gk.totalNnz, gk.startRow, gk.stopRow] == list(gold[key + "scalars"]),
+              "klein distribution: header differs from the reference's", failures)
+        rpk, colk, valk = api.gmatrix_arrays(gk)
+        check(np.array_equal(rpk, gold[key + "rowPtr"]) and np.array_equal(colk, gold[key + "cols"]) and np.array_equal(valk, gold[key + "vals"]),
+              "klein distribution: arrays differ from the reference's", failures)
+
     # an irregular SPD matrix (random long-range couplings, 1..40 entries per row): every rank neighbours every other
     # one, halo lists are not contiguous planes, the SELL sort really permutes rows, row lengths vary
     rng = np.random.default_rng(7)

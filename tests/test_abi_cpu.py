@@ -275,3 +275,60 @@ def test_bmx_write_then_read_per_rank(tmp_path, fixtures_dir, P):
         assert np.array_equal(cl, col0[lo:hi]) and np.array_equal(vl, val0[lo:hi].astype(np.float32).astype(np.float64))
         L.sbFreeGMatrix(C.byref(m))
         start += n
+
+
+# ------------------------------------------------------------------------------------------- .bmx pinned by the reference
+@pytest.fixture(scope="module")
+def ref_files():
+    """outputs of the reference's own matrixBinWrite / matrixBinRead / multi-rank commDistributeMatrix (shim ranks),
+    tests/golden/make_file_golden.py"""
+    return np.load(os.path.join(ROOT, "tests", "golden", "ref_files.npz"))
+
+
+def test_bmx_written_bytes_equal_the_reference_file(tmp_path, fixtures_dir):
+    """matrixBinWrite (matrixBinfile.c:38-105): the file this library writes for klein is byte-identical to the one the
+    reference's own code wrote through MPI-IO (tests/golden/reference_fixtures/klein_ref.bmx)."""
+    L = api.lib()
+    one = api.Comm()
+    one.rank, one.size = 0, 1
+    g = api.matrixRead(os.path.join(fixtures_dir, "matrix_band_klein.mtx"))
+    path = str(tmp_path / "klein.bmx")
+    L.matrixBinWrite(C.byref(g), C.byref(one), path.encode())
+    mine, ref_bytes = open(path, "rb").read(), open(os.path.join(fixtures_dir, "klein_ref.bmx"), "rb").read()
+    assert len(ref_bytes) == 2820 and mine == ref_bytes
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 7])
+def test_bmx_read_equals_the_reference_reader(ref_files, fixtures_dir, P):
+    """matrixBinRead (matrixBinfile.c:107-236) of the reference-written file, every rank of P: header fields, local
+    row pointers, columns and float32-rounded values equal what the reference's own reader returned on P shim ranks."""
+    L = api.lib()
+    path = os.path.join(fixtures_dir, "klein_ref.bmx")
+    live = None
+    from oracle import ref
+    if ref.available("mpi_CRS"):
+        live = ref.mpi_bmx_read(P, path)
+    for r in range(P):
+        c = api.Comm()
+        c.rank, c.size = r, P
+        m = api.GMatrix()
+        L.matrixBinRead(C.byref(m), C.byref(c), path.encode())
+        m._device = False
+        key = "bmx_klein_P%d_r%d_" % (P, r)
+        assert [m.nr, m.nc, m.nnz, m.totalNr, m.totalNnz, m.startRow, m.stopRow] == list(ref_files[key + "scalars"])
+        rp, col, val = api.gmatrix_arrays(m)
+        assert np.array_equal(rp, ref_files[key + "rowPtr"]) and np.array_equal(col, ref_files[key + "cols"])
+        assert np.array_equal(val, ref_files[key + "vals"])
+        if live is not None:
+            assert np.array_equal(rp, live[r]["rowPtr"]) and np.array_equal(col, live[r]["cols"]) and np.array_equal(val, live[r]["vals"])
+        L.sbFreeGMatrix(C.byref(m))
+
+
+def test_single_rank_mm_path_equals_the_reference_mpi_build(ref_files, fixtures_dir):
+    """MMMatrixRead + commDistributeMatrix + matrixConvertfromMM on ONE rank against the reference's -D_MPI build
+    (which, unlike its non-MPI branch, fills totalNr / totalNnz: comm.c:366-368 vs :404-410)."""
+    g = api.matrixRead(os.path.join(fixtures_dir, "matrix_band_klein.mtx"))
+    key = "mm_matrix_band_klein_P1_r0_"
+    assert [g.nr, g.nc, g.nnz, g.totalNr, g.totalNnz, g.startRow, g.stopRow] == list(ref_files[key + "scalars"])
+    rp, col, val = api.gmatrix_arrays(g)
+    assert np.array_equal(rp, ref_files[key + "rowPtr"]) and np.array_equal(col, ref_files[key + "cols"]) and np.array_equal(val, ref_files[key + "vals"])
