@@ -171,6 +171,9 @@ void sbTimerDestroy(void* timer);
 int sbDeviceCount(void);
 void sbSetDevice(int device);
 void sbFlushL2(void);                                /* overwrites a buffer larger than L2 */
+/* GB/s of a read-only streaming kernel over a fresh buffer of `bytes` (>> L2), best of `reps`: the read-stream peak
+ * quoted beside the copy peak of MEASURED_PEAKS.json (the SpMV is a ~98 % read stream) */
+double sbMeasureReadBandwidth(size_t bytes, int reps);
 size_t sbKernelLaunchCount(void);                    /* number of this library's kernel launches so far */
 
 /* ---------------------------------------------------------------- matrix sources */

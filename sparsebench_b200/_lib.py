@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsparsebench_b200.so")
+LIB_PATH = os.environ.get("SB_LIB") or os.path.join(HERE, "libsparsebench_b200.so")   # SB_LIB: an experimental build
 _lib = None
 
 

@@ -103,6 +103,8 @@ def lib():
         L.sbTimerStopMs.restype = C.c_double
         L.sbTimerDestroy.argtypes = [C.c_void_p]
         L.sbKernelLaunchCount.restype = C.c_size_t
+        L.sbMeasureReadBandwidth.restype = C.c_double
+        L.sbMeasureReadBandwidth.argtypes = [C.c_size_t, C.c_int]
         L.sbSetDevice.argtypes = [C.c_int]
         L.matrixGenerate.argtypes = [C.POINTER(GMatrix), C.POINTER(Parameter), C.c_int, C.c_int, C.c_bool]
         L.sbGenerateDevice.argtypes = [C.POINTER(GMatrix), C.POINTER(Parameter), C.c_int, C.c_int, C.c_bool]

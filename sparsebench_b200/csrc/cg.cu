@@ -38,6 +38,7 @@ struct CgSolver {
   PeerReduce pendingRho;                   // epoch of the newest rho that has been pushed but not yet collected
   const int* elems = nullptr;              // multi-GPU send list in solver numbering (owned by the Comm)
   bool pBorrowed = false;                  // p is the Comm's persistent, peer-mapped halo vector
+  unsigned long long* syncTrace = nullptr; // SB_SYNC_TRACE=1: device counters of the waits inside the multi-GPU kernels
   uint32_t intLo = 0, intHi = 0;           // SpMV units [intLo, intHi) reference no halo column
   uint32_t n = 0;
   size_t rowSlots = 0, colSlots = 0;
@@ -182,7 +183,7 @@ struct CgSolver {
     fused = (flags & SB_CG_FUSED) != 0;
     profile = (flags & SB_CG_PROFILE) != 0;
     print = (flags & SB_CG_PRINT) != 0 && (!comm || comm->rank == 0);
-    overlap = (flags & SB_CG_NO_OVERLAP) == 0;
+    overlap = (flags & SB_CG_NO_OVERLAP) == 0 && getenv("SB_CG_NO_OVERLAP") == nullptr;
     generated = param->filename && (strcmp(param->filename, "generate") == 0 || strcmp(param->filename, "generate7P") == 0);
     n = A.nr;
     rowSlots = (size_t)(A.nrPadded > n ? A.nrPadded : n) + 2;
@@ -198,6 +199,10 @@ struct CgSolver {
         pBorrowed = gated = p != nullptr;
       }
       elems = commSolverElements(comm, A.permKey, A.oldToNew, s);   // vectors are row-permuted: send p[oldToNew[element]]
+      if (gated && getenv("SB_SYNC_TRACE")) {
+        syncTrace = (unsigned long long*)sbAllocateDevice(64, sizeof(unsigned long long) * 16);
+        SB_CUDA(cudaMemsetAsync(syncTrace, 0, sizeof(unsigned long long) * 16, s));
+      }
       if (gated) {
         fusedReduce = fused && getenv("SB_NO_FUSED_REDUCE") == nullptr;
         fusedPut = fusedReduce && getenv("SB_NO_FUSED_PUT") == nullptr && commPrepareFusedPut(comm, A.permKey, elems);
@@ -295,10 +300,15 @@ struct CgSolver {
           FusedPut fp;
           HaloGate gate;
           if (fusedPut) gate = commFusedPutBegin(comm, &fp);    // the halo exchange (:122) rides on the p update
+          if (syncTrace) {
+            gate.trace = syncTrace;
+            pendingRho.trace = pendingRho.size ? syncTrace + 8 : nullptr;
+          }
           // the p update completes the global rho[k-1] and stores it to the host mirror itself
           launchCgUpdateP(n, k, rho, r, p, pendingRho.size ? &pendingRho : nullptr, fusedPut ? &fp : nullptr, hRho, s);   // :109 / :111-114
           mark(R_UPDATE_P);
-          const PeerReduce prPAp = commBeginReduce(comm);
+          PeerReduce prPAp = commBeginReduce(comm);
+          if (syncTrace) prPAp.trace = syncTrace + 4;
           DotArgs d { pAp + k, false, 1, &prPAp };
           spmvWithHalo(&d, fusedPut ? &gate : nullptr);         // :122-125
           pendingRho = commBeginReduce(comm);
@@ -354,6 +364,15 @@ struct CgSolver {
     Context& c = ctx();
     SB_CUDA(cudaStreamSynchronize(s));
     if (pBorrowed) commReleaseHaloVector(comm);
+    if (syncTrace) {
+      unsigned long long h[16];
+      sbCopyToHost(h, syncTrace, sizeof(h));
+      sbFree(syncTrace);
+      fprintf(stderr, "[sync trace r%d] %d iterations | halo gate: %.2f us mean, %.2f us max per waiting CTA/warp (%llu waits) | "
+                      "collect p.Ap (x/r update, block 0): %.2f us mean over %llu | collect r.r (p update, block 0): %.2f us mean over %llu\n",
+          comm ? comm->rank : 0, k - 1, h[2] ? 1e-3 * (double)h[0] / (double)h[2] : 0.0, 1e-3 * (double)h[1], h[2],
+          h[5] ? 1e-3 * (double)h[4] / (double)h[5] : 0.0, h[5], h[9] ? 1e-3 * (double)h[8] / (double)h[9] : 0.0, h[9]);
+    }
     if (fused && (int)hist.size() < k) {
       // iteration k-1 was the last one executed; record its normr = sqrt(rho[k-2])
       const double last = k >= 3 ? sqrt(hRho[k - 2]) : normr;

@@ -103,9 +103,18 @@ __device__ __forceinline__ void gridSum(double blockPartial, double* partials, u
 
 // Second half of the all-reduce: every thread of the calling block gets the global sum. `vals` is shared memory
 // for kMaxRanks doubles. Contains block barriers: call from all threads.
+__device__ __forceinline__ unsigned long long globalTimerNs()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 __device__ __forceinline__ double peerCollect(const PeerReduce& pr, double* vals)
 {
   const int slot = (int)(pr.epoch % kRedDepth);
+  const bool traced = pr.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  const unsigned long long t0 = traced ? globalTimerNs() : 0ull;
   if ((int)threadIdx.x < pr.size) {
     const unsigned long long* flag = &pr.mine->redFlag[slot][threadIdx.x];
     unsigned long long seen;
@@ -119,6 +128,10 @@ __device__ __forceinline__ double peerCollect(const PeerReduce& pr, double* vals
     vals[threadIdx.x] = *(volatile double*)&pr.mine->redVal[slot][threadIdx.x];
   }
   __syncthreads();
+  if (traced) {                                           // how long the slowest peer's partial kept this rank waiting
+    atomicAdd(pr.trace, globalTimerNs() - t0);
+    atomicAdd(pr.trace + 1, 1ull);
+  }
   double acc = vals[0];
   for (int r = 1; r < pr.size; r++) acc += vals[r];      // rank order: same bits on every rank
   __syncthreads();

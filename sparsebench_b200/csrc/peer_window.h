@@ -24,6 +24,7 @@ struct PeerReduce {
   unsigned long long epoch = 0;
   CtrlWindow* mine = nullptr;
   CtrlWindow* const* peers = nullptr;   // device array of `size` mapped windows (own window at [rank])
+  unsigned long long* trace = nullptr;  // SB_SYNC_TRACE: [0] += ns block 0 waited in the collect, [1] += 1
 };
 
 } // namespace sb

@@ -171,6 +171,7 @@ struct HaloGate {
   int nsrc = 0;                                            // 0: no gate
   unsigned long long target[kMaxGateSources] = {};         // elements received from source i since the vector was attached
   const unsigned long long* flag[kMaxGateSources] = {};
+  unsigned long long* trace = nullptr;                     // SB_SYNC_TRACE: [0] += ns waited, [1] = max ns, [2] += 1 (per waiting CTA / warp)
 };
 // The same delivery fused into the kernel that produces the values (the CG's p update): element e of the vector
 // goes to position inv[d][e - lo[d]] of destination d's halo (negative: not sent there).

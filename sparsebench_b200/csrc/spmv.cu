@@ -51,11 +51,13 @@ static bool useLegacyKernels()
 template <bool COHERENT>
 __device__ __forceinline__ double gatherX(const double* p)
 {
+#ifndef SB_EXPERIMENT_NC       // -DSB_EXPERIMENT_NC: timing experiment only (read-only path even behind the gate)
   if (COHERENT) {
     double v;
     asm("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
   }
+#endif
   return __ldg(p);
 }
 
@@ -65,6 +67,7 @@ __device__ __forceinline__ double gatherX(const double* p)
 struct GateSmem {
   const unsigned long long* flag[kMaxGateSources];
   unsigned long long target[kMaxGateSources];
+  unsigned long long* trace;
 };
 __device__ __forceinline__ void gateStore(GateSmem& g, const HaloGate& gate)
 {
@@ -73,10 +76,13 @@ __device__ __forceinline__ void gateStore(GateSmem& g, const HaloGate& gate)
     g.flag[i] = gate.flag[i];
     g.target[i] = gate.target[i];
   }
+  g.trace = gate.trace;
 }
 // Called by ONE thread.
 __device__ __noinline__ void gateWait(const GateSmem* g, int nsrc)
 {
+  unsigned long long* trace = g->trace;
+  const unsigned long long t0 = trace ? globalTimerNs() : 0ull;
   for (int i = 0; i < nsrc; i++) {
     const unsigned long long* p = g->flag[i];
     const unsigned long long target = g->target[i];
@@ -88,6 +94,12 @@ __device__ __noinline__ void gateWait(const GateSmem* g, int nsrc)
       __nanosleep(40);
       if (clock64() - start > 40000000000ll) __trap();   // dead peer: fail instead of hanging the GPU
     }
+  }
+  if (trace) {
+    const unsigned long long dt = globalTimerNs() - t0;
+    atomicAdd(trace, dt);
+    atomicMax(trace + 1, dt);
+    atomicAdd(trace + 2, 1ull);
   }
 }
 
