@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "device_utils.cuh"
 #include "peer_window.h"
 #include "sb_internal.h"
 #include "sb_partition.h"
@@ -47,7 +48,6 @@ namespace sb {
 // MPI_Neighbor_alltoallv (C1) of comm.c:627-651 are one launch. The all-reduce of a dot product is one
 // single-CTA kernel: every rank stores its partial into slot [rank] of every peer and sums the slots of its
 // own window in rank order, so all ranks obtain bit-identical results.
-constexpr long long kSpinTimeoutCycles = 40000000000ll;   // ~20 s: a dead peer must not hang the GPU forever
 
 struct PutPlan {
   int ndest;
@@ -303,10 +303,10 @@ __device__ __forceinline__ void stReleaseSys(unsigned long long* p, unsigned lon
 __device__ __forceinline__ void spinUntilAtLeast(const unsigned long long* p, unsigned long long target)
 {
   if (ldAcquireSys(p) >= target) return;
-  const long long start = clock64();
+  const unsigned long long start = globalTimerNs();
   while (ldAcquireSys(p) < target) {
     __nanosleep(40);
-    if (clock64() - start > kSpinTimeoutCycles) __trap();
+    if (globalTimerNs() - start > kPeerTimeoutNs) __trap();
   }
 }
 

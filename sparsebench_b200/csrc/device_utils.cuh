@@ -29,6 +29,17 @@ __device__ __forceinline__ double2 ldStream2(const double* p)
   return v;
 }
 
+// wall-clock nanoseconds (the same on every SM, independent of the SM clock)
+__device__ __forceinline__ unsigned long long globalTimerNs()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// A kernel that waits for a peer gives up after this long and traps (the host sees a launch failure and exits): a dead
+// peer must not hang the GPU forever.
+constexpr unsigned long long kPeerTimeoutNs = 20000000000ull;   // 20 s
+
 // The reference accumulates `sum += val * x` with a separately rounded multiply and add (strict C, no
 // contraction on baseline x86-64). Keeping that order and rounding makes row sums bit-identical to the
 // reference's; fp64 pipes are <5 % utilised by an HBM-bound SpMV, so the extra instruction is free.
@@ -103,13 +114,6 @@ __device__ __forceinline__ void gridSum(double blockPartial, double* partials, u
 
 // Second half of the all-reduce: every thread of the calling block gets the global sum. `vals` is shared memory
 // for kMaxRanks doubles. Contains block barriers: call from all threads.
-__device__ __forceinline__ unsigned long long globalTimerNs()
-{
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-
 __device__ __forceinline__ double peerCollect(const PeerReduce& pr, double* vals)
 {
   const int slot = (int)(pr.epoch % kRedDepth);
@@ -118,12 +122,12 @@ __device__ __forceinline__ double peerCollect(const PeerReduce& pr, double* vals
   if ((int)threadIdx.x < pr.size) {
     const unsigned long long* flag = &pr.mine->redFlag[slot][threadIdx.x];
     unsigned long long seen;
-    const long long start = clock64();
+    const unsigned long long start = globalTimerNs();
     for (;;) {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
       if (seen >= pr.epoch) break;
       __nanosleep(40);
-      if (clock64() - start > 40000000000ll) __trap();   // dead peer: fail instead of hanging the GPU
+      if (globalTimerNs() - start > kPeerTimeoutNs) __trap();
     }
     vals[threadIdx.x] = *(volatile double*)&pr.mine->redVal[slot][threadIdx.x];
   }

@@ -87,12 +87,12 @@ __device__ __noinline__ void gateWait(const GateSmem* g, int nsrc)
     const unsigned long long* p = g->flag[i];
     const unsigned long long target = g->target[i];
     unsigned long long v;
-    const long long start = clock64();
+    const unsigned long long start = globalTimerNs();
     for (;;) {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
       if (v >= target) break;
       __nanosleep(40);
-      if (clock64() - start > 40000000000ll) __trap();   // dead peer: fail instead of hanging the GPU
+      if (globalTimerNs() - start > kPeerTimeoutNs) __trap();   // dead peer: fail instead of hanging the GPU
     }
   }
   if (trace) {
