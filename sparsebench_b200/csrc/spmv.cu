@@ -390,7 +390,6 @@ spmvSellAnyCKernel(SellView A, const double* __restrict__ x, double* __restrict_
 // touch rowPtr/col/val in global memory, and the number of consumer warps is independent of the bytes in
 // flight. Tiles whose non-zeros do not fit a stage are read straight from global memory by the same lanes.
 constexpr uint32_t kPipeMaxRows = 768;                  // row pointers per stage
-constexpr int kRowsVar = 12;                            // default VAR of spmvRowsPipeKernel (see there; sweep in profiles/README.md)
 // fused dot: the tile's own x entries are staged behind the ring, one slot of kPipeXBytes per stage
 constexpr uint32_t kPipeXBytes = (kPipeMaxRows + 8) * 8;
 
@@ -479,7 +478,7 @@ struct CcrsPipe {                                       // stage: {col, pad, val
 //   8  fused dot: the tile's own x entries arrive with the tile through the bulk-copy engine (one more 16-byte
 //      granular copy per tile into a slot behind the ring) instead of through one more global load per row:
 //      fused-dot cost +2.0 % -> +1.0 % at 256^3, +3.3 % -> +1.7 % at 128^3
-// Default: 12.
+// Defaults (Access::kVar): CRS 12; CCRS 4 (its 16-byte record fetch leaves no registers for the x slots: fused dot +15 % with 8).
 template <bool DOT, int LPR, typename L, bool GATED, int VAR>
 __global__ void __launch_bounds__((L::kWarps + 1) * 32, 1)
 spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __restrict__ x, double* __restrict__ y,
@@ -713,6 +712,7 @@ struct CrsAccess {
   template <typename P> P pipe() const { return P { col, val }; }
   static constexpr uint32_t kStagesFor3584 = 4, kStagesFor5376 = 3;   // 4 x 46 KB + the x slots of the fused dot
   static constexpr int kDefaultCfg = 0;                 // 23 consumer warps (+1 producer = 6 warps per scheduler, 80 registers), 3 stages of 66 KB
+  static constexpr int kVar = 12;                       // spmvRowsPipeKernel VAR
   __device__ __forceinline__ void load(uint64_t j, uint32_t& c, double& v) const
   {
     c = ldStream(col + j);
@@ -725,6 +725,7 @@ struct CcrsAccess {
   template <typename P> P pipe() const { return P { entries }; }
   static constexpr uint32_t kStagesFor3584 = 3, kStagesFor5376 = 2;
   static constexpr int kDefaultCfg = 1;                 // 16 consumer warps, 3 stages of 59 KB (16-byte records)
+  static constexpr int kVar = 4;
   __device__ __forceinline__ void load(uint64_t j, uint32_t& c, double& v) const
   {
     const double2 e = ldStream2(reinterpret_cast<const double*>(entries + j));   // one 16-byte record
@@ -820,8 +821,8 @@ static bool tryRowsPipe(Access acc, const uint32_t* rowPtr, double avg, const do
     if (g) launchRowsPipe<LPRV, P, true, V>(acc.template pipe<P>(), rowPtr, x, y, lo, hi, tileRows, dot, g, s);      \
     else launchRowsPipe<LPRV, P, false, V>(acc.template pipe<P>(), rowPtr, x, y, lo, hi, tileRows, dot, nullptr, s); \
   } while (0)
-#define SB_PIPE(LPRV) SB_PIPE_V(LPRV, kRowsVar)
-  static const int var = envInt("SB_ROWS_VAR", kRowsVar);       // tuning knob for the 4-lanes-per-row case (the stencil)
+#define SB_PIPE(LPRV) SB_PIPE_V(LPRV, Access::kVar)
+  static const int var = envInt("SB_ROWS_VAR", Access::kVar);       // tuning knob for the 4-lanes-per-row case (the stencil)
   switch (lpr) {
   case 1: SB_PIPE(1); break;
   case 2: SB_PIPE(2); break;
