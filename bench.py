@@ -451,7 +451,7 @@ def main():
             traffic = json.load(open(tpath)).get(args.workload)
             if traffic is not None:
                 traffic_src = ("profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed "
-                               "`ncu --set full` capture of this kernel (profiles/r1_sell256_spmv_tma_lockstep.ncu.txt); a constant "
+                               "`ncu --set full` capture of this kernel (profiles/r2_sell256_spmv_and_vector_kernels.ncu.txt); a constant "
                                "read from file, NOT measured in this run")
         except Exception:
             traffic = None

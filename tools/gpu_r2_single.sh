@@ -4,7 +4,7 @@ set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 nproc >> gpurun_out/gpu.txt; free -g >> gpurun_out/gpu.txt
-timeout 1500 python -m pytest tests -m gpu -x -q --timeout 600 > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest.log; tail -3 gpurun_out/pytest.log
+timeout 1500 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest.log; tail -3 gpurun_out/pytest.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 SB_BENCH_VERBOSE=1 timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_sell256.json 2> gpurun_out/bench_sell256.err; echo "bench sell256 rc=$?"
 tail -c 600 gpurun_out/bench_sell256.err
