@@ -26,13 +26,31 @@
 extern "C" {
 #endif
 
-/* util.h:35-53 defines CG_UINT / CG_FLOAT as macros (UINT_TYPE=1, PRECISION=2); when the reference's util.h was
- * included first (a reference translation unit compiled against this header, see integration/), those are used */
+/* util.h:35-53: the reference's compile-time type switches. PRECISION=2 / UINT_TYPE=1 (double, unsigned int) are the
+ * defaults and what libsparsebench_b200.so is built with; the variant libraries libsparsebench_b200_f32.so
+ * (-DPRECISION=1), _u64.so (-DUINT_TYPE=2) and _f32u64.so are the same sources compiled with the other settings --
+ * compile the caller with the same -DPRECISION / -DUINT_TYPE and link the matching library. When the reference's util.h
+ * was included first (a reference translation unit compiled against this header, see integration/), its CG_UINT /
+ * CG_FLOAT macros are used. */
+#ifndef PRECISION
+#define PRECISION 2
+#endif
+#ifndef UINT_TYPE
+#define UINT_TYPE 1
+#endif
 #ifndef CG_UINT
+#if UINT_TYPE == 1
 typedef unsigned int CG_UINT;
+#else
+typedef unsigned long long int CG_UINT;
+#endif
 #endif
 #ifndef CG_FLOAT
+#if PRECISION == 1
+typedef float CG_FLOAT;
+#else
 typedef double CG_FLOAT;
+#endif
 #endif
 
 /* ---------------------------------------------------------------- data structures */

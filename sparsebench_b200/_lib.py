@@ -7,9 +7,12 @@ LIB_PATH = os.environ.get("SB_LIB") or os.path.join(HERE, "libsparsebench_b200.s
 _lib = None
 
 
-def load():
-    global _lib
+def load(variant=""):
+    """variant: "" (double / unsigned int), "f32", "u64", "f32u64" -- one per process"""
+    global _lib, LIB_PATH
     if _lib is None:
+        if variant and not os.environ.get("SB_LIB"):
+            LIB_PATH = os.path.join(HERE, "libsparsebench_b200_%s.so" % variant)
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(
                 "%s is missing: build it with `python -m sparsebench_b200.build` (nvcc, sm_100a). "
@@ -21,6 +24,6 @@ def load():
     return _lib
 
 
-def load_dropin(fmt):
-    load()
-    return C.CDLL(os.path.join(HERE, "libsparsebench_b200_%s.so" % fmt))
+def load_dropin(fmt, variant=""):
+    load(variant)
+    return C.CDLL(os.path.join(HERE, "libsparsebench_b200_%s%s.so" % (fmt, "_" + variant if variant else "")))

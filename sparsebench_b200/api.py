@@ -4,14 +4,26 @@ Same names, argument meaning and error behaviour as the reference's C functions 
 allocate.h, timing.h); numpy arrays stand in for host arrays, DeviceBuffer for what allocate() returns.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
 from ._lib import load
 
-U = C.c_uint32
+# The reference's compile-time type switches (util.h:35-53) select one of four builds of the library; this mirror
+# follows the environment variable SB_VARIANT ("" = double / unsigned int, "f32", "u64", "f32u64"), read at import.
+VARIANT = os.environ.get("SB_VARIANT", "")
+assert VARIANT in ("", "f32", "u64", "f32u64"), VARIANT
+F = C.c_float if "f32" in VARIANT else C.c_double          # CG_FLOAT
+U = C.c_uint64 if "u64" in VARIANT else C.c_uint32         # CG_UINT
+RDT = np.dtype(np.float32 if "f32" in VARIANT else np.float64)
+IDT = np.dtype(np.uint64 if "u64" in VARIANT else np.uint32)
 _HEAD = [("nr", U), ("nc", U), ("nnz", U), ("totalNr", U), ("totalNnz", U), ("startRow", U), ("stopRow", U)]
-ENTRY_DTYPE = np.dtype([("col", np.uint32), ("pad", np.uint32), ("val", np.float64)])   # matrix.h:24-27
+# matrix.h:24-27 `struct { CG_UINT col; CG_FLOAT val; }` with the C compiler's padding
+ENTRY_DTYPE = np.dtype({"": [("col", np.uint32), ("pad", np.uint32), ("val", np.float64)],
+                        "f32": [("col", np.uint32), ("val", np.float32)],
+                        "u64": [("col", np.uint64), ("val", np.float64)],
+                        "f32u64": [("col", np.uint64), ("val", np.float32), ("pad", np.uint32)]}[VARIANT])
 
 FMT_CRS, FMT_SCS, FMT_CCRS = 0, 1, 2
 FMT_NAMES = {FMT_CRS: "CRS", FMT_SCS: "SCS", FMT_CCRS: "CCRS"}
@@ -81,7 +93,7 @@ _configured = False
 
 def lib():
     global _configured
-    L = load()
+    L = load(VARIANT)
     if not _configured:
         L.allocate.restype = C.c_void_p
         L.allocate.argtypes = [C.c_size_t, C.c_size_t]
@@ -124,8 +136,8 @@ def lib():
         L.sbSpmvOrdered.restype = C.c_int
         L.sbSpmvDot.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.sbTrimPool.argtypes = []
-        L.waxpby.argtypes = [U, C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
-        L.ddot.argtypes = [U, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+        L.waxpby.argtypes = [U, F, C.c_void_p, F, C.c_void_p, C.c_void_p]
+        L.ddot.argtypes = [U, C.c_void_p, C.c_void_p, C.POINTER(F)]
         L.sbSolveCG.argtypes = [C.POINTER(Comm), C.POINTER(Parameter), C.c_void_p, C.c_int, C.POINTER(CGInfo)]
         L.sbSolveCG.restype = C.c_int
         L.sbCGCreate.argtypes = [C.POINTER(Comm), C.POINTER(Parameter), C.c_void_p, C.c_int, C.POINTER(CGInfo)]
@@ -138,7 +150,7 @@ def lib():
         L.commFinalize.argtypes = [C.POINTER(Comm)]
         L.commPartition.argtypes = [C.POINTER(Comm), C.POINTER(GMatrix)]
         L.commExchange.argtypes = [C.POINTER(Comm), U, C.c_void_p]
-        L.commReduction.argtypes = [C.POINTER(C.c_double), C.c_int]
+        L.commReduction.argtypes = [C.POINTER(F), C.c_int]
         L.sbCommGetUniqueId.argtypes = [C.c_void_p]
         L.sbCommInitRank.argtypes = [C.POINTER(Comm), C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.sbPartitionLocal.restype = C.c_void_p
@@ -178,7 +190,8 @@ class UnifiedBuffer(DeviceBuffer):
         self.nbytes = int(nbytes)
         self.ptr = lib().allocate(64, self.nbytes)
 
-    def host(self, dtype=np.float64):
+    def host(self, dtype=None):
+        dtype = RDT if dtype is None else dtype
         n = self.nbytes // np.dtype(dtype).itemsize
         return np.ctypeslib.as_array(C.cast(self.ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dtype))), (n,))
 
@@ -198,6 +211,11 @@ def to_device(a, slots=None):
     if a.nbytes:
         lib().sbCopyToDevice(buf.ptr, a.ctypes.data, a.nbytes)
     return buf
+
+
+def vec(a):
+    """numpy vector in the library's value type (CG_FLOAT)"""
+    return np.ascontiguousarray(a, RDT)
 
 
 def to_host(ptr, dtype, count):
@@ -256,7 +274,7 @@ def matrixRead(filename, comm=None):
 
 def gmatrix_from_csr(rowPtr, col, val, nc=None, startRow=0, totalNr=None):
     """Host GMatrix over numpy arrays (what MMMatrixRead + matrixConvertfromMM would hand over)."""
-    rowPtr = np.ascontiguousarray(rowPtr, np.uint32)
+    rowPtr = np.ascontiguousarray(rowPtr, IDT)
     e = np.zeros(max(len(col), 1), ENTRY_DTYPE)
     e["col"][:len(col)] = col
     e["val"][:len(col)] = val
@@ -274,12 +292,12 @@ def gmatrix_from_csr(rowPtr, col, val, nc=None, startRow=0, totalNr=None):
 def gmatrix_arrays(g):
     """(rowPtr, col, val) of a host or device GMatrix as numpy arrays."""
     if getattr(g, "_device", False):
-        rp = to_host(g.rowPtr, np.uint32, g.nr + 1)
+        rp = to_host(g.rowPtr, IDT, g.nr + 1)
         e = to_host(g.entries, ENTRY_DTYPE, int(rp[-1]))
     else:
-        rp = np.ctypeslib.as_array(C.cast(g.rowPtr, C.POINTER(C.c_uint32)), (g.nr + 1,)).copy()
+        rp = np.ctypeslib.as_array(C.cast(g.rowPtr, C.POINTER(U)), (g.nr + 1,)).copy()
         n = int(rp[-1])
-        e = np.frombuffer((C.c_char * (16 * max(n, 1))).from_address(g.entries), ENTRY_DTYPE, count=n)
+        e = np.frombuffer((C.c_char * (ENTRY_DTYPE.itemsize * max(n, 1))).from_address(g.entries), ENTRY_DTYPE, count=n)
     return rp, e["col"].copy(), e["val"].copy()
 
 
@@ -303,16 +321,16 @@ def spMVM(m, x, y):
 
 
 def crs_arrays(m):
-    rp = to_host(m.rowPtr, np.uint32, m.nr + 1)
+    rp = to_host(m.rowPtr, IDT, m.nr + 1)
     n = int(rp[-1])
-    return rp, to_host(m.colInd, np.uint32, n), to_host(m.val, np.float64, n)
+    return rp, to_host(m.colInd, IDT, n), to_host(m.val, RDT, n)
 
 
 def scs_arrays(m):
     return dict(C=m.C, sigma=m.sigma, nr=m.nr, nc=m.nc, nChunks=m.nChunks, nrPadded=m.nrPadded, nElems=m.nElems,
-                oldToNewPerm=to_host(m.oldToNewPerm, np.uint32, m.nr), newToOldPerm=to_host(m.newToOldPerm, np.uint32, m.nr),
-                chunkLens=to_host(m.chunkLens, np.uint32, m.nChunks), chunkPtr=to_host(m.chunkPtr, np.uint32, m.nChunks + 1),
-                colInd=to_host(m.colInd, np.uint32, m.nElems), val=to_host(m.val, np.float64, m.nElems))
+                oldToNewPerm=to_host(m.oldToNewPerm, IDT, m.nr), newToOldPerm=to_host(m.newToOldPerm, IDT, m.nr),
+                chunkLens=to_host(m.chunkLens, IDT, m.nChunks), chunkPtr=to_host(m.chunkPtr, IDT, m.nChunks + 1),
+                colInd=to_host(m.colInd, IDT, m.nElems), val=to_host(m.val, RDT, m.nElems))
 
 
 # ------------------------------------------------------------------ Krylov kernels (solver.c)
@@ -321,7 +339,7 @@ def waxpby(n, alpha, x, beta, y, w):
 
 
 def ddot(n, x, y):
-    r = C.c_double(0.0)
+    r = F(0.0)
     lib().ddot(n, x.ptr, y.ptr, C.byref(r))
     return r.value
 
@@ -344,14 +362,14 @@ def solveCG(m, itermax, eps, comm=None, generated=True, b=None, x=None, flags=CG
         if isinstance(b, DeviceBuffer):
             info.b = b.ptr
         else:
-            b = np.ascontiguousarray(b, np.float64); keep.append(b); info.b = b.ctypes.data
+            b = np.ascontiguousarray(b, RDT); keep.append(b); info.b = b.ctypes.data
     xo = None
     if x is not None or want_x:
         if isinstance(x, DeviceBuffer):
             info.x = x.ptr
             xo = x
         else:
-            xo = np.zeros(m.nr) if x is None else np.array(x, np.float64)
+            xo = np.zeros(m.nr, RDT) if x is None else np.array(x, RDT)
             info.x = xo.ctypes.data
     k = lib().sbSolveCG(C.byref(comm), C.byref(p), C.byref(m), m._fmt, C.byref(info))
     return k, hist[:info.nhist].copy(), xo, info

@@ -32,16 +32,39 @@ def _headers():
     return hs
 
 
-def build(force=False, verbose=False):
-    os.makedirs(OBJ, exist_ok=True)
+# The reference's compile-time type switches (util.h:35-53) as build variants of the same sources.
+VARIANTS = {
+    "": [],                                              # double, unsigned int: libsparsebench_b200.so (the graded configs)
+    "f32": ["-DPRECISION=1"],                            # float values
+    "u64": ["-DUINT_TYPE=2"],                            # unsigned long long indices
+    "f32u64": ["-DPRECISION=1", "-DUINT_TYPE=2"],
+}
+
+
+def lib_path(variant=""):
+    return os.path.join(HERE, "libsparsebench_b200%s.so" % ("_" + variant if variant else ""))
+
+
+def build(force=False, verbose=False, variants=None):
+    """builds the default library and (variants=None: all) the type variants; returns the default library's path"""
+    for v in (VARIANTS if variants is None else variants):
+        _build_one(v, force, verbose)
+    return LIB
+
+
+def _build_one(variant, force, verbose):
+    defs = VARIANTS[variant]
+    obj_dir = OBJ + ("_" + variant if variant else "")
+    lib = lib_path(variant)
+    os.makedirs(obj_dir, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs, procs = [], []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(OBJ, src.rsplit(".", 1)[0] + ".o")
+        o = os.path.join(obj_dir, src.rsplit(".", 1)[0] + ".o")
         objs.append(o)
         if force or _newer([s] + _headers(), o):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [nvcc] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:
@@ -50,18 +73,20 @@ def build(force=False, verbose=False):
             sys.stderr.write("---- %s\n%s\n" % (src, out))
         failed |= p.returncode != 0
     if failed:
-        raise RuntimeError("nvcc failed")
-    if force or procs or not os.path.exists(LIB):
-        subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs +
+        raise RuntimeError("nvcc failed (variant %r)" % variant)
+    if force or procs or not os.path.exists(lib):
+        subprocess.check_call([nvcc, "-shared", "-o", lib] + objs +
                               ["-Xlinker", "-Bsymbolic", "-lnccl", "-lpthread", "-cudart", "static"])
+    suffix = "_" + variant if variant else ""
     for fmt in ("CRS", "SCS", "CCRS"):
-        shim = os.path.join(HERE, "libsparsebench_b200_%s.so" % fmt)
+        shim = os.path.join(HERE, "libsparsebench_b200_%s%s.so" % (fmt, suffix))
         src = os.path.join(CSRC, "dropin.c")
-        if force or _newer([src, LIB] + _headers(), shim):
-            subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-D" + fmt, "-I" + os.path.join(ROOT, "include"), src,
-                                   "-o", shim, "-L" + HERE, "-lsparsebench_b200", "-Wl,-rpath,$ORIGIN"])
-    return LIB
+        if force or _newer([src, lib] + _headers(), shim):
+            subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-D" + fmt] + defs + ["-I" + os.path.join(ROOT, "include"), src,
+                                   "-o", shim, "-L" + HERE, "-lsparsebench_b200" + suffix, "-Wl,-rpath,$ORIGIN"])
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variants=[("" if v == "default" else v) for v in only] or None))

@@ -39,15 +39,16 @@ struct CgSolver {
   const int* elems = nullptr;              // multi-GPU send list in solver numbering (owned by the Comm)
   bool pBorrowed = false;                  // p is the Comm's persistent, peer-mapped halo vector
   unsigned long long* syncTrace = nullptr; // SB_SYNC_TRACE=1: device counters of the waits inside the multi-GPU kernels
-  uint32_t intLo = 0, intHi = 0;           // SpMV units [intLo, intHi) reference no halo column
-  uint32_t n = 0;
+  idx_t intLo = 0, intHi = 0;           // SpMV units [intLo, intHi) reference no halo column
+  idx_t n = 0;
   size_t rowSlots = 0, colSlots = 0;
   // vectors (CGSolver.c:69-79), solver order (SELL: permuted)
-  double *r = nullptr, *p = nullptr, *Ap = nullptr, *x = nullptr, *b = nullptr, *tmp = nullptr;
-  double *rho = nullptr, *pAp = nullptr;   // device scalars indexed by iteration: rho[j] = r_j.r_j, pAp[k] = p_k.Ap_k
-  double* hRho = nullptr;                  // mapped pinned mirror of rho: written by the kernels themselves, polled by the host
+  real_t *r = nullptr, *p = nullptr, *Ap = nullptr, *x = nullptr, *b = nullptr, *tmp = nullptr;
+  real_t *rho = nullptr, *pAp = nullptr;   // device scalars indexed by iteration: rho[j] = r_j.r_j, pAp[k] = p_k.Ap_k
+  real_t* hRho = nullptr;                  // mapped pinned mirror of rho: written by the kernels themselves, polled by the host
   std::vector<double> hist;
-  double normr = 0.0, rtrans = 0.0, oldrtrans = 0.0;
+  double normr = 0.0;                      // printed / compared in double like the reference's sqrt() result
+  real_t rtrans = 0.0, oldrtrans = 0.0;
   int k = 1;
   bool stopped = false;
   // optional per-kernel event timing: a fixed pool of events created in setup(), drained into regionMs whenever
@@ -83,20 +84,20 @@ struct CgSolver {
 
   // Blocks until the device has published the global rho[j]. No copy and no event sits in the stream for this: the
   // kernel that completes the sum stores it into mapped host memory (gridSum's mirror / the p update's collect).
-  double waitRho(int j)
+  static bool rhoPending(real_t v)
   {
-    volatile unsigned long long* slot = reinterpret_cast<volatile unsigned long long*>(hRho + j);
+    return memcmp(&v, &kRhoPending, sizeof(real_t)) == 0;     // all-ones: a NaN pattern no arithmetic produces
+  }
+  real_t waitRho(int j)
+  {
+    volatile real_t* slot = hRho + j;
     for (unsigned long spins = 1;; spins++) {
-      const unsigned long long bits = *slot;
-      if (bits != kRhoPending) {
-        double v;
-        memcpy(&v, &bits, sizeof(v));
-        return v;
-      }
+      const real_t v = *slot;
+      if (!rhoPending(v)) return v;
       if ((spins & 0x3fff) == 0) {             // a failed or finished stream must not leave the host spinning
         const cudaError_t e = cudaStreamQuery(s);
         if (e == cudaSuccess) {
-          if (*slot == kRhoPending) SB_FATAL("CG: the stream drained but rho[%d] never arrived", j);
+          if (rhoPending(*slot)) SB_FATAL("CG: the stream drained but rho[%d] never arrived", j);
         } else if (e != cudaErrorNotReady) {
           SB_CUDA(e);
         }
@@ -104,7 +105,7 @@ struct CgSolver {
     }
   }
 
-  void allreduce(double* d, int op)
+  void allreduce(real_t* d, int op)
   {
     if (!commActive(comm)) return;
     commAllreduceDevice(comm, d, 1, op, s);
@@ -116,7 +117,7 @@ struct CgSolver {
   // column while those stores are in flight, waits on the arrival counters, and finishes with the boundary rows.
   void spmvWithHalo(const DotArgs* dot, const HaloGate* already = nullptr)
   {
-    const uint32_t units = spmvUnits(A);
+    const idx_t units = spmvUnits(A);
     if (commActive(comm)) {
       if (gated) {
         // `already`: the p update itself delivered the halo (FusedPut); otherwise a put kernel does
@@ -135,15 +136,15 @@ struct CgSolver {
 
   // caller vector (host or device, original row order) -> device vector in solver order, on stream `st`;
   // `stage` receives a host vector that still has to be permuted
-  void importVector(const double* src, double* dst, double* stage, cudaStream_t st)
+  void importVector(const real_t* src, real_t* dst, real_t* stage, cudaStream_t st)
   {
-    const size_t bytes = sizeof(double) * n;
+    const size_t bytes = sizeof(real_t) * n;
     const bool dev = isDevicePointer(src);
     if (dev) ensureOnDevice(src);
     if (!A.oldToNew) {
       SB_CUDA(cudaMemcpyAsync(dst, src, bytes, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
     } else {
-      const double* staged = src;
+      const real_t* staged = src;
       if (!dev) {
         SB_CUDA(cudaMemcpyAsync(stage, src, bytes, cudaMemcpyHostToDevice, st));
         staged = stage;
@@ -152,9 +153,9 @@ struct CgSolver {
     }
   }
 
-  void exportVector(const double* src, double* dst)
+  void exportVector(const real_t* src, real_t* dst)
   {
-    const size_t bytes = sizeof(double) * n;
+    const size_t bytes = sizeof(real_t) * n;
     const bool dev = isDevicePointer(dst);
     if (!A.oldToNew) {
       SB_CUDA(cudaMemcpyAsync(dst, src, bytes, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
@@ -177,7 +178,7 @@ struct CgSolver {
     comm = comm_;
     A = A_;
     s = c.stream;
-    eps = param->eps;
+    eps = (double)(real_t)param->eps;                         // CG_FLOAT eps = (CG_FLOAT)param->eps, CGSolver.c:64
     itermax = param->itermax;
     flags = info ? info->flags : (SB_CG_FUSED | SB_CG_PRINT);
     fused = (flags & SB_CG_FUSED) != 0;
@@ -208,21 +209,21 @@ struct CgSolver {
         fusedPut = fusedReduce && getenv("SB_NO_FUSED_PUT") == nullptr && commPrepareFusedPut(comm, A.permKey, elems);
       }
     }
-    r = (double*)sbAllocateDevice(64, sizeof(double) * rowSlots);
+    r = (real_t*)sbAllocateDevice(64, sizeof(real_t) * rowSlots);
     if (!p) {
-      p = (double*)sbAllocateDevice(64, sizeof(double) * colSlots);
-      SB_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * colSlots, s));
+      p = (real_t*)sbAllocateDevice(64, sizeof(real_t) * colSlots);
+      SB_CUDA(cudaMemsetAsync(p, 0, sizeof(real_t) * colSlots, s));
     }
-    Ap = (double*)sbAllocateDevice(64, sizeof(double) * rowSlots);
-    x = (double*)sbAllocateDevice(64, sizeof(double) * rowSlots);
-    b = (double*)sbAllocateDevice(64, sizeof(double) * rowSlots);
-    tmp = (double*)sbAllocateDevice(64, sizeof(double) * rowSlots);
-    rho = (double*)sbAllocateDevice(64, sizeof(double) * nScal);
-    pAp = (double*)sbAllocateDevice(64, sizeof(double) * nScal);
-    hRho = (double*)sbAllocateHost(sizeof(double) * nScal);
-    SB_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * rowSlots, s));
-    SB_CUDA(cudaMemsetAsync(rho, 0, sizeof(double) * nScal, s));
-    SB_CUDA(cudaMemsetAsync(pAp, 0, sizeof(double) * nScal, s));
+    Ap = (real_t*)sbAllocateDevice(64, sizeof(real_t) * rowSlots);
+    x = (real_t*)sbAllocateDevice(64, sizeof(real_t) * rowSlots);
+    b = (real_t*)sbAllocateDevice(64, sizeof(real_t) * rowSlots);
+    tmp = (real_t*)sbAllocateDevice(64, sizeof(real_t) * rowSlots);
+    rho = (real_t*)sbAllocateDevice(64, sizeof(real_t) * nScal);
+    pAp = (real_t*)sbAllocateDevice(64, sizeof(real_t) * nScal);
+    hRho = (real_t*)sbAllocateHost(sizeof(real_t) * nScal);
+    SB_CUDA(cudaMemsetAsync(x, 0, sizeof(real_t) * rowSlots, s));
+    SB_CUDA(cudaMemsetAsync(rho, 0, sizeof(real_t) * nScal, s));
+    SB_CUDA(cudaMemsetAsync(pAp, 0, sizeof(real_t) * nScal, s));
     if (profile) {
       evPool.resize(kProfEvents);
       for (cudaEvent_t& e : evPool) SB_CUDA(cudaEventCreate(&e));
@@ -260,11 +261,11 @@ struct CgSolver {
     launchWaxpby(n, 1.0, b, -1.0, Ap, r, s);
     launchDot(n, r, r, rho, 0, s);
     allreduce(rho, SB_SUM);
-    SB_CUDA(cudaMemcpyAsync(hRho, rho, sizeof(double), cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaMemcpyAsync(hRho, rho, sizeof(real_t), cudaMemcpyDeviceToHost, s));
     SB_CUDA(cudaStreamSynchronize(s));
     rtrans = hRho[0];
-    for (int j = 1; j < nScal; j++) memcpy(hRho + j, &kRhoPending, sizeof(double));
-    normr = sqrt(rtrans);
+    for (int j = 1; j < nScal; j++) memcpy(hRho + j, &kRhoPending, sizeof(real_t));
+    normr = (double)(real_t)sqrt((double)rtrans);             // CG_FLOAT normr = sqrt(rtrans), CGSolver.c:100
     hist.push_back(normr);
     if (print) printf("Initial Residual = %E\n", normr);      // :102
     printFreq = itermax / 10;                                 // :85-91
@@ -287,7 +288,7 @@ struct CgSolver {
       // the normr tested before iteration k is sqrt(rho[max(k-2,0)]) -- the reference's lagging test (:107,:116)
       for (; k < stopK; k++) {
         if ((int)hist.size() < k) {                            // hist[k-1] = normr of iteration k-1 = sqrt(rho[k-2])
-          if (k >= 3) normr = sqrt(waitRho(k - 2));
+          if (k >= 3) normr = (double)(real_t)sqrt((double)waitRho(k - 2));
           hist.push_back(normr);
           printIteration(k - 1, normr);
         }
@@ -327,7 +328,7 @@ struct CgSolver {
         mark(R_UPDATE_XR);
         if (commActive(comm)) {
           allreduce(rho + k, SB_SUM);
-          SB_CUDA(cudaMemcpyAsync(hRho + k, rho + k, sizeof(double), cudaMemcpyDeviceToHost, s));
+          SB_CUDA(cudaMemcpyAsync(hRho + k, rho + k, sizeof(real_t), cudaMemcpyDeviceToHost, s));
         }
       }
     } else {
@@ -342,14 +343,14 @@ struct CgSolver {
         } else {
           oldrtrans = rtrans;
           ddot(n, r, r, &rtrans);
-          const double beta = rtrans / oldrtrans;
+          const real_t beta = rtrans / oldrtrans;
           launchWaxpby(n, 1.0, r, beta, p, p, s);
         }
-        normr = sqrt(rtrans);
+        normr = (double)(real_t)sqrt((double)rtrans);
         hist.push_back(normr);
         printIteration(k, normr);
         spmvWithHalo(nullptr);
-        double alpha = 0.0;
+        real_t alpha = 0.0;
         ddot(n, p, Ap, &alpha);
         alpha = rtrans / alpha;
         launchWaxpby(n, 1.0, x, alpha, p, x, s);
@@ -375,18 +376,19 @@ struct CgSolver {
     }
     if (fused && (int)hist.size() < k) {
       // iteration k-1 was the last one executed; record its normr = sqrt(rho[k-2])
-      const double last = k >= 3 ? sqrt(hRho[k - 2]) : normr;
+      const double last = k >= 3 ? (double)(real_t)sqrt((double)hRho[k - 2]) : normr;
       hist.push_back(last);
       printIteration(k - 1, last);
     }
     if (print) printf("Solution performed %d iterations and took %.2fs\n", k, loopMs * 1e-3);   // :133
     double maxErr = -1.0;
     if (generated) {                                           // solverCheckResidual, :40-60
-      launchMaxErr(n, x, c.dScalar + 8, s);
-      SB_CUDA(cudaMemcpyAsync(c.hScalar + 8, c.dScalar + 8, sizeof(double), cudaMemcpyDeviceToHost, s));
+      launchMaxErr(n, x, c.dWide, s);
+      SB_CUDA(cudaMemcpyAsync(c.hWide, c.dWide, sizeof(double), cudaMemcpyDeviceToHost, s));
       SB_CUDA(cudaStreamSynchronize(s));
-      maxErr = c.hScalar[8];
-      commReduction(&maxErr, SB_MAX);
+      CG_FLOAT worst = (CG_FLOAT)c.hWide[0];                     // CG_FLOAT residual, CGSolver.c:46-55
+      commReduction(&worst, SB_MAX);
+      maxErr = (double)worst;
       if (print) printf("Difference between computed and exact  = %f\n", maxErr);
     }
     if (info) {

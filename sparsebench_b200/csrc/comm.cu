@@ -29,6 +29,8 @@
     }                                                                                            \
   } while (0)
 
+static const ncclDataType_t kNcclReal = sizeof(real_t) == 8 ? ncclDouble : ncclFloat;
+
 struct SbPartitionPlan {
   sb::PartitionPlan plan;
 };
@@ -39,7 +41,7 @@ namespace sb {
 // Inside one NVSwitch box every GPU can store straight into every other GPU's memory. Each rank owns two
 // windows that its peers map through CUDA IPC:
 //   control window : halo arrival / acknowledge counters and the slots of the scalar all-reduce
-//   halo window    : two receive slots (double buffering by exchange parity) of externalCount doubles, laid
+//   halo window    : two receive slots (double buffering by exchange parity) of externalCount values, laid
 //                    out like the halo part of x (grouped by source in rdispls order)
 // Halo exchange = the SENDER's kernel gathers x[elementsToSend[i]] and stores the values directly into the
 // receivers' slots over NVLink, then publishes the exchange number (release, system scope); the receiver's
@@ -52,7 +54,7 @@ namespace sb {
 struct PutPlan {
   int ndest;
   int sdispl[kMaxRanks + 1];                           // element offsets per destination (comm.c:150)
-  double* remote[2][kMaxRanks];                        // destination slot (per parity), already offset to my segment
+  real_t* remote[2][kMaxRanks];                        // destination slot (per parity), already offset to my segment
   unsigned long long* remoteFlag[kMaxRanks];           // &destCtrl->haloFlag[myRank]
   const unsigned long long* ack[kMaxRanks];            // &myCtrl->haloAck[destRank]
 };
@@ -62,7 +64,7 @@ struct WaitPlan {
   int externalCount;
   const unsigned long long* flag[kMaxRanks];           // &myCtrl->haloFlag[sourceRank]
   unsigned long long* remoteAck[kMaxRanks];            // &sourceCtrl->haloAck[myRank]
-  const double* slot[2];
+  const real_t* slot[2];
 };
 
 enum { COMM_NCCL = 0, COMM_PEER = 1 };
@@ -72,26 +74,26 @@ struct CommExt {
   int rank = 0, size = 1;
   int mode = COMM_NCCL;
   int* dElementsToSend = nullptr;
-  double* dScalar = nullptr;      // staging for host-scalar reductions
-  double* hScalar = nullptr;
+  real_t* dScalar = nullptr;      // staging for host-scalar reductions
+  real_t* hScalar = nullptr;
   std::vector<int> wantMatrix;    // [requester][owner] halo counts of the current partition
   bool installed = false;         // device lists / windows match the Comm lists
   // peer mode
   CtrlWindow* ctrl = nullptr;
   std::vector<CtrlWindow*> peerCtrl;
   CtrlWindow** dPeerCtrl = nullptr;
-  double* halo = nullptr;
-  std::vector<double*> peerHalo;
+  real_t* halo = nullptr;
+  std::vector<real_t*> peerHalo;
   PutPlan* dPut = nullptr;
   WaitPlan* dWait = nullptr;
   unsigned long long haloSeq = 0, redEpoch = 0;
   // persistent halo vector (the CG's p): allocated, zeroed and mapped by every peer ONCE per partition
   // (commAcquireHaloVector); solves only borrow it, the arrival counters keep running across solves
-  double* arena = nullptr;
+  real_t* arena = nullptr;
   size_t arenaSlots = 0;
-  uint32_t arenaRows = 0;
+  idx_t arenaRows = 0;
   bool arenaBusy = false;
-  std::vector<double*> peerVec;
+  std::vector<real_t*> peerVec;
   PutPlan putDirect;               // host copy of *dPutDirect
   PutPlan* dPutDirect = nullptr;
   unsigned long long directSeq = 0;
@@ -144,8 +146,8 @@ static void allGatherInts(CommExt* e, const int* mine, int count, int* all)
 static void ncclBarrier(CommExt* e)
 {
   Context& c = ctx();
-  SB_CUDA(cudaMemsetAsync(e->dScalar + 4, 0, sizeof(double), c.stream));
-  SB_NCCL(ncclAllReduce(e->dScalar + 4, e->dScalar + 4, 1, ncclDouble, ncclSum, e->nccl, c.stream));
+  SB_CUDA(cudaMemsetAsync(e->dScalar + 4, 0, sizeof(real_t), c.stream));
+  SB_NCCL(ncclAllReduce(e->dScalar + 4, e->dScalar + 4, 1, kNcclReal, ncclSum, e->nccl, c.stream));
   SB_CUDA(cudaStreamSynchronize(c.stream));
 }
 
@@ -206,8 +208,8 @@ static void attach(Comm* c, int rank, int size, int device, const ncclUniqueId* 
   e->rank = rank;
   e->size = size;
   SB_NCCL(ncclCommInitRank(&e->nccl, size, *id, rank));
-  e->dScalar = (double*)sbAllocateDevice(64, sizeof(double) * 8);
-  e->hScalar = (double*)sbAllocateHost(sizeof(double) * 8);
+  e->dScalar = (real_t*)sbAllocateDevice(64, sizeof(real_t) * 8);
+  e->hScalar = (real_t*)sbAllocateHost(sizeof(real_t) * 8);
   c->communicator = e;
   g_world = e;
   // SB_COMM=nccl keeps every exchange on NCCL (the measured baseline); default: NVLink peer windows
@@ -284,7 +286,7 @@ static void tcpBroadcastId(int rank, int size, ncclUniqueId* id)
 }
 
 // ---- kernels
-__global__ void packKernel(int n, const int* __restrict__ elements, const double* __restrict__ x, double* __restrict__ out)
+__global__ void packKernel(int n, const int* __restrict__ elements, const real_t* __restrict__ x, real_t* __restrict__ out)
 {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = x[elements[i]];   // comm.c:635-638
 }
@@ -321,7 +323,7 @@ __device__ __forceinline__ void signalAddSys(unsigned long long* p, unsigned lon
 }
 
 __global__ void __launch_bounds__(kHaloThreads)
-haloPutKernel(const PutPlan* __restrict__ plan, const int* __restrict__ elements, const double* __restrict__ x,
+haloPutKernel(const PutPlan* __restrict__ plan, const int* __restrict__ elements, const real_t* __restrict__ x,
     unsigned long long seq, bool direct)
 {
   __shared__ unsigned int stored[kMaxRanks];            // direct mode: elements this block delivered per destination
@@ -335,7 +337,7 @@ haloPutKernel(const PutPlan* __restrict__ plan, const int* __restrict__ elements
   const int stride = gridDim.x * blockDim.x;
   for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {   // 4 independent gathers in flight
     int idx[4];
-    double v[4];
+    real_t v[4];
 #pragma unroll
     for (int u = 0; u < 4; u++)
       if (i0 + u * stride < total) idx[u] = elements[i0 + u * stride];
@@ -363,16 +365,16 @@ haloPutKernel(const PutPlan* __restrict__ plan, const int* __restrict__ elements
 
 // Receiver side: wait for every source's `seq`, copy the slot behind the local part of x, acknowledge.
 __global__ void __launch_bounds__(kHaloThreads)
-haloWaitKernel(const WaitPlan* __restrict__ plan, double* __restrict__ xHalo, unsigned long long seq)
+haloWaitKernel(const WaitPlan* __restrict__ plan, real_t* __restrict__ xHalo, unsigned long long seq)
 {
   const int ns = plan->nsrc;
   if ((int)threadIdx.x < ns) spinUntilAtLeast(plan->flag[threadIdx.x], seq * kPutBlocks);
   __syncthreads();
-  const double* src = plan->slot[seq & 1ull];
+  const real_t* src = plan->slot[seq & 1ull];
   const int n = plan->externalCount;
   const int stride = gridDim.x * blockDim.x;
   for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
-    double v[4];
+    real_t v[4];
 #pragma unroll
     for (int u = 0; u < 4; u++)
       if (i0 + u * stride < n) v[u] = __ldcg(src + i0 + u * stride);
@@ -384,46 +386,46 @@ haloWaitKernel(const WaitPlan* __restrict__ plan, double* __restrict__ xHalo, un
   if ((int)threadIdx.x < ns) signalAddSys(plan->remoteAck[threadIdx.x]);   // release: ordered after this block's reads
 }
 
-// All-reduce of one double over the peer windows (replaces MPI_Allreduce of comm.c:657,659).
+// All-reduce of one value over the peer windows (replaces MPI_Allreduce of comm.c:657,659).
 __global__ void __launch_bounds__(kMaxRanks)
 peerAllreduceKernel(CtrlWindow* mine, CtrlWindow* const* __restrict__ peers, int rank, int size, unsigned long long epoch,
-    double* d, int op)
+    real_t* d, int op)
 {
-  __shared__ double vals[kMaxRanks];
+  __shared__ real_t vals[kMaxRanks];
   const int t = threadIdx.x;
   const int slot = (int)(epoch % kRedDepth);
   if (t < size) {
-    const double v = *d;
+    const real_t v = *d;
     CtrlWindow* w = peers[t];
-    *(volatile double*)&w->redVal[slot][rank] = v;
+    *(volatile double*)&w->redVal[slot][rank] = (double)v;   // the window's slots are doubles in every build
     __threadfence_system();
     stReleaseSys(&w->redFlag[slot][rank], epoch);
     spinUntilAtLeast(&mine->redFlag[slot][t], epoch);
-    vals[t] = *(volatile double*)&mine->redVal[slot][t];
+    vals[t] = (real_t) * (volatile double*)&mine->redVal[slot][t];
   }
   __syncthreads();
   if (t == 0) {
-    double acc = vals[0];
+    real_t acc = vals[0];
     for (int r = 1; r < size; r++) acc = (op == SB_MAX) ? (vals[r] > acc ? vals[r] : acc) : acc + vals[r];   // rank order: same bits on every rank
     *d = acc;
   }
 }
 
-__global__ void flagExternalKernel(uint64_t n, const Entry* __restrict__ e, uint32_t startRow, uint32_t stopRow,
-    unsigned char* __restrict__ flag, uint32_t* __restrict__ col)
+__global__ void flagExternalKernel(uint64_t n, const Entry* __restrict__ e, idx_t startRow, idx_t stopRow,
+    unsigned char* __restrict__ flag, idx_t* __restrict__ col)
 {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t c = e[i].col;
+    const idx_t c = e[i].col;
     col[i] = c;
     flag[i] = (c < startRow || c > stopRow) ? 1 : 0;       // comm.c:457 (stopRow inclusive)
   }
 }
 
-__global__ void renumberKernel(uint64_t n, Entry* __restrict__ e, uint32_t startRow, uint32_t stopRow, int nExt,
-    const uint32_t* __restrict__ sortedGlobal, const uint32_t* __restrict__ sortedLocal)
+__global__ void renumberKernel(uint64_t n, Entry* __restrict__ e, idx_t startRow, idx_t stopRow, int nExt,
+    const idx_t* __restrict__ sortedGlobal, const idx_t* __restrict__ sortedLocal)
 {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t c = e[i].col;
+    const idx_t c = e[i].col;
     if (c >= startRow && c <= stopRow) {
       e[i].col = c - startRow;                             // comm.c:100-101
     } else {
@@ -479,13 +481,13 @@ static void installPartition(Comm* c)
     if ((int)e->wantMatrix.size() != size * size) SB_FATAL("commPartition: missing halo count matrix");
     const int* W = e->wantMatrix.data();
     const size_t ext0 = (size_t)c->externalCount;
-    e->halo = (double*)sbAllocateDevice(256, sizeof(double) * (2 * ext0 + 2));
-    SB_CUDA(cudaMemset(e->halo, 0, sizeof(double) * (2 * ext0 + 2)));
+    e->halo = (real_t*)sbAllocateDevice(256, sizeof(real_t) * (2 * ext0 + 2));
+    SB_CUDA(cudaMemset(e->halo, 0, sizeof(real_t) * (2 * ext0 + 2)));
     SB_CUDA(cudaDeviceSynchronize());
     std::vector<void*> peers;
     if (!mapPeers(e, e->halo, peers)) SB_FATAL("commPartition: CUDA IPC mapping of the halo windows failed");
     e->peerHalo.resize((size_t)size);
-    for (int r = 0; r < size; r++) e->peerHalo[(size_t)r] = (double*)peers[(size_t)r];
+    for (int r = 0; r < size; r++) e->peerHalo[(size_t)r] = (real_t*)peers[(size_t)r];
     PutPlan put;
     memset(&put, 0, sizeof(put));
     put.ndest = c->outdegree;
@@ -537,7 +539,7 @@ bool commPeerMode(const Comm* c)
 }
 
 // First half of an exchange: after this call the neighbours' copies of my boundary values are on their way.
-void commHaloPut(Comm* c, const double* x, const int* elements, cudaStream_t s)
+void commHaloPut(Comm* c, const real_t* x, const int* elements, cudaStream_t s)
 {
   CommExt* e = ext(c);
   if (!e || (c->indegree == 0 && c->outdegree == 0)) return;
@@ -552,7 +554,7 @@ void commHaloPut(Comm* c, const double* x, const int* elements, cudaStream_t s)
 }
 
 // Second half: x[numRows .. numRows+externalCount) holds the neighbours' values when this kernel has run.
-void commHaloWait(Comm* c, uint32_t numRows, double* x, cudaStream_t s)
+void commHaloWait(Comm* c, idx_t numRows, real_t* x, cudaStream_t s)
 {
   CommExt* e = ext(c);
   if (!e || (c->indegree == 0 && c->outdegree == 0)) return;
@@ -563,17 +565,17 @@ void commHaloWait(Comm* c, uint32_t numRows, double* x, cudaStream_t s)
   }
 }
 
-// All-reduce of one host double over the ranks of `e` (the body of commReduction).
-static void hostAllreduce(CommExt* e, double* v, int op)
+// All-reduce of one host scalar over the ranks of `e` (the body of commReduction).
+static void hostAllreduce(CommExt* e, real_t* v, int op)
 {
   Context& c = ctx();
   e->hScalar[0] = *v;
-  SB_CUDA(cudaMemcpyAsync(e->dScalar, e->hScalar, sizeof(double), cudaMemcpyHostToDevice, c.stream));
+  SB_CUDA(cudaMemcpyAsync(e->dScalar, e->hScalar, sizeof(real_t), cudaMemcpyHostToDevice, c.stream));
   Comm tmp;
   memset(&tmp, 0, sizeof(tmp));
   tmp.communicator = e;
   commAllreduceDevice(&tmp, e->dScalar, 1, op, c.stream);
-  SB_CUDA(cudaMemcpyAsync(e->hScalar, e->dScalar, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  SB_CUDA(cudaMemcpyAsync(e->hScalar, e->dScalar, sizeof(real_t), cudaMemcpyDeviceToHost, c.stream));
   SB_CUDA(cudaStreamSynchronize(c.stream));
   *v = e->hScalar[0];
 }
@@ -609,13 +611,13 @@ static void releaseArena(Comm* c)
 
 // Collective. Allocates the persistent halo vector, lets every peer map it and builds the put plan: my boundary
 // values go straight behind destination d's local rows, at d's rdispl for me (comm.c:135).
-static bool registerArena(Comm* c, size_t slots, uint32_t numRows)
+static bool registerArena(Comm* c, size_t slots, idx_t numRows)
 {
   CommExt* e = ext(c);
   releaseArena(c);
   const int size = e->size, rank = e->rank;
-  e->arena = (double*)sbAllocateDevice(256, sizeof(double) * slots);
-  SB_CUDA(cudaMemset(e->arena, 0, sizeof(double) * slots));
+  e->arena = (real_t*)sbAllocateDevice(256, sizeof(real_t) * slots);
+  SB_CUDA(cudaMemset(e->arena, 0, sizeof(real_t) * slots));
   SB_CUDA(cudaDeviceSynchronize());
   std::vector<void*> peers;
   if (!mapPeers(e, e->arena, peers)) {
@@ -626,7 +628,7 @@ static bool registerArena(Comm* c, size_t slots, uint32_t numRows)
   e->arenaSlots = slots;
   e->arenaRows = numRows;
   e->peerVec.resize((size_t)size);
-  for (int r = 0; r < size; r++) e->peerVec[(size_t)r] = (double*)peers[(size_t)r];
+  for (int r = 0; r < size; r++) e->peerVec[(size_t)r] = (real_t*)peers[(size_t)r];
   std::vector<int> rows((size_t)size);
   int mine = (int)numRows;
   allGatherInts(e, &mine, 1, rows.data());
@@ -660,7 +662,7 @@ static bool registerArena(Comm* c, size_t slots, uint32_t numRows)
 // Why the halo part may be reused from solve to solve without any further synchronisation: a rank can only start
 // storing the next solve's first halo after it has collected the previous solve's last p.Ap, i.e. after every
 // rank's last SpMV -- the only reader of the halo -- has completed. The caller must not clear slots >= numRows.
-double* commAcquireHaloVector(Comm* c, uint32_t numRows, size_t slots, bool localOk)
+real_t* commAcquireHaloVector(Comm* c, idx_t numRows, size_t slots, bool localOk)
 {
   CommExt* e = ext(c);
   if (!e || e->mode != COMM_PEER) return nullptr;
@@ -668,7 +670,7 @@ double* commAcquireHaloVector(Comm* c, uint32_t numRows, size_t slots, bool loca
   if (e->arenaBusy) SB_FATAL("commAcquireHaloVector: the halo vector is in use by another solver");
   const bool fits = e->arena && e->arenaSlots >= slots && e->arenaRows == numRows;
   const bool ok = localOk && c->indegree <= kMaxGateSources;
-  double v = (ok ? 1.0 : 0.0) + (fits ? 0.0 : 1024.0);       // both collective decisions in one sum
+  real_t v = (ok ? 1.0 : 0.0) + (fits ? 0.0 : 1024.0);       // both collective decisions in one sum
   hostAllreduce(e, &v, SB_SUM);
   const long long sum = (long long)(v + 0.5);
   if (sum % 1024 != e->size) return nullptr;
@@ -685,7 +687,7 @@ void commReleaseHaloVector(Comm* c)
 
 // Send list in the solver's row numbering: the CG keeps SELL vectors in permuted order, so it sends
 // p[oldToNew[element]]. Cached per permutation (`key`: unique id of the converted matrix, 0 = no permutation).
-const int* commSolverElements(Comm* c, uint64_t key, const uint32_t* oldToNew, cudaStream_t s)
+const int* commSolverElements(Comm* c, uint64_t key, const idx_t* oldToNew, cudaStream_t s)
 {
   CommExt* e = ext(c);
   if (!e) return nullptr;
@@ -693,7 +695,7 @@ const int* commSolverElements(Comm* c, uint64_t key, const uint32_t* oldToNew, c
   if (key == 0 || !oldToNew || c->totalSendCount == 0) return e->dElementsToSend;
   if (e->dElemsSolver && e->elemsKey == key) return e->dElemsSolver;
   if (!e->dElemsSolver) e->dElemsSolver = (int*)sbAllocateDevice(64, sizeof(int) * (size_t)c->totalSendCount);
-  launchPermuteIndices((uint32_t)c->totalSendCount, oldToNew, e->dElementsToSend, e->dElemsSolver, s);
+  launchPermuteIndices((idx_t)c->totalSendCount, oldToNew, e->dElementsToSend, e->dElemsSolver, s);
   e->elemsKey = key;
   return e->dElemsSolver;
 }
@@ -724,8 +726,8 @@ bool commPrepareFusedPut(Comm* c, uint64_t key, const int* elements)
       int* dInv = (int*)sbAllocateDevice(64, sizeof(int) * inv.size());
       sbCopyToDevice(dInv, inv.data(), sizeof(int) * inv.size());
       e->fusedInv.push_back(dInv);
-      e->fused.lo[i] = (uint32_t)lo;
-      e->fused.hi[i] = (uint32_t)hi;
+      e->fused.lo[i] = (idx_t)lo;
+      e->fused.hi[i] = (idx_t)hi;
       e->fused.inv[i] = dInv;
       e->fused.remote[i] = e->putDirect.remote[0][i];
       e->fused.remoteFlag[i] = e->putDirect.remoteFlag[i];
@@ -747,7 +749,7 @@ static HaloGate directGate(Comm* c, CommExt* e)
   return g;
 }
 
-HaloGate commHaloPutDirect(Comm* c, const double* x, const int* elements, cudaStream_t s)
+HaloGate commHaloPutDirect(Comm* c, const real_t* x, const int* elements, cudaStream_t s)
 {
   CommExt* e = ext(c);
   if (!e || !e->arenaBusy || x != e->arena) SB_FATAL("commHaloPutDirect: not the registered halo vector");
@@ -771,7 +773,7 @@ HaloGate commFusedPutBegin(Comm* c, FusedPut* fp)
   return directGate(c, e);
 }
 
-void commExchangeOnStream(Comm* c, uint32_t numRows, double* x, const int* elements, cudaStream_t s)
+void commExchangeOnStream(Comm* c, idx_t numRows, real_t* x, const int* elements, cudaStream_t s)
 {
   CommExt* e = ext(c);
   if (!e || (c->indegree == 0 && c->outdegree == 0)) return;
@@ -792,13 +794,13 @@ void commExchangeOnStream(Comm* c, uint32_t numRows, double* x, const int* eleme
   // MPI_Neighbor_alltoallv (comm.c:640-648): straight into the halo part of x, no receive staging
   SB_NCCL(ncclGroupStart());
   for (int i = 0; i < c->outdegree; i++)
-    SB_NCCL(ncclSend(c->sendBuffer + c->sdispls[i], (size_t)c->sendCounts[i], ncclDouble, c->destinations[i], e->nccl, s));
+    SB_NCCL(ncclSend(c->sendBuffer + c->sdispls[i], (size_t)c->sendCounts[i], kNcclReal, c->destinations[i], e->nccl, s));
   for (int i = 0; i < c->indegree; i++)
-    SB_NCCL(ncclRecv(x + numRows + c->rdispls[i], (size_t)c->recvCounts[i], ncclDouble, c->sources[i], e->nccl, s));
+    SB_NCCL(ncclRecv(x + numRows + c->rdispls[i], (size_t)c->recvCounts[i], kNcclReal, c->sources[i], e->nccl, s));
   SB_NCCL(ncclGroupEnd());
 }
 
-void commAllreduceDevice(Comm* c, double* d, int count, int op, cudaStream_t s)
+void commAllreduceDevice(Comm* c, real_t* d, int count, int op, cudaStream_t s)
 {
   CommExt* e = ext(c);
   if (!e) return;
@@ -811,7 +813,7 @@ void commAllreduceDevice(Comm* c, double* d, int count, int op, cudaStream_t s)
     }
     return;
   }
-  SB_NCCL(ncclAllReduce(d, d, (size_t)count, ncclDouble, op == SB_MAX ? ncclMax : ncclSum, e->nccl, s));
+  SB_NCCL(ncclAllReduce(d, d, (size_t)count, kNcclReal, op == SB_MAX ? ncclMax : ncclSum, e->nccl, s));
 }
 
 // Next epoch of the peer-window all-reduce, for kernels that fuse the push / collect halves (peer mode only).
@@ -881,7 +883,8 @@ void commPrintBanner(Comm* c)
   char host[256] = "";
   gethostname(host, sizeof(host) - 1);
   if (c->rank == 0) {
-    printf("sparsebench_b200: CUDA hot path for sm_100a, double precision floats and integer type unsigned int\n");
+    printf("sparsebench_b200: CUDA hot path for sm_100a, %s precision floats and integer type %s\n", sizeof(real_t) == 8 ? "double" : "single",
+        sizeof(idx_t) == 4 ? "unsigned int" : "unsigned long long int");   // comm.c:196-199 (PRECISION_STRING, UINT_STRING)
     if (c->size > 1) printf("One process per GPU using %d ranks, transport: %s\n", c->size, commPeerMode(c) ? "NVLink peer windows" : "NCCL");
   }
   for (int i = 0; i < c->size; i++) {
@@ -891,7 +894,7 @@ void commPrintBanner(Comm* c)
       fflush(stdout);
     }
     if (c->size > 1) {
-      double z = 0.0;
+      real_t z = 0.0;
       commReduction(&z, SB_SUM);                          // commBarrier() of comm.c:211,219
     }
   }
@@ -1024,18 +1027,18 @@ void commDistributeMatrix(Comm* c, MMMatrix* m, MMMatrix* mLocal)
 SbPartitionPlan* sbPartitionLocal(GMatrix* m, int rank, int size, const CG_UINT* startRows, int* wantCounts)
 {
   SbPartitionPlan* P = new SbPartitionPlan();
-  const uint32_t startRow = m->startRow, stopRow = m->stopRow, nr = m->nr;
+  const idx_t startRow = m->startRow, stopRow = m->stopRow, nr = m->nr;
   if (isDevicePointer(m->entries)) {
     // device GMatrix: compact the external references in entry order, number them on the host, rewrite on the device
     Context& c = ctx();
     cudaStream_t s = c.stream;
-    uint32_t stored = 0;
-    SB_CUDA(cudaMemcpyAsync(&stored, m->rowPtr + nr, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    idx_t stored = 0;
+    SB_CUDA(cudaMemcpyAsync(&stored, m->rowPtr + nr, sizeof(idx_t), cudaMemcpyDeviceToHost, s));
     SB_CUDA(cudaStreamSynchronize(s));
     const uint64_t n = stored;
     unsigned char* flag = (unsigned char*)sbAllocateDevice(64, n ? n : 1);
-    uint32_t* col = (uint32_t*)sbAllocateDevice(64, sizeof(uint32_t) * (n ? n : 1));
-    uint32_t* sel = (uint32_t*)sbAllocateDevice(64, sizeof(uint32_t) * (n ? n : 1));
+    idx_t* col = (idx_t*)sbAllocateDevice(64, sizeof(idx_t) * (n ? n : 1));
+    idx_t* sel = (idx_t*)sbAllocateDevice(64, sizeof(idx_t) * (n ? n : 1));
     int* dCount = (int*)sbAllocateDevice(64, sizeof(int));
     const int threads = 256;
     const int blocks = (int)std::min<uint64_t>((n + threads - 1) / threads + 1, (uint64_t)c.numSMs * 16);
@@ -1048,34 +1051,34 @@ SbPartitionPlan* sbPartitionLocal(GMatrix* m, int rank, int size, const CG_UINT*
     int nRefs = 0;
     SB_CUDA(cudaMemcpyAsync(&nRefs, dCount, sizeof(int), cudaMemcpyDeviceToHost, s));
     SB_CUDA(cudaStreamSynchronize(s));
-    std::vector<uint32_t> refs((size_t)nRefs);
-    if (nRefs) sbCopyToHost(refs.data(), sel, sizeof(uint32_t) * (size_t)nRefs);
+    std::vector<idx_t> refs((size_t)nRefs);
+    if (nRefs) sbCopyToHost(refs.data(), sel, sizeof(idx_t) * (size_t)nRefs);
     P->plan.build(refs.data(), refs.size(), rank, size, nr, startRow, startRows);
     const int nExt = (int)P->plan.extGlobal.size();
-    std::vector<std::pair<uint32_t, uint32_t>> table((size_t)nExt);
+    std::vector<std::pair<idx_t, idx_t>> table((size_t)nExt);
     for (int i = 0; i < nExt; i++) table[(size_t)i] = { P->plan.extGlobal[(size_t)i], P->plan.localId[(size_t)i] };
     std::sort(table.begin(), table.end());
-    std::vector<uint32_t> g((size_t)nExt), l((size_t)nExt);
+    std::vector<idx_t> g((size_t)nExt), l((size_t)nExt);
     for (int i = 0; i < nExt; i++) { g[(size_t)i] = table[(size_t)i].first; l[(size_t)i] = table[(size_t)i].second; }
-    uint32_t* dg = (uint32_t*)sbAllocateDevice(64, sizeof(uint32_t) * (size_t)(nExt ? nExt : 1));
-    uint32_t* dl = (uint32_t*)sbAllocateDevice(64, sizeof(uint32_t) * (size_t)(nExt ? nExt : 1));
+    idx_t* dg = (idx_t*)sbAllocateDevice(64, sizeof(idx_t) * (size_t)(nExt ? nExt : 1));
+    idx_t* dl = (idx_t*)sbAllocateDevice(64, sizeof(idx_t) * (size_t)(nExt ? nExt : 1));
     if (nExt) {
-      sbCopyToDevice(dg, g.data(), sizeof(uint32_t) * (size_t)nExt);
-      sbCopyToDevice(dl, l.data(), sizeof(uint32_t) * (size_t)nExt);
+      sbCopyToDevice(dg, g.data(), sizeof(idx_t) * (size_t)nExt);
+      sbCopyToDevice(dl, l.data(), sizeof(idx_t) * (size_t)nExt);
     }
     renumberKernel<<<blocks, threads, 0, s>>>(n, m->entries, startRow, stopRow, nExt, dg, dl);
     SB_CUDA(cudaGetLastError());
     SB_CUDA(cudaStreamSynchronize(s));
     sbFree(flag); sbFree(col); sbFree(sel); sbFree(dCount); sbFree(tmp); sbFree(dg); sbFree(dl);
   } else {
-    const uint32_t stored = m->rowPtr[nr];
-    std::vector<uint32_t> refs;
-    for (uint32_t j = 0; j < stored; j++) {
-      const uint32_t col = m->entries[j].col;
+    const idx_t stored = m->rowPtr[nr];
+    std::vector<idx_t> refs;
+    for (idx_t j = 0; j < stored; j++) {
+      const idx_t col = m->entries[j].col;
       if (col < startRow || col > stopRow) refs.push_back(col);
     }
     P->plan.build(refs.data(), refs.size(), rank, size, nr, startRow, startRows);
-    for (uint32_t j = 0; j < stored; j++) m->entries[j].col = P->plan.renumber(m->entries[j].col, stopRow);
+    for (idx_t j = 0; j < stored; j++) m->entries[j].col = P->plan.renumber(m->entries[j].col, stopRow);
   }
   m->nc = m->nc + (CG_UINT)P->plan.extGlobal.size();        // comm.c:616
   for (int o = 0; o < size; o++) wantCounts[o] = P->plan.want[(size_t)o];

@@ -5,28 +5,51 @@
 #include <stdint.h>
 
 #include "peer_window.h"
+#include "sb_types.h"
 
 namespace sb {
 
 // Matrix values / indices are read exactly once per SpMV: keep them out of L1 so the cache stays with the
-// gathered x vector (B200: 256 KB L1+smem per SM, 126 MB L2).
+// gathered x vector (B200: 256 KB L1+smem per SM, 126 MB L2). One overload per width the two type switches produce.
 __device__ __forceinline__ double ldStream(const double* p)
 {
   double v;
   asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
-__device__ __forceinline__ uint32_t ldStream(const uint32_t* p)
+__device__ __forceinline__ float ldStream(const float* p)
 {
-  uint32_t v;
+  float v;
+  asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ unsigned int ldStream(const unsigned int* p)
+{
+  unsigned int v;
   asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
-__device__ __forceinline__ double2 ldStream2(const double* p)
+__device__ __forceinline__ unsigned long long ldStream(const unsigned long long* p)
 {
-  double2 v;
-  asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  unsigned long long v;
+  asm("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
   return v;
+}
+// one {col, val} record of the CCRS format (8 or 16 bytes, naturally aligned)
+__device__ __forceinline__ Entry ldStreamEntry(const Entry* p)
+{
+  Entry e;
+  if (sizeof(Entry) == 16) {
+    unsigned long long a, b;
+    asm("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
+    memcpy(&e, &a, 8);
+    memcpy(reinterpret_cast<char*>(&e) + 8, &b, 8);
+  } else {
+    unsigned long long a;
+    asm("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(a) : "l"(p));
+    memcpy(&e, &a, sizeof(Entry) < 8 ? sizeof(Entry) : 8);
+  }
+  return e;
 }
 
 // wall-clock nanoseconds (the same on every SM, independent of the SM clock)
@@ -44,23 +67,31 @@ constexpr unsigned long long kPeerTimeoutNs = 20000000000ull;   // 20 s
 // contraction on baseline x86-64). Keeping that order and rounding makes row sums bit-identical to the
 // reference's; fp64 pipes are <5 % utilised by an HBM-bound SpMV, so the extra instruction is free.
 __device__ __forceinline__ double mulAdd(double acc, double a, double b) { return __dadd_rn(acc, __dmul_rn(a, b)); }
+__device__ __forceinline__ float mulAdd(float acc, float a, float b) { return __fadd_rn(acc, __fmul_rn(a, b)); }
+// x + a*y and a*x + b*y with every operation rounded separately (waxpby of solver.c:16-39, strict C semantics)
+__device__ __forceinline__ double addRn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float addRn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double mulRn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float mulRn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double divRn(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float divRn(float a, float b) { return __fdiv_rn(a, b); }
 
-__device__ __forceinline__ double warpSum(double v)
+__device__ __forceinline__ real_t warpSum(real_t v)
 {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
-// Sum over the block in a fixed order; result valid in thread 0. `scratch` holds >= 32 doubles.
-__device__ __forceinline__ double blockSum(double v, double* scratch)
+// Sum over the block in a fixed order; result valid in thread 0. `scratch` holds >= 32 values.
+__device__ __forceinline__ real_t blockSum(real_t v, real_t* scratch)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
   v = warpSum(v);
   __syncthreads();              // scratch may still be in use by a previous call
   if (lane == 0) scratch[warp] = v;
   __syncthreads();
-  double t = 0.0;
+  real_t t = 0.0;
   if (warp == 0) {
     t = lane < nwarps ? scratch[lane] : 0.0;
     t = warpSum(t);
@@ -76,8 +107,8 @@ __device__ __forceinline__ double blockSum(double v, double* scratch)
 // that consumes the scalar, so no separate all-reduce launch sits between the two.
 // `mirror` (optional): a second place the final value is stored to -- the solver passes mapped pinned host memory, so
 // the host sees rho[k] without a copy or an event in the stream.
-__device__ __forceinline__ void gridSum(double blockPartial, double* partials, unsigned int* ticket, double* out,
-    bool accumulate, double* scratch, const PeerReduce* push = nullptr, double* mirror = nullptr)
+__device__ __forceinline__ void gridSum(real_t blockPartial, real_t* partials, unsigned int* ticket, real_t* out,
+    bool accumulate, real_t* scratch, const PeerReduce* push = nullptr, real_t* mirror = nullptr)
 {
   __shared__ bool amLast;
   if (threadIdx.x == 0) {
@@ -89,22 +120,22 @@ __device__ __forceinline__ void gridSum(double blockPartial, double* partials, u
   __syncthreads();
   if (amLast) {
     __threadfence();
-    double v = 0.0;
+    real_t v = 0.0;
     for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) v += __ldcg(partials + i);
     v = blockSum(v, scratch);
     if (threadIdx.x == 0) {
       v = accumulate ? (*out + v) : v;
       *out = v;
-      if (mirror) *(volatile double*)mirror = v;
+      if (mirror) *(volatile real_t*)mirror = v;
       scratch[0] = v;
     }
     if (push && push->size > 0) {
       __syncthreads();
       if ((int)threadIdx.x < push->size) {
-        const double mine = scratch[0];
+        const real_t mine = scratch[0];
         CtrlWindow* w = push->peers[threadIdx.x];
         const int slot = (int)(push->epoch % kRedDepth);
-        *(volatile double*)&w->redVal[slot][push->rank] = mine;
+        *(volatile double*)&w->redVal[slot][push->rank] = (double)mine;      // the window's slots are doubles in every build
         __threadfence_system();
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&w->redFlag[slot][push->rank]), "l"(push->epoch) : "memory");
       }
@@ -114,7 +145,7 @@ __device__ __forceinline__ void gridSum(double blockPartial, double* partials, u
 
 // Second half of the all-reduce: every thread of the calling block gets the global sum. `vals` is shared memory
 // for kMaxRanks doubles. Contains block barriers: call from all threads.
-__device__ __forceinline__ double peerCollect(const PeerReduce& pr, double* vals)
+__device__ __forceinline__ real_t peerCollect(const PeerReduce& pr, real_t* vals)
 {
   const int slot = (int)(pr.epoch % kRedDepth);
   const bool traced = pr.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
@@ -129,14 +160,14 @@ __device__ __forceinline__ double peerCollect(const PeerReduce& pr, double* vals
       __nanosleep(40);
       if (globalTimerNs() - start > kPeerTimeoutNs) __trap();
     }
-    vals[threadIdx.x] = *(volatile double*)&pr.mine->redVal[slot][threadIdx.x];
+    vals[threadIdx.x] = (real_t) * (volatile double*)&pr.mine->redVal[slot][threadIdx.x];
   }
   __syncthreads();
   if (traced) {                                           // how long the slowest peer's partial kept this rank waiting
     atomicAdd(pr.trace, globalTimerNs() - t0);
     atomicAdd(pr.trace + 1, 1ull);
   }
-  double acc = vals[0];
+  real_t acc = vals[0];
   for (int r = 1; r < pr.size; r++) acc += vals[r];      // rank order: same bits on every rank
   __syncthreads();
   return acc;

@@ -50,7 +50,7 @@ void eraseExt(const void* key)
 
 // Device view of the input GMatrix (uploads host arrays; owns what it uploaded).
 struct DeviceInput {
-  const uint32_t* rowPtr = nullptr;
+  const idx_t* rowPtr = nullptr;
   const Entry* entries = nullptr;
   uint64_t stored = 0;      // rowPtr[nr]
   bool owned = false;
@@ -69,15 +69,15 @@ static DeviceInput stageInput(const GMatrix* im)
   if (isDevicePointer(im->entries) || isDevicePointer(im->rowPtr)) {
     in.rowPtr = im->rowPtr;
     in.entries = im->entries;
-    uint32_t last = 0;
-    SB_CUDA(cudaMemcpyAsync(&last, im->rowPtr + nr, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+    idx_t last = 0;
+    SB_CUDA(cudaMemcpyAsync(&last, im->rowPtr + nr, sizeof(idx_t), cudaMemcpyDeviceToHost, c.stream));
     SB_CUDA(cudaStreamSynchronize(c.stream));
     in.stored = last;
   } else {
     in.stored = im->rowPtr[nr];
-    uint32_t* rp = (uint32_t*)sbAllocateDevice(64, sizeof(uint32_t) * (nr + 1 + 8));   // +8: bulk-copy granularity (CCRS shares it)
+    idx_t* rp = (idx_t*)sbAllocateDevice(64, sizeof(idx_t) * (nr + 1 + 8));   // +8: bulk-copy granularity (CCRS shares it)
     Entry* en = (Entry*)sbAllocateDevice(64, sizeof(Entry) * (in.stored ? in.stored : 1));
-    SB_CUDA(cudaMemcpyAsync(rp, im->rowPtr, sizeof(uint32_t) * (nr + 1), cudaMemcpyHostToDevice, c.stream));
+    SB_CUDA(cudaMemcpyAsync(rp, im->rowPtr, sizeof(idx_t) * (nr + 1), cudaMemcpyHostToDevice, c.stream));
     SB_CUDA(cudaMemcpyAsync(en, im->entries, sizeof(Entry) * in.stored, cudaMemcpyHostToDevice, c.stream));
     SB_CUDA(cudaStreamSynchronize(c.stream));
     in.rowPtr = rp;
@@ -96,8 +96,8 @@ static inline int gridFor(uint64_t work, int threads, int perSM = 16)
 }
 
 // ------------------------------------------------------------------------------------------- CRS
-__global__ void splitEntriesKernel(uint64_t n, const Entry* __restrict__ e, uint32_t* __restrict__ col,
-    double* __restrict__ val)
+__global__ void splitEntriesKernel(uint64_t n, const Entry* __restrict__ e, idx_t* __restrict__ col,
+    real_t* __restrict__ val)
 {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     Entry t = e[i];
@@ -107,11 +107,11 @@ __global__ void splitEntriesKernel(uint64_t n, const Entry* __restrict__ e, uint
 }
 
 // ------------------------------------------------------------------------------------------- SELL-C-sigma
-__global__ void scsKeysKernel(uint32_t nr, uint32_t nrPadded, uint32_t sigma, const uint32_t* __restrict__ rowPtr,
-    uint64_t* __restrict__ keys, uint32_t* __restrict__ idx, uint32_t* __restrict__ len)
+__global__ void scsKeysKernel(idx_t nr, idx_t nrPadded, idx_t sigma, const idx_t* __restrict__ rowPtr,
+    uint64_t* __restrict__ keys, idx_t* __restrict__ idx, idx_t* __restrict__ len)
 {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nrPadded; i += gridDim.x * blockDim.x) {
-    const uint32_t l = i < nr ? rowPtr[i + 1] - rowPtr[i] : 0u;     // padding rows have length 0 (matrix-SCS.c:49-58)
+  for (idx_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nrPadded; i += gridDim.x * blockDim.x) {
+    const idx_t l = i < nr ? rowPtr[i + 1] - rowPtr[i] : 0u;     // padding rows have length 0 (matrix-SCS.c:49-58)
     // ascending sort of (window, ~length) == per-window descending length; radix sort is stable, so ties
     // keep ascending row order exactly like the reference's mergesort (matrix-SCS.c:20-29, :61-79)
     keys[i] = ((uint64_t)(i / sigma) << 32) | (uint64_t)(0xffffffffu - l);
@@ -120,13 +120,13 @@ __global__ void scsKeysKernel(uint32_t nr, uint32_t nrPadded, uint32_t sigma, co
   }
 }
 
-__global__ void scsChunkLenKernel(uint32_t nChunks, uint32_t C, const uint64_t* __restrict__ sortedKeys,
-    uint32_t* __restrict__ chunkLens, uint64_t* __restrict__ chunkElems)
+__global__ void scsChunkLenKernel(idx_t nChunks, idx_t C, const uint64_t* __restrict__ sortedKeys,
+    idx_t* __restrict__ chunkLens, uint64_t* __restrict__ chunkElems)
 {
-  for (uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x; ch < nChunks; ch += gridDim.x * blockDim.x) {
-    uint32_t longest = 0;
-    for (uint32_t k = 0; k < C; k++) {
-      const uint32_t l = 0xffffffffu - (uint32_t)(sortedKeys[(uint64_t)ch * C + k] & 0xffffffffu);
+  for (idx_t ch = blockIdx.x * blockDim.x + threadIdx.x; ch < nChunks; ch += gridDim.x * blockDim.x) {
+    idx_t longest = 0;
+    for (idx_t k = 0; k < C; k++) {
+      const idx_t l = 0xffffffffu - (idx_t)(sortedKeys[(uint64_t)ch * C + k] & 0xffffffffu);
       longest = l > longest ? l : longest;
     }
     chunkLens[ch] = longest;                       // matrix-SCS.c:100-108
@@ -134,16 +134,16 @@ __global__ void scsChunkLenKernel(uint32_t nChunks, uint32_t C, const uint64_t* 
   }
 }
 
-__global__ void scsNarrowKernel(uint32_t n, const uint64_t* __restrict__ wide, uint32_t* __restrict__ narrow)
+__global__ void scsNarrowKernel(idx_t n, const uint64_t* __restrict__ wide, idx_t* __restrict__ narrow)
 {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) narrow[i] = (uint32_t)wide[i];
+  for (idx_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) narrow[i] = (idx_t)wide[i];
 }
 
-__global__ void scsPermKernel(uint32_t nr, uint32_t nrPadded, const uint32_t* __restrict__ sortedIdx,
-    uint32_t* __restrict__ oldToNew, uint32_t* __restrict__ newToOld, unsigned int* __restrict__ notIdentity)
+__global__ void scsPermKernel(idx_t nr, idx_t nrPadded, const idx_t* __restrict__ sortedIdx,
+    idx_t* __restrict__ oldToNew, idx_t* __restrict__ newToOld, unsigned int* __restrict__ notIdentity)
 {
-  for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < nrPadded; pos += gridDim.x * blockDim.x) {
-    const uint32_t old = sortedIdx[pos];
+  for (idx_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < nrPadded; pos += gridDim.x * blockDim.x) {
+    const idx_t old = sortedIdx[pos];
     if (old < nr) {                                // matrix-SCS.c:120-143
       oldToNew[old] = pos;
       newToOld[pos] = old;                         // pos < nr: real rows always sort ahead of padding rows
@@ -152,17 +152,17 @@ __global__ void scsPermKernel(uint32_t nr, uint32_t nrPadded, const uint32_t* __
   }
 }
 
-__global__ void scsFillKernel(uint32_t nr, uint32_t C, const uint32_t* __restrict__ rowPtr,
-    const Entry* __restrict__ entries, const uint32_t* __restrict__ oldToNew, const uint32_t* __restrict__ chunkPtr,
-    uint32_t* __restrict__ col, double* __restrict__ val, uint32_t* __restrict__ colPerm,
-    uint32_t* __restrict__ rowLenPerm)
+__global__ void scsFillKernel(idx_t nr, idx_t C, const idx_t* __restrict__ rowPtr,
+    const Entry* __restrict__ entries, const idx_t* __restrict__ oldToNew, const idx_t* __restrict__ chunkPtr,
+    idx_t* __restrict__ col, real_t* __restrict__ val, idx_t* __restrict__ colPerm,
+    idx_t* __restrict__ rowLenPerm)
 {
   // one row per thread; j-th stored entry of row i goes to chunkPtr[r/C] + j*C + r%C (matrix-SCS.c:164-192)
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nr; i += gridDim.x * blockDim.x) {
-    const uint32_t r = oldToNew[i];
+  for (idx_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nr; i += gridDim.x * blockDim.x) {
+    const idx_t r = oldToNew[i];
     const uint64_t base = (uint64_t)chunkPtr[r / C] + r % C;
-    const uint32_t lo = rowPtr[i], hi = rowPtr[i + 1];
-    for (uint32_t j = lo; j < hi; j++) {
+    const idx_t lo = rowPtr[i], hi = rowPtr[i + 1];
+    for (idx_t j = lo; j < hi; j++) {
       const Entry e = entries[j];
       const uint64_t at = base + (uint64_t)(j - lo) * C;
       col[at] = e.col;
@@ -173,17 +173,17 @@ __global__ void scsFillKernel(uint32_t nr, uint32_t C, const uint32_t* __restric
   }
 }
 
-__global__ void scsPadColPermKernel(uint64_t nElems, const double* __restrict__ val, uint32_t* colPerm, uint32_t zeroTarget)
+__global__ void scsPadColPermKernel(uint64_t nElems, const real_t* __restrict__ val, idx_t* colPerm, idx_t zeroTarget)
 {
   // padding elements carry col 0 / val 0 in the reference numbering (matrix-SCS.c:150-155); in the permuted
   // numbering they must keep pointing at the slot that holds original row 0
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nElems; i += (uint64_t)gridDim.x * blockDim.x)
-    if (colPerm[i] == 0xffffffffu) colPerm[i] = zeroTarget;
+    if (colPerm[i] == (idx_t) ~(idx_t)0) colPerm[i] = zeroTarget;     // still the 0xff fill: a padding element
 }
 
-__global__ void rowLenKernel(uint32_t nr, const uint32_t* __restrict__ rowPtr, uint32_t* __restrict__ len)
+__global__ void rowLenKernel(idx_t nr, const idx_t* __restrict__ rowPtr, idx_t* __restrict__ len)
 {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nr; i += gridDim.x * blockDim.x) len[i] = rowPtr[i + 1] - rowPtr[i];
+  for (idx_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nr; i += gridDim.x * blockDim.x) len[i] = rowPtr[i + 1] - rowPtr[i];
 }
 
 Operator makeOperator(void* matrix, int fmt)
@@ -294,11 +294,11 @@ void sbSCS_convertMatrix(SbSCSMatrix* m, GMatrix* im)
   if (m->C == 0 || m->sigma == 0) SB_FATAL("sbSCS_convertMatrix: Matrix.C and Matrix.sigma must be set by the caller (matrix-SCS.c:40)");
   copyHeader(&m->nr, im);
   m->nc = im->nr;                                        // matrix-SCS.c:38
-  const uint32_t nr = im->nr, C = m->C, sigma = m->sigma;
-  const uint32_t nChunks = (nr + C - 1) / C;             // :40
+  const idx_t nr = im->nr, C = m->C, sigma = m->sigma;
+  const idx_t nChunks = (nr + C - 1) / C;             // :40
   const uint64_t nrPadded64 = (uint64_t)nChunks * C;     // :41
-  if (nrPadded64 > 0xffffffffull) SB_FATAL("sbSCS_convertMatrix: padded row count overflows CG_UINT");
-  const uint32_t nrPadded = (uint32_t)nrPadded64;
+  if (nrPadded64 > 0xffffffffull) SB_FATAL("sbSCS_convertMatrix: more than 2^32 padded rows");   // the sort key packs (window, length) into 64 bits
+  const idx_t nrPadded = (idx_t)nrPadded64;
   m->nChunks = nChunks;
   m->nrPadded = nrPadded;
   DeviceInput in = stageInput(im);
@@ -306,16 +306,16 @@ void sbSCS_convertMatrix(SbSCSMatrix* m, GMatrix* im)
   const size_t np = nrPadded ? nrPadded : 1;
   uint64_t* keys = (uint64_t*)sbAllocateDevice(64, sizeof(uint64_t) * np);
   uint64_t* keysSorted = (uint64_t*)sbAllocateDevice(64, sizeof(uint64_t) * np);
-  uint32_t* idx = (uint32_t*)sbAllocateDevice(64, sizeof(uint32_t) * np);
-  uint32_t* idxSorted = (uint32_t*)sbAllocateDevice(64, sizeof(uint32_t) * np);
+  idx_t* idx = (idx_t*)sbAllocateDevice(64, sizeof(idx_t) * np);
+  idx_t* idxSorted = (idx_t*)sbAllocateDevice(64, sizeof(idx_t) * np);
   ScsExt* ext = new ScsExt();
-  ext->rowLenOrig = (uint32_t*)sbAllocateDevice(64, sizeof(uint32_t) * np);
-  ext->rowLenPerm = (uint32_t*)sbAllocateDevice(64, sizeof(uint32_t) * np);
+  ext->rowLenOrig = (idx_t*)sbAllocateDevice(64, sizeof(idx_t) * np);
+  ext->rowLenPerm = (idx_t*)sbAllocateDevice(64, sizeof(idx_t) * np);
   ext->nnzTrue = in.stored;
   ext->nc = im->nc;
   static std::atomic<uint64_t> nextId { 1 };
   ext->id = nextId.fetch_add(1);
-  SB_CUDA(cudaMemsetAsync(ext->rowLenPerm, 0, sizeof(uint32_t) * np, s));
+  SB_CUDA(cudaMemsetAsync(ext->rowLenPerm, 0, sizeof(idx_t) * np, s));
   scsKeysKernel<<<gridFor(nrPadded, 256), 256, 0, s>>>(nr, nrPadded, sigma, in.rowPtr, keys, idx, ext->rowLenOrig);
   SB_CUDA(cudaGetLastError());
   if (sigma > 1 && nrPadded > 1) {
@@ -327,7 +327,7 @@ void sbSCS_convertMatrix(SbSCSMatrix* m, GMatrix* im)
     sbFree(tmp);
   } else {
     SB_CUDA(cudaMemcpyAsync(keysSorted, keys, sizeof(uint64_t) * np, cudaMemcpyDeviceToDevice, s));
-    SB_CUDA(cudaMemcpyAsync(idxSorted, idx, sizeof(uint32_t) * np, cudaMemcpyDeviceToDevice, s));
+    SB_CUDA(cudaMemcpyAsync(idxSorted, idx, sizeof(idx_t) * np, cudaMemcpyDeviceToDevice, s));
   }
 
   m->chunkLens = (CG_UINT*)sbAllocateDevice(64, sizeof(CG_UINT) * (nChunks ? nChunks : 1));
@@ -350,7 +350,8 @@ void sbSCS_convertMatrix(SbSCSMatrix* m, GMatrix* im)
   uint64_t nElems = 0;
   SB_CUDA(cudaMemcpyAsync(&nElems, chunkPtr64 + nChunks, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
   SB_CUDA(cudaStreamSynchronize(s));
-  if (nElems > 0xffffffffull) SB_FATAL("sbSCS_convertMatrix: %llu padded elements overflow CG_UINT chunkPtr", (unsigned long long)nElems);
+  if (sizeof(idx_t) == 4 && nElems > 0xffffffffull)
+    SB_FATAL("sbSCS_convertMatrix: %llu padded elements overflow CG_UINT chunkPtr (use the 64-bit index build)", (unsigned long long)nElems);
   m->nElems = (CG_UINT)nElems;                           // :110-114
   scsNarrowKernel<<<gridFor((uint64_t)nChunks + 1, 256), 256, 0, s>>>(nChunks + 1, chunkPtr64, m->chunkPtr);
   SB_CUDA(cudaGetLastError());
@@ -367,19 +368,19 @@ void sbSCS_convertMatrix(SbSCSMatrix* m, GMatrix* im)
   const size_t ne = nElems ? nElems : 1;
   m->colInd = (CG_UINT*)sbAllocateDevice(64, sizeof(CG_UINT) * ne);
   m->val = (CG_FLOAT*)sbAllocateDevice(64, sizeof(CG_FLOAT) * ne);
-  ext->colPerm = (uint32_t*)sbAllocateDevice(64, sizeof(uint32_t) * ne);
+  ext->colPerm = (idx_t*)sbAllocateDevice(64, sizeof(idx_t) * ne);
   SB_CUDA(cudaMemsetAsync(m->colInd, 0, sizeof(CG_UINT) * ne, s));      // :150-155
   SB_CUDA(cudaMemsetAsync(m->val, 0, sizeof(CG_FLOAT) * ne, s));
-  SB_CUDA(cudaMemsetAsync(ext->colPerm, 0xff, sizeof(uint32_t) * ne, s));
+  SB_CUDA(cudaMemsetAsync(ext->colPerm, 0xff, sizeof(idx_t) * ne, s));
   if (nr) {
     scsFillKernel<<<gridFor(nr, 128), 128, 0, s>>>(nr, C, in.rowPtr, in.entries, m->oldToNewPerm, m->chunkPtr, m->colInd,
         m->val, ext->colPerm, ext->rowLenPerm);
     SB_CUDA(cudaGetLastError());
   }
   unsigned int hostNotIdentity = 0;
-  uint32_t zeroTarget = 0;
+  idx_t zeroTarget = 0;
   SB_CUDA(cudaMemcpyAsync(&hostNotIdentity, notIdentity, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
-  if (nr) SB_CUDA(cudaMemcpyAsync(&zeroTarget, m->oldToNewPerm, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  if (nr) SB_CUDA(cudaMemcpyAsync(&zeroTarget, m->oldToNewPerm, sizeof(idx_t), cudaMemcpyDeviceToHost, s));
   SB_CUDA(cudaStreamSynchronize(s));
   if (nElems) {
     scsPadColPermKernel<<<gridFor(nElems, 256), 256, 0, s>>>(nElems, m->val, ext->colPerm, zeroTarget);

@@ -53,14 +53,14 @@ __host__ __device__ inline int visitRow(const Geometry& g, long long row, F f)
   return count;
 }
 
-__global__ void rowLengthKernel(Geometry g, uint32_t* len)
+__global__ void rowLengthKernel(Geometry g, idx_t* len)
 {
   for (long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x; row < g.localRows;
        row += (long long)gridDim.x * blockDim.x)
-    len[row] = (uint32_t)visitRow(g, row, [](long long, bool) {});
+    len[row] = (idx_t)visitRow(g, row, [](long long, bool) {});
 }
 
-__global__ void fillKernel(Geometry g, const uint32_t* __restrict__ rowPtr, Entry* __restrict__ entries)
+__global__ void fillKernel(Geometry g, const idx_t* __restrict__ rowPtr, Entry* __restrict__ entries)
 {
   for (long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x; row < g.localRows;
        row += (long long)gridDim.x * blockDim.x) {
@@ -103,7 +103,7 @@ void matrixGenerate(GMatrix* m, Parameter* p, int rank, int size, bool use_7pt_s
   checkSizes(g);
   if (!rank) {   // matrix.c:43-52
     printf(use_7pt_stencil ? "Generate 7pt matrix with " : "Generate 27pt matrix with ");
-    printf("%.2e total rows and %.2e nonzeros\n", (double)g.totalRows, (double)(27 * g.localRows));
+    printf("%.2e total rows and %.2e nonzeros\n", (real_t)g.totalRows, (real_t)(27 * g.localRows));
   }
   void *rp = nullptr, *en = nullptr;
   if (posix_memalign(&rp, 64, sizeof(CG_UINT) * (size_t)(g.localRows + 1)) ||
@@ -132,7 +132,7 @@ void sbGenerateDevice(GMatrix* m, Parameter* p, int rank, int size, bool use_7pt
   checkSizes(g);
   sb::Context& c = sb::ctx();
   const size_t n = (size_t)g.localRows;
-  uint32_t* len = (uint32_t*)sbAllocateDevice(64, sizeof(uint32_t) * n);
+  idx_t* len = (idx_t*)sbAllocateDevice(64, sizeof(idx_t) * n);
   m->rowPtr = (CG_UINT*)sbAllocateDevice(64, sizeof(CG_UINT) * (n + 1 + 8));   // +8: bulk-copy granularity of the SpMV kernels (CCRS shares this array)
   const int threads = 256;
   const int blocks = (int)((n + threads - 1) / threads < (size_t)c.numSMs * 16 ? (n + threads - 1) / threads : (size_t)c.numSMs * 16);

@@ -19,36 +19,36 @@ namespace sb {
 
 namespace {
 struct OrdinalSet {
-  std::vector<uint32_t> key;
+  std::vector<idx_t> key;
   std::vector<int> ord;
-  uint32_t mask = 0;
+  idx_t mask = 0;
   explicit OrdinalSet(size_t expect)
   {
     size_t cap = 16;
     while (cap < 2 * expect + 8) cap <<= 1;
     key.assign(cap, 0);
     ord.assign(cap, -1);
-    mask = (uint32_t)(cap - 1);
+    mask = (idx_t)(cap - 1);
   }
-  uint32_t slot(uint32_t k) const
+  idx_t slot(idx_t k) const
   {
-    uint32_t h = (k * 2654435761u) & mask;
+    idx_t h = (k * 2654435761u) & mask;
     while (ord[h] >= 0 && key[h] != k) h = (h + 1) & mask;
     return h;
   }
 };
 } // namespace
 
-void PartitionPlan::build(const uint32_t* extRefs, size_t nRefs, int rank_, int size_, uint32_t nr_, uint32_t startRow_,
-    const uint32_t* startRows)
+void PartitionPlan::build(const idx_t* extRefs, size_t nRefs, int rank_, int size_, idx_t nr_, idx_t startRow_,
+    const idx_t* startRows)
 {
   rank = rank_; size = size_; nr = nr_; startRow = startRow_;
   // step 1 (comm.c:452-473): ordinals in first-encounter order
   OrdinalSet seen(nRefs);
   extGlobal.clear();
   for (size_t i = 0; i < nRefs; i++) {
-    const uint32_t c = extRefs[i];
-    const uint32_t h = seen.slot(c);
+    const idx_t c = extRefs[i];
+    const idx_t h = seen.slot(c);
     if (seen.ord[h] < 0) {
       seen.key[h] = c;
       seen.ord[h] = (int)extGlobal.size();
@@ -82,7 +82,7 @@ void PartitionPlan::build(const uint32_t* extRefs, size_t nRefs, int rank_, int 
   std::vector<int> fill = groupStart;
   for (int i = 0; i < nExt; i++) {
     const int slot = fill[(size_t)owner[(size_t)i]]++;
-    localId[(size_t)i] = (uint32_t)((int)nr + slot);
+    localId[(size_t)i] = (idx_t)((int)nr + slot);
     requests[(size_t)slot] = (int)extGlobal[(size_t)i];        // externalsReordered (comm.c:108-110)
   }
   // lookup table for the column rewrite
@@ -91,10 +91,10 @@ void PartitionPlan::build(const uint32_t* extRefs, size_t nRefs, int rank_, int 
   lookupMask = seen.mask;
 }
 
-uint32_t PartitionPlan::renumber(uint32_t col, uint32_t stopRow) const
+idx_t PartitionPlan::renumber(idx_t col, idx_t stopRow) const
 {
   if (col >= startRow && col <= stopRow) return col - startRow;       // comm.c:100-101
-  uint32_t h = (col * 2654435761u) & lookupMask;
+  idx_t h = (col * 2654435761u) & lookupMask;
   while (lookupOrd[h] >= 0 && lookupKey[h] != col) h = (h + 1) & lookupMask;
   return localId[(size_t)lookupOrd[h]];                               // comm.c:102-104
 }

@@ -41,6 +41,8 @@ static void initContext()
   SB_CUDA(cudaMalloc(&g_ctx.dScalar, sizeof(double) * 64));
   SB_CUDA(cudaMemset(g_ctx.dScalar, 0, sizeof(double) * 64));
   SB_CUDA(cudaMallocHost(&g_ctx.hScalar, sizeof(double) * 64));
+  SB_CUDA(cudaMalloc(&g_ctx.dWide, sizeof(double) * 8));
+  SB_CUDA(cudaMallocHost(&g_ctx.hWide, sizeof(double) * 8));
 }
 
 Context& ctx()
@@ -248,7 +250,7 @@ double sbMeasureReadBandwidth(size_t bytes, int reps)
   float best = 1e30f;
   for (int r = 0; r < reps + 2; r++) {
     SB_CUDA(cudaEventRecord(a, c.stream));
-    readStreamKernel<<<c.numSMs * 4, 512, 0, c.stream>>>(buf, bytes / 16, c.dScalar + 16);
+    readStreamKernel<<<c.numSMs * 4, 512, 0, c.stream>>>(buf, bytes / 16, c.dWide + 4);
     SB_CUDA(cudaEventRecord(b, c.stream));
     SB_CUDA(cudaEventSynchronize(b));
     float ms = 0.f;

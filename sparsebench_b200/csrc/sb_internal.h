@@ -6,6 +6,7 @@
 #include <stdlib.h>
 
 #include "peer_window.h"
+#include "sb_types.h"
 #include "sparsebench_b200.h"
 
 // Error convention of the reference: message + exit(EXIT_FAILURE) (allocate.c:19-33).
@@ -36,10 +37,12 @@ struct Context {
   int numSMs = 0;
   cudaStream_t stream = nullptr;     // blocking stream: ordered with the legacy default stream
   cudaStream_t commStream = nullptr; // halo exchange side stream
-  double* partials = nullptr;        // kMaxPartials doubles per reduction slot, 4 slots
+  real_t* partials = nullptr;        // kMaxPartials doubles per reduction slot, 4 slots
   unsigned int* tickets = nullptr;   // last-block tickets, one per reduction slot
-  double* dScalar = nullptr;         // small device scalar block (64 doubles)
-  double* hScalar = nullptr;         // pinned mirror
+  real_t* dScalar = nullptr;         // small device scalar block (64 doubles)
+  real_t* hScalar = nullptr;         // pinned mirror
+  double* dWide = nullptr;           // 8 doubles whatever the value type (maxErr is computed in double)
+  double* hWide = nullptr;
   void* flushBuf = nullptr;
   size_t flushBytes = 0;
   size_t launches = 0;
@@ -72,40 +75,40 @@ inline void launchPdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sm
 
 // ---- sparse formats: device-side views the kernels take
 struct CrsView {
-  uint32_t nr;
-  const uint32_t* rowPtr;
-  const uint32_t* col;
-  const double* val;
+  idx_t nr;
+  const idx_t* rowPtr;
+  const idx_t* col;
+  const real_t* val;
 };
 struct SellView {
-  uint32_t nChunks, nr, C;
-  const uint32_t* chunkPtr;
-  const uint32_t* chunkLens;
-  const uint32_t* col;
-  const double* val;
+  idx_t nChunks, nr, C;
+  const idx_t* chunkPtr;
+  const idx_t* chunkLens;
+  const idx_t* col;
+  const real_t* val;
 };
 struct CcrsView {
-  uint32_t nr;
-  const uint32_t* rowPtr;
+  idx_t nr;
+  const idx_t* rowPtr;
   const Entry* entries;
 };
 
 // cached interior/boundary split of a converted matrix (spmvInteriorUnits)
 struct HaloSplit {
   bool valid = false;
-  uint32_t lo = 0, hi = 0;
+  idx_t lo = 0, hi = 0;
 };
 
 // A sparse operator as the CG driver sees it.
 struct Operator {
   int fmt;
   HaloSplit* split = nullptr;              // cache slot in the matrix's side table
-  uint32_t nr = 0, nc = 0, nrPadded = 0;   // vectors written by spmv need nrPadded slots
+  idx_t nr = 0, nc = 0, nrPadded = 0;   // vectors written by spmv need nrPadded slots
   uint64_t nnzTrue = 0;
-  const uint32_t* rowPtr = nullptr;        // CRS/CCRS: device rowPtr (b = 27-(len-1) rule); SCS: original-order rowLen
-  const uint32_t* rowLen = nullptr;        // SCS: row lengths in vector (permuted) order
-  const uint32_t* oldToNew = nullptr;      // SCS with sigma>1: vectors live in permuted order
-  const uint32_t* newToOld = nullptr;
+  const idx_t* rowPtr = nullptr;        // CRS/CCRS: device rowPtr (b = 27-(len-1) rule); SCS: original-order rowLen
+  const idx_t* rowLen = nullptr;        // SCS: row lengths in vector (permuted) order
+  const idx_t* oldToNew = nullptr;      // SCS with sigma>1: vectors live in permuted order
+  const idx_t* newToOld = nullptr;
   uint64_t permKey = 0;                    // unique id of the row permutation (0: none); cache key of derived lists
   CrsView crs{};
   SellView sell{};                         // col = symmetric-permuted columns when oldToNew != nullptr
@@ -117,47 +120,47 @@ struct FusedPut;
 
 // Fused dot-product epilogue: *out = (accumulate ? *out : 0) + sum, reduced through scratch slot `slot` (0..3).
 struct DotArgs {
-  double* out;
+  real_t* out;
   bool accumulate;
   int slot;
   const PeerReduce* push = nullptr;   // multi-GPU: the last block also stores the sum into every peer's window
 };
 // y = A x on units [lo,hi) (rows for CRS/CCRS, chunks for SELL); with `dot` also sum_i x[i]*y[i] over them.
-uint32_t spmvUnits(const Operator& A);
+idx_t spmvUnits(const Operator& A);
 // largest unit range [lo, hi) around the middle whose rows reference no halo column (col >= nr); blocks the stream
-void spmvInteriorUnits(const Operator& A, uint32_t* lo, uint32_t* hi, cudaStream_t s);
-void launchSpmv(const Operator& A, const double* x, double* y, uint32_t lo, uint32_t hi, const DotArgs* dot,
+void spmvInteriorUnits(const Operator& A, idx_t* lo, idx_t* hi, cudaStream_t s);
+void launchSpmv(const Operator& A, const real_t* x, real_t* y, idx_t lo, idx_t hi, const DotArgs* dot,
     cudaStream_t s);
 // y = A x over all units in ONE launch, ordered interior [intLo,intHi) first; the kernel waits on `gate` before the
 // first unit outside that range (those reference halo columns, which a peer is storing while the interior runs)
 bool spmvGatedAvailable(const Operator& A);
-void launchSpmvGated(const Operator& A, const double* x, double* y, uint32_t intLo, uint32_t intHi, const HaloGate& gate,
+void launchSpmvGated(const Operator& A, const real_t* x, real_t* y, idx_t intLo, idx_t intHi, const HaloGate& gate,
     const DotArgs* dot, cudaStream_t s);
 
 // ---- vector kernels (vecops.cu)
-void launchWaxpby(uint32_t n, double alpha, const double* x, double beta, const double* y, double* w, cudaStream_t s);
+void launchWaxpby(idx_t n, real_t alpha, const real_t* x, real_t beta, const real_t* y, real_t* w, cudaStream_t s);
 // *dResult (device) = sum x[i]*y[i], deterministic one-kernel grid reduction through scratch slot `slot`
-void launchDot(uint32_t n, const double* x, const double* y, double* dResult, int slot, cudaStream_t s);
+void launchDot(idx_t n, const real_t* x, const real_t* y, real_t* dResult, int slot, cudaStream_t s);
 // fused CG passes: rho[j] = r_j.r_j, pAp[k] = p_k.Ap_k live on the device, k is the 1-based iteration
 // collect*: the scalar this kernel needs (rho[k-1] resp. pAp[k]) is still spread over the peer window and is summed
 // in the kernel's prologue; pushRho: rho[k] is pushed to the peers instead of being all-reduced by a separate kernel
 // hostRho: mapped pinned mirror of rho[] -- the kernel that produces the GLOBAL rho[j] also stores it there
-void launchCgUpdateP(uint32_t n, int k, double* rho, const double* r, double* p, const PeerReduce* collectRho,
-    const FusedPut* put, double* hostRho, cudaStream_t s);
-void launchCgUpdateXR(uint32_t n, int k, double* rho, double* pAp, double* x, double* r, const double* p,
-    const double* Ap, int slot, const PeerReduce* collectPAp, const PeerReduce* pushRho, double* hostRho, cudaStream_t s);
+void launchCgUpdateP(idx_t n, int k, real_t* rho, const real_t* r, real_t* p, const PeerReduce* collectRho,
+    const FusedPut* put, real_t* hostRho, cudaStream_t s);
+void launchCgUpdateXR(idx_t n, int k, real_t* rho, real_t* pAp, real_t* x, real_t* r, const real_t* p,
+    const real_t* Ap, int slot, const PeerReduce* collectPAp, const PeerReduce* pushRho, real_t* hostRho, cudaStream_t s);
 
-void launchInitVectors(uint32_t n, const uint32_t* rowPtr, const uint32_t* rowLen, bool generated, double* x, double* b,
+void launchInitVectors(idx_t n, const idx_t* rowPtr, const idx_t* rowLen, bool generated, real_t* x, real_t* b,
     cudaStream_t s);
-void launchScatter(uint32_t n, const uint32_t* map, const double* in, double* out, cudaStream_t s);   // out[map[i]] = in[i]
-void launchGather(uint32_t n, const uint32_t* map, const double* in, double* out, cudaStream_t s);    // out[i] = in[map[i]]
-void launchMaxErr(uint32_t n, const double* x, double* out, cudaStream_t s);
-void launchPermuteIndices(uint32_t n, const uint32_t* map, const int* in, int* out, cudaStream_t s);   // out[i] = map[in[i]]
+void launchScatter(idx_t n, const idx_t* map, const real_t* in, real_t* out, cudaStream_t s);   // out[map[i]] = in[i]
+void launchGather(idx_t n, const idx_t* map, const real_t* in, real_t* out, cudaStream_t s);    // out[i] = in[map[i]]
+void launchMaxErr(idx_t n, const real_t* x, double* out, cudaStream_t s);
+void launchPermuteIndices(idx_t n, const idx_t* map, const int* in, int* out, cudaStream_t s);   // out[i] = map[in[i]]
 
 // ---- communication (comm.cu)
 // `elements` overrides the device copy of Comm.elementsToSend (the CG passes row-permuted indices for SELL)
-void commExchangeOnStream(Comm* c, uint32_t numRows, double* x, const int* elements, cudaStream_t s);
-void commAllreduceDevice(Comm* c, double* d, int count, int op, cudaStream_t s);
+void commExchangeOnStream(Comm* c, idx_t numRows, real_t* x, const int* elements, cudaStream_t s);
+void commAllreduceDevice(Comm* c, real_t* d, int count, int op, cudaStream_t s);
 // NVLink peer-window transport
 bool commPeerMode(const Comm* c);
 const int* commDeviceElements(Comm* c);                    // device copy of Comm.elementsToSend
@@ -178,32 +181,32 @@ struct HaloGate {
 constexpr int kMaxFusedDests = 4;
 struct FusedPut {
   int ndest = 0;                                           // 0: not in use
-  uint32_t lo[kMaxFusedDests] = {}, hi[kMaxFusedDests] = {};   // inclusive element range that holds everything sent to d
+  idx_t lo[kMaxFusedDests] = {}, hi[kMaxFusedDests] = {};   // inclusive element range that holds everything sent to d
   const int* inv[kMaxFusedDests] = {};
-  double* remote[kMaxFusedDests] = {};
+  real_t* remote[kMaxFusedDests] = {};
   unsigned long long* remoteFlag[kMaxFusedDests] = {};
 };
 // Collective. Borrows the Comm's persistent halo vector (>= slots doubles, zero-filled when first registered; peers
 // map it once per partition, not per solve) for one solver; nullptr (on every rank) -> allocate your own vector and
 // use commExchangeOnStream. The borrower must not clear slots >= numRows: a faster peer may already have stored the
 // next exchange's halo there.
-double* commAcquireHaloVector(Comm* c, uint32_t numRows, size_t slots, bool localOk);
+real_t* commAcquireHaloVector(Comm* c, idx_t numRows, size_t slots, bool localOk);
 void commReleaseHaloVector(Comm* c);
 // send list in the solver's row numbering (device; SELL keeps vectors in permuted order), cached per permutation key
-const int* commSolverElements(Comm* c, uint64_t key, const uint32_t* oldToNew, cudaStream_t s);
+const int* commSolverElements(Comm* c, uint64_t key, const idx_t* oldToNew, cudaStream_t s);
 bool commPrepareFusedPut(Comm* c, uint64_t key, const int* elements);    // false: too many destinations for FusedPut
 HaloGate commFusedPutBegin(Comm* c, FusedPut* fp);                   // next exchange, performed by the caller's kernel
-HaloGate commHaloPutDirect(Comm* c, const double* x, const int* elements, cudaStream_t s);   // returns the gate to wait on
+HaloGate commHaloPutDirect(Comm* c, const real_t* x, const int* elements, cudaStream_t s);   // returns the gate to wait on
 
 // ---- side tables keyed by the device array a Matrix struct points to
 struct ScsExt {
   HaloSplit split;
-  uint32_t* colPerm = nullptr;   // symmetric-permuted column ids (CG keeps vectors in permuted order)
-  uint32_t* rowLenPerm = nullptr;
-  uint32_t* rowLenOrig = nullptr;
+  idx_t* colPerm = nullptr;   // symmetric-permuted column ids (CG keeps vectors in permuted order)
+  idx_t* rowLenPerm = nullptr;
+  idx_t* rowLenOrig = nullptr;
   bool identityPerm = true;
   uint64_t nnzTrue = 0;
-  uint32_t nc = 0;               // columns incl. halo (the reference's SCS struct drops it, matrix-SCS.c:38)
+  idx_t nc = 0;               // columns incl. halo (the reference's SCS struct drops it, matrix-SCS.c:38)
   uint64_t id = 0;               // unique per conversion, never reused
 };
 struct CrsExt {

@@ -5,6 +5,8 @@
 
 #include <vector>
 
+#include "sb_types.h"
+
 namespace sb {
 
 struct CommLists {
@@ -14,18 +16,18 @@ struct CommLists {
 
 struct PartitionPlan {
   int rank = 0, size = 1;
-  uint32_t nr = 0, startRow = 0;
-  std::vector<uint32_t> extGlobal;   // external global ids, first-encounter order (comm.c:452-473)
-  std::vector<uint32_t> localId;     // halo slot (>= nr) of each ordinal (comm.c:57-81)
+  idx_t nr = 0, startRow = 0;
+  std::vector<idx_t> extGlobal;   // external global ids, first-encounter order (comm.c:452-473)
+  std::vector<idx_t> localId;     // halo slot (>= nr) of each ordinal (comm.c:57-81)
   std::vector<int> want;             // want[owner] = number of externals owned by `owner` (comm.c:496-520)
   std::vector<int> requests;         // externalsReordered: global id held by halo slot j (comm.c:108-110)
-  std::vector<uint32_t> lookupKey;
+  std::vector<idx_t> lookupKey;
   std::vector<int> lookupOrd;
-  uint32_t lookupMask = 0;
+  idx_t lookupMask = 0;
 
-  void build(const uint32_t* extRefs, size_t nRefs, int rank, int size, uint32_t nr, uint32_t startRow,
-      const uint32_t* startRows);
-  uint32_t renumber(uint32_t col, uint32_t stopRow) const;
+  void build(const idx_t* extRefs, size_t nRefs, int rank, int size, idx_t nr, idx_t startRow,
+      const idx_t* startRows);
+  idx_t renumber(idx_t col, idx_t stopRow) const;
   void requestSlice(const int* wantMatrix, int source, const int** ptr, int* count) const;
   void finish(CommLists& out, const int* wantMatrix, const int* received) const;
 };

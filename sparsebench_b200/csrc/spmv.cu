@@ -48,15 +48,23 @@ static bool useLegacyKernels()
 // x gather. Plain kernels use the read-only path (ld.global.nc). Gated kernels read halo values that peers store
 // WHILE the kernel runs: those loads must be coherent ones -- then the acquire on the arrival counter plus the
 // block / warp barrier behind it orders them after the peers' stores (ld.global.nc gives no such guarantee).
+__device__ __forceinline__ double ldCoherent(const double* p)
+{
+  double v;
+  asm("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ldCoherent(const float* p)
+{
+  float v;
+  asm("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
 template <bool COHERENT>
-__device__ __forceinline__ double gatherX(const double* p)
+__device__ __forceinline__ real_t gatherX(const real_t* p)
 {
 #ifndef SB_EXPERIMENT_NC       // -DSB_EXPERIMENT_NC: timing experiment only (read-only path even behind the gate)
-  if (COHERENT) {
-    double v;
-    asm("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
-  }
+  if (COHERENT) return ldCoherent(p);
 #endif
   return __ldg(p);
 }
@@ -108,15 +116,16 @@ __device__ __noinline__ void gateWait(const GateSmem* g, int nsrc)
 // gated kernel are coherent loads (gatherX), because the peers store halo values while it is already running.
 template <bool DOT, int WARPS, int J, int S, int U, bool LOCKSTEP, bool GATED>
 __global__ void __launch_bounds__(WARPS * 32, 1)
-spmvSell32TmaKernel(SellView A, const double* __restrict__ x, double* __restrict__ y, uint32_t lo, uint32_t hi,
-    double* partials, unsigned int* ticket, double* dotOut, bool accumulate, uint32_t rot, uint32_t nInterior, HaloGate gate,
+spmvSell32TmaKernel(SellView A, const real_t* __restrict__ x, real_t* __restrict__ y, idx_t lo, idx_t hi,
+    real_t* partials, unsigned int* ticket, real_t* dotOut, bool accumulate, idx_t rot, idx_t nInterior, HaloGate gate,
     PeerReduce push)
 {
   extern __shared__ __align__(128) unsigned char ring[];
-  __shared__ double scratch[32];
+  __shared__ real_t scratch[32];
   __shared__ uint64_t bars[WARPS * S];
   __shared__ GateSmem gateSmem;
-  constexpr uint32_t kStageBytes = J * 32 * 12;
+  constexpr uint32_t kValBytes = 32 * sizeof(real_t), kColBytes = 32 * sizeof(idx_t);   // one chunk column: 32 values, 32 ids
+  constexpr uint32_t kStageBytes = J * (kValBytes + kColBytes);
   constexpr uint32_t kFull = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char* mine = ring + (size_t)warp * S * kStageBytes;
@@ -141,7 +150,7 @@ spmvSell32TmaKernel(SellView A, const double* __restrict__ x, double* __restrict
   const uint64_t ctaFirst = (uint64_t)blockIdx.x * WARPS;
   const uint64_t first = ctaFirst + warp;
   // this warp's t-th chunk is first + t*stride; lane l of a metadata block B holds chunk t = 32*B + l
-  auto loadMeta = [&](uint32_t block, uint32_t& lenL, uint32_t& ptrL) {
+  auto loadMeta = [&](idx_t block, idx_t& lenL, idx_t& ptrL) {
     const uint64_t l = first + ((uint64_t)block * 32 + lane) * stride;
     const uint64_t ch = l < n ? phys(l) : 0;
     lenL = l < n ? __ldg(A.chunkLens + ch) : 0u;
@@ -149,11 +158,11 @@ spmvSell32TmaKernel(SellView A, const double* __restrict__ x, double* __restrict
   };
 
   // producer cursor: next slab to request = columns [pj, pj+J) of logical chunk pc (empty chunks have no slab)
-  uint32_t pLenL, pPtrL, pT = 0;
+  idx_t pLenL, pPtrL, pT = 0;
   loadMeta(0, pLenL, pPtrL);
-  uint32_t cLenL = pLenL, cT = 0;
+  idx_t cLenL = pLenL, cT = 0;
   uint64_t pc = first;
-  uint32_t pj = 0, plen = __shfl_sync(kFull, pLenL, 0), pptr = __shfl_sync(kFull, pPtrL, 0);
+  idx_t pj = 0, plen = __shfl_sync(kFull, pLenL, 0), pptr = __shfl_sync(kFull, pPtrL, 0);
   auto produce = [&](int s) {
     while (pc < n && pj >= plen) {
       pc += stride;
@@ -164,13 +173,13 @@ spmvSell32TmaKernel(SellView A, const double* __restrict__ x, double* __restrict
       pptr = __shfl_sync(kFull, pPtrL, pT & 31u);
     }
     if (pc >= n) return;
-    const uint32_t cols = min((uint32_t)J, plen - pj);
+    const idx_t cols = min((idx_t)J, plen - pj);
     if (lane == 0) {
       const uint64_t off = (uint64_t)pptr + (uint64_t)pj * 32;
       unsigned char* dst = mine + (size_t)s * kStageBytes;
-      mbarExpectTx(bar + s, cols * 32 * 12);
-      bulkLoad(dst, A.val + off, cols * 256, bar + s);
-      bulkLoad(dst + J * 256, A.col + off, cols * 128, bar + s);
+      mbarExpectTx(bar + s, (uint32_t)cols * (kValBytes + kColBytes));
+      bulkLoad(dst, A.val + off, (uint32_t)cols * kValBytes, bar + s);
+      bulkLoad(dst + J * kValBytes, A.col + off, (uint32_t)cols * kColBytes, bar + s);
     }
     pj += cols;
   };
@@ -180,8 +189,8 @@ spmvSell32TmaKernel(SellView A, const double* __restrict__ x, double* __restrict
   griddepWait();
 
   int cs = 0;
-  uint32_t phases = 0;
-  double dotAcc = 0.0;
+  idx_t phases = 0;
+  real_t dotAcc = 0.0;
   bool gatePassed = false;
   // LOCKSTEP: the CTA's warps advance one chunk each per step and meet at a barrier, so that they keep working on
   // 32*WARPS consecutive rows (one shared window of x in L1) instead of drifting apart
@@ -201,24 +210,24 @@ spmvSell32TmaKernel(SellView A, const double* __restrict__ x, double* __restrict
       continue;
     }
     if (cT != 0 && (cT & 31u) == 0) {
-      uint32_t unused;
+      idx_t unused;
       loadMeta(cT >> 5, cLenL, unused);
     }
-    const uint32_t len = __shfl_sync(kFull, cLenL, cT & 31u);
+    const idx_t len = __shfl_sync(kFull, cLenL, cT & 31u);
     const uint64_t row = phys(lchunk) * 32 + lane;
-    double xr = 0.0;
+    real_t xr = 0.0;
     if (DOT && row < A.nr) xr = __ldg(x + row);
-    double sum = 0.0;
-    for (uint32_t j0 = 0; j0 < len; j0 += J) {
-      const uint32_t cols = min((uint32_t)J, len - j0);
+    real_t sum = 0.0;
+    for (idx_t j0 = 0; j0 < len; j0 += J) {
+      const idx_t cols = min((idx_t)J, len - j0);
       mbarWait(bar + cs, (phases >> cs) & 1u);
       phases ^= 1u << cs;
-      const double* v = reinterpret_cast<const double*>(mine + (size_t)cs * kStageBytes) + lane;
-      const uint32_t* c = reinterpret_cast<const uint32_t*>(mine + (size_t)cs * kStageBytes + J * 256) + lane;
+      const real_t* v = reinterpret_cast<const real_t*>(mine + (size_t)cs * kStageBytes) + lane;
+      const idx_t* c = reinterpret_cast<const idx_t*>(mine + (size_t)cs * kStageBytes + J * kValBytes) + lane;
 #pragma unroll
-      for (uint32_t j = 0; j < (uint32_t)J; j += U) {
+      for (idx_t j = 0; j < (idx_t)J; j += U) {
         if (j < cols) {                              // warp-uniform
-          double xx[U], vv[U];
+          real_t xx[U], vv[U];
 #pragma unroll
           for (int u = 0; u < U; u++)
             if (j + u < cols) xx[u] = gatherX<GATED>(x + c[(j + u) * 32]);
@@ -239,22 +248,22 @@ spmvSell32TmaKernel(SellView A, const double* __restrict__ x, double* __restrict
     if (LOCKSTEP) __syncthreads();
   }
   if (DOT) {
-    const double b = blockSum(dotAcc, scratch);
+    const real_t b = blockSum(dotAcc, scratch);
     gridSum(b, partials, ticket, dotOut, accumulate, scratch, push.size ? &push : nullptr);
   }
 }
 
 struct SellGate {                                     // nullptr-able extra arguments of a gated launch
-  uint32_t rot, nInterior;
+  idx_t rot, nInterior;
   HaloGate gate;
 };
 
 template <int WARPS, int J, int S, int U, bool LOCKSTEP, bool GATED>
-static void launchSell32TmaCfg(const SellView& A, const double* x, double* y, uint32_t lo, uint32_t hi, const DotArgs* dot,
+static void launchSell32TmaCfg(const SellView& A, const real_t* x, real_t* y, idx_t lo, idx_t hi, const DotArgs* dot,
     const SellGate* g, cudaStream_t s)
 {
   Context& c = ctx();
-  const size_t smem = (size_t)WARPS * S * J * 32 * 12;
+  const size_t smem = (size_t)WARPS * S * J * 32 * (sizeof(real_t) + sizeof(idx_t));
   static bool configured = false;
   if (!configured) {
     allowLargeSmem(spmvSell32TmaKernel<true, WARPS, J, S, U, LOCKSTEP, GATED>, smem);
@@ -263,7 +272,7 @@ static void launchSell32TmaCfg(const SellView& A, const double* x, double* y, ui
   }
   uint64_t blocks = ((uint64_t)(hi - lo) + WARPS - 1) / WARPS;
   if (blocks > (uint64_t)c.numSMs) blocks = c.numSMs;
-  const uint32_t rot = g ? g->rot : 0u, nInt = g ? g->nInterior : 0u;
+  const idx_t rot = g ? g->rot : 0u, nInt = g ? g->nInterior : 0u;
   const HaloGate gate = g ? g->gate : HaloGate();
   if (dot)
     launchPdl(spmvSell32TmaKernel<true, WARPS, J, S, U, LOCKSTEP, GATED>, dim3((unsigned)blocks), dim3(WARPS * 32), smem, s, A, x, y, lo,
@@ -271,11 +280,11 @@ static void launchSell32TmaCfg(const SellView& A, const double* x, double* y, ui
         dot->push ? *dot->push : PeerReduce());
   else
     launchPdl(spmvSell32TmaKernel<false, WARPS, J, S, U, LOCKSTEP, GATED>, dim3((unsigned)blocks), dim3(WARPS * 32), smem, s, A, x, y, lo,
-        hi, (double*)nullptr, (unsigned int*)nullptr, (double*)nullptr, false, rot, nInt, gate, PeerReduce());
+        hi, (real_t*)nullptr, (unsigned int*)nullptr, (real_t*)nullptr, false, rot, nInt, gate, PeerReduce());
   countLaunch();
 }
 
-static void launchSell32Tma(const SellView& A, const double* x, double* y, uint32_t lo, uint32_t hi, const DotArgs* dot,
+static void launchSell32Tma(const SellView& A, const real_t* x, real_t* y, idx_t lo, idx_t hi, const DotArgs* dot,
     const SellGate* g, cudaStream_t s)
 {
   if (g) {
@@ -298,24 +307,24 @@ constexpr int kSellUnroll = 8;
 
 template <bool DOT>
 __global__ void __launch_bounds__(256, 4)
-spmvSell32Kernel(SellView A, const double* __restrict__ x, double* __restrict__ y, uint32_t lo, uint32_t hi,
-    double* partials, unsigned int* ticket, double* dotOut, bool accumulate)
+spmvSell32Kernel(SellView A, const real_t* __restrict__ x, real_t* __restrict__ y, idx_t lo, idx_t hi,
+    real_t* partials, unsigned int* ticket, real_t* dotOut, bool accumulate)
 {
-  __shared__ double scratch[32];
+  __shared__ real_t scratch[32];
   const int lane = threadIdx.x & 31;
-  const uint32_t warpsPerBlock = blockDim.x >> 5;
-  double dotAcc = 0.0;
+  const idx_t warpsPerBlock = blockDim.x >> 5;
+  real_t dotAcc = 0.0;
   for (uint64_t chunk = (uint64_t)lo + blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); chunk < hi;
        chunk += (uint64_t)gridDim.x * warpsPerBlock) {
     const uint64_t base = (uint64_t)A.chunkPtr[chunk] + lane;
-    const uint32_t len = A.chunkLens[chunk];
-    const double* __restrict__ v = A.val + base;
-    const uint32_t* __restrict__ c = A.col + base;
-    double sum = 0.0;
-    uint32_t j = 0;
+    const idx_t len = A.chunkLens[chunk];
+    const real_t* __restrict__ v = A.val + base;
+    const idx_t* __restrict__ c = A.col + base;
+    real_t sum = 0.0;
+    idx_t j = 0;
     for (; j + kSellUnroll <= len; j += kSellUnroll) {
-      uint32_t cc[kSellUnroll];
-      double vv[kSellUnroll], xx[kSellUnroll];
+      idx_t cc[kSellUnroll];
+      real_t vv[kSellUnroll], xx[kSellUnroll];
 #pragma unroll
       for (int u = 0; u < kSellUnroll; u++) {
         cc[u] = ldStream(c + (uint64_t)(j + u) * 32);
@@ -327,8 +336,8 @@ spmvSell32Kernel(SellView A, const double* __restrict__ x, double* __restrict__ 
       for (int u = 0; u < kSellUnroll; u++) sum = mulAdd(sum, vv[u], xx[u]);
     }
     if (j < len) {   // tail of the chunk: same batch, predicated (len is warp-uniform)
-      uint32_t cc[kSellUnroll];
-      double vv[kSellUnroll], xx[kSellUnroll];
+      idx_t cc[kSellUnroll];
+      real_t vv[kSellUnroll], xx[kSellUnroll];
 #pragma unroll
       for (int u = 0; u < kSellUnroll; u++)
         if (j + u < len) {
@@ -347,7 +356,7 @@ spmvSell32Kernel(SellView A, const double* __restrict__ x, double* __restrict__ 
     if (DOT && row < A.nr) dotAcc = fma(sum, __ldg(x + row), dotAcc);
   }
   if (DOT) {
-    const double b = blockSum(dotAcc, scratch);
+    const real_t b = blockSum(dotAcc, scratch);
     gridSum(b, partials, ticket, dotOut, accumulate, scratch);
   }
 }
@@ -356,19 +365,19 @@ spmvSell32Kernel(SellView A, const double* __restrict__ x, double* __restrict__ 
 // per-row summation order. Correctness path, not tuned.
 template <bool DOT>
 __global__ void __launch_bounds__(256)
-spmvSellAnyCKernel(SellView A, const double* __restrict__ x, double* __restrict__ y, uint32_t lo, uint32_t hi,
-    double* partials, unsigned int* ticket, double* dotOut, bool accumulate)
+spmvSellAnyCKernel(SellView A, const real_t* __restrict__ x, real_t* __restrict__ y, idx_t lo, idx_t hi,
+    real_t* partials, unsigned int* ticket, real_t* dotOut, bool accumulate)
 {
-  __shared__ double scratch[32];
-  double dotAcc = 0.0;
+  __shared__ real_t scratch[32];
+  real_t dotAcc = 0.0;
   const uint64_t rowLo = (uint64_t)lo * A.C, rowHi = (uint64_t)hi * A.C;
   for (uint64_t row = rowLo + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; row < rowHi;
        row += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t chunk = row / A.C;
     const uint64_t base = (uint64_t)A.chunkPtr[chunk] + row % A.C;
-    const uint32_t len = A.chunkLens[chunk];
-    double sum = 0.0;
-    for (uint32_t j = 0; j < len; j++) {
+    const idx_t len = A.chunkLens[chunk];
+    real_t sum = 0.0;
+    for (idx_t j = 0; j < len; j++) {
       const uint64_t e = base + (uint64_t)j * A.C;
       sum = mulAdd(sum, A.val[e], __ldg(x + A.col[e]));
     }
@@ -376,7 +385,7 @@ spmvSellAnyCKernel(SellView A, const double* __restrict__ x, double* __restrict_
     if (DOT && row < A.nr) dotAcc = fma(sum, __ldg(x + row), dotAcc);
   }
   if (DOT) {
-    const double b = blockSum(dotAcc, scratch);
+    const real_t b = blockSum(dotAcc, scratch);
     gridSum(b, partials, ticket, dotOut, accumulate, scratch);
   }
 }
@@ -389,42 +398,47 @@ spmvSellAnyCKernel(SellView A, const double* __restrict__ x, double* __restrict_
 // with xor-shuffles. The global stream is perfectly coalesced whatever the row lengths are, consumers never
 // touch rowPtr/col/val in global memory, and the number of consumer warps is independent of the bytes in
 // flight. Tiles whose non-zeros do not fit a stage are read straight from global memory by the same lanes.
-constexpr uint32_t kPipeMaxRows = 768;                  // row pointers per stage
+constexpr uint32_t kPipeMaxRows = 768;               // row pointers per stage
 // fused dot: the tile's own x entries are staged behind the ring, one slot of kPipeXBytes per stage
-constexpr uint32_t kPipeXBytes = (kPipeMaxRows + 8) * 8;
+constexpr uint32_t kPipeXBytes = (kPipeMaxRows + 8) * sizeof(real_t);
+constexpr uint64_t kXAlign = 16 / sizeof(real_t);     // bulk copies move multiples of 16 bytes from 16-byte aligned addresses
 
 template <int WARPS, uint32_t CAP, uint32_t STAGES>
 struct CrsPipe {                                        // stage: val[CAP+8] | col[CAP+8] | rowPtr[kPipeMaxRows+8]
   static constexpr int kWarps = WARPS;                  // consumer warps (+1 producer warp)
   static constexpr uint32_t kCap = CAP, kStages = STAGES;
-  static constexpr uint32_t kColOff = (CAP + 8) * 8, kRpOff = (CAP + 8) * 12, kBytes = kRpOff + (kPipeMaxRows + 8) * 4;
-  const uint32_t* col;
-  const double* val;
+  static constexpr uint32_t kColOff = (CAP + 8) * sizeof(real_t), kRpOff = kColOff + (CAP + 8) * sizeof(idx_t),
+                            kBytes = kRpOff + (kPipeMaxRows + 8) * sizeof(idx_t);
+  const idx_t* col;
+  const real_t* val;
   // elements [s, e) -> shared; bulk copies need 16-byte granularity, so the range is widened to multiples of 4
   __device__ __forceinline__ static uint64_t origin(uint64_t s) { return s & ~3ull; }
-  __device__ __forceinline__ static uint32_t bytes(uint64_t s, uint64_t e) { return (uint32_t)(((e + 3) & ~3ull) - (s & ~3ull)) * 12; }
+  __device__ __forceinline__ static uint32_t bytes(uint64_t s, uint64_t e)
+  {
+    return (uint32_t)(((e + 3) & ~3ull) - (s & ~3ull)) * (uint32_t)(sizeof(real_t) + sizeof(idx_t));
+  }
   __device__ __forceinline__ void request(unsigned char* dst, uint64_t s, uint64_t e, uint64_t* bar) const
   {
     const uint64_t a = s & ~3ull;
     const uint32_t n = (uint32_t)(((e + 3) & ~3ull) - a);
-    bulkLoad(dst, val + a, n * 8, bar);
-    bulkLoad(dst + kColOff, col + a, n * 4, bar);
+    bulkLoad(dst, val + a, n * (uint32_t)sizeof(real_t), bar);
+    bulkLoad(dst + kColOff, col + a, n * (uint32_t)sizeof(idx_t), bar);
   }
   static constexpr bool kSplitFetch = true;             // column ids first: they die once their gather is issued
-  __device__ __forceinline__ static void fetch(const unsigned char* st, uint32_t i, uint32_t& c, double& v)
+  __device__ __forceinline__ static void fetch(const unsigned char* st, uint32_t i, idx_t& c, real_t& v)
   {
-    v = reinterpret_cast<const double*>(st)[i];
-    c = reinterpret_cast<const uint32_t*>(st + kColOff)[i];
+    v = reinterpret_cast<const real_t*>(st)[i];
+    c = reinterpret_cast<const idx_t*>(st + kColOff)[i];
   }
-  __device__ __forceinline__ static uint32_t fetchCol(const unsigned char* st, uint32_t i)
+  __device__ __forceinline__ static idx_t fetchCol(const unsigned char* st, uint32_t i)
   {
-    return reinterpret_cast<const uint32_t*>(st + kColOff)[i];
+    return reinterpret_cast<const idx_t*>(st + kColOff)[i];
   }
-  __device__ __forceinline__ static double fetchVal(const unsigned char* st, uint32_t i)
+  __device__ __forceinline__ static real_t fetchVal(const unsigned char* st, uint32_t i)
   {
-    return reinterpret_cast<const double*>(st)[i];
+    return reinterpret_cast<const real_t*>(st)[i];
   }
-  __device__ __forceinline__ void fetchGlobal(uint64_t j, uint32_t& c, double& v) const
+  __device__ __forceinline__ void fetchGlobal(uint64_t j, idx_t& c, real_t& v) const
   {
     c = ldStream(col + j);
     v = ldStream(val + j);
@@ -432,37 +446,48 @@ struct CrsPipe {                                        // stage: val[CAP+8] | c
 };
 
 template <int WARPS, uint32_t CAP, uint32_t STAGES>
-struct CcrsPipe {                                       // stage: {col, pad, val}[CAP] | rowPtr[kPipeMaxRows+8]
+struct CcrsPipe {                                       // stage: {col, (pad,) val}[CAP] | rowPtr[kPipeMaxRows+8]
   static constexpr int kWarps = WARPS;
   static constexpr uint32_t kCap = CAP, kStages = STAGES;
-  static constexpr uint32_t kRpOff = CAP * 16, kBytes = kRpOff + (kPipeMaxRows + 8) * 4;
+  static constexpr uint32_t kRec = sizeof(Entry);       // 16 bytes (8 for float values with 32-bit ids)
+  static constexpr uint64_t kAlign = 16 / kRec;         // records per 16 bytes: granularity of the bulk copies
+  static constexpr uint32_t kRpOff = CAP * kRec, kBytes = kRpOff + (kPipeMaxRows + 8) * sizeof(idx_t);
   const Entry* entries;
-  __device__ __forceinline__ static uint64_t origin(uint64_t s) { return s; }
-  __device__ __forceinline__ static uint32_t bytes(uint64_t s, uint64_t e) { return (uint32_t)(e - s) * 16; }
+  __device__ __forceinline__ static uint64_t origin(uint64_t s) { return s & ~(kAlign - 1); }
+  __device__ __forceinline__ static uint32_t bytes(uint64_t s, uint64_t e)
+  {
+    return (uint32_t)(((e + kAlign - 1) & ~(kAlign - 1)) - origin(s)) * kRec;
+  }
   __device__ __forceinline__ void request(unsigned char* dst, uint64_t s, uint64_t e, uint64_t* bar) const
   {
-    bulkLoad(dst, entries + s, (uint32_t)(e - s) * 16, bar);
+    bulkLoad(dst, entries + origin(s), bytes(s, e), bar);
   }
   static constexpr bool kSplitFetch = false;            // one LDS.128 per record beats two narrower reads
-  __device__ __forceinline__ static void fetch(const unsigned char* st, uint32_t i, uint32_t& c, double& v)
+  __device__ __forceinline__ static Entry record(const unsigned char* st, uint32_t i)
   {
-    const double2 e = reinterpret_cast<const double2*>(st)[i];   // one 16-byte {col, pad, val} record
-    c = (uint32_t)__double_as_longlong(e.x);
-    v = e.y;
+    Entry e;
+    if constexpr (kRec == 16) {
+      const uint4 r = reinterpret_cast<const uint4*>(st)[i];   // one 16-byte {col, pad, val} record
+      memcpy(&e, &r, 16);
+    } else {
+      const uint2 r = reinterpret_cast<const uint2*>(st)[i];
+      memcpy(&e, &r, 8);
+    }
+    return e;
   }
-  __device__ __forceinline__ static uint32_t fetchCol(const unsigned char* st, uint32_t i)
+  __device__ __forceinline__ static void fetch(const unsigned char* st, uint32_t i, idx_t& c, real_t& v)
   {
-    return reinterpret_cast<const uint32_t*>(st)[4 * i];
+    const Entry e = record(st, i);
+    c = e.col;
+    v = e.val;
   }
-  __device__ __forceinline__ static double fetchVal(const unsigned char* st, uint32_t i)
+  __device__ __forceinline__ static idx_t fetchCol(const unsigned char* st, uint32_t i) { return reinterpret_cast<const Entry*>(st)[i].col; }
+  __device__ __forceinline__ static real_t fetchVal(const unsigned char* st, uint32_t i) { return reinterpret_cast<const Entry*>(st)[i].val; }
+  __device__ __forceinline__ void fetchGlobal(uint64_t j, idx_t& c, real_t& v) const
   {
-    return reinterpret_cast<const double*>(st)[2 * i + 1];
-  }
-  __device__ __forceinline__ void fetchGlobal(uint64_t j, uint32_t& c, double& v) const
-  {
-    const double2 e = ldStream2(reinterpret_cast<const double*>(entries + j));
-    c = (uint32_t)__double_as_longlong(e.x);
-    v = e.y;
+    const Entry e = ldStreamEntry(entries + j);
+    c = e.col;
+    v = e.val;
   }
 };
 
@@ -481,15 +506,15 @@ struct CcrsPipe {                                       // stage: {col, pad, val
 // Defaults (Access::kVar): CRS 12; CCRS 4 (its 16-byte record fetch leaves no registers for the x slots: fused dot +15 % with 8).
 template <bool DOT, int LPR, typename L, bool GATED, int VAR>
 __global__ void __launch_bounds__((L::kWarps + 1) * 32, 1)
-spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __restrict__ x, double* __restrict__ y,
-    uint32_t lo, uint32_t hi, uint32_t tileRows, double* partials, unsigned int* ticket, double* dotOut, bool accumulate,
-    uint32_t intLo, uint32_t intHi, HaloGate gate, PeerReduce push)
+spmvRowsPipeKernel(L acc, const idx_t* __restrict__ rowPtr, const real_t* __restrict__ x, real_t* __restrict__ y,
+    idx_t lo, idx_t hi, idx_t tileRows, real_t* partials, unsigned int* ticket, real_t* dotOut, bool accumulate,
+    idx_t intLo, idx_t intHi, HaloGate gate, PeerReduce push)
 {
   extern __shared__ __align__(128) unsigned char ring[];
-  __shared__ double scratch[32];
+  __shared__ real_t scratch[32];
   __shared__ uint64_t fullBar[L::kStages], emptyBar[L::kStages];
   __shared__ GateSmem gateSmem;
-  constexpr uint32_t S = L::kStages;
+  constexpr idx_t S = L::kStages;
   constexpr int kPipeWarps = L::kWarps;
   constexpr bool EARLYX = (VAR & 1) != 0, ALIGN = (VAR & 2) != 0, XSMEM = (VAR & 8) != 0;
   constexpr int UN = (VAR & 4) ? 7 : 8;                  // slots per lane per batch
@@ -499,7 +524,7 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
   griddepLaunchDependents();
   if (threadIdx.x == 0) {
     if (GATED) gateStore(gateSmem, gate);
-    for (uint32_t s = 0; s < S; s++) {
+    for (idx_t s = 0; s < S; s++) {
       mbarInit(fullBar + s, 1);
       mbarInit(emptyBar + s, kPipeWarps);
     }
@@ -528,25 +553,26 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
     return gated;
   };
 
-  double dotAcc = 0.0;
+  real_t dotAcc = 0.0;
   if (warp == kPipeWarps) {
     // ---- producer: one thread keeps the ring full. The first S tiles are requested before griddepWait(): only the
     // matrix is touched, so the ring fills while the previous kernel drains; their x entries (fused dot) follow it.
     if (lane == 0) {
-      uint32_t i = 0;
+      idx_t i = 0;
       bool waited = false;
       for (uint64_t t = blockIdx.x; t < nTiles; t += gridDim.x, i++) {
-        const uint32_t s = i % S, k = i / S;
+        const idx_t s = i % S, k = i / S;
         if (k > 0 && !waited) {
           griddepWait();
           waited = true;
           if (DOT && XSMEM) {                                  // x entries of the tiles requested so far
-            uint32_t j = 0;
+            idx_t j = 0;
             for (uint64_t t2 = blockIdx.x; j < S && t2 < nTiles; t2 += gridDim.x, j++) {
               uint64_t q0, q1;
               tileRange(t2, q0, q1);
-              const uint64_t ax = q0 & ~1ull;
-              bulkLoadKeep(ring + (size_t)S * L::kBytes + (size_t)j * kPipeXBytes, x + ax, (uint32_t)((q1 - ax + 1) & ~1ull) * 8, fullBar + j);
+              const uint64_t ax = q0 & ~(kXAlign - 1);
+              bulkLoadKeep(ring + (size_t)S * L::kBytes + (size_t)j * kPipeXBytes, x + ax,
+                  (uint32_t)((q1 - ax + kXAlign - 1) & ~(kXAlign - 1)) * (uint32_t)sizeof(real_t), fullBar + j);
             }
           }
         }
@@ -558,23 +584,25 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
         const bool fits = be > bs && be - L::origin(bs) <= L::kCap;
         if (k > 0) mbarWait(emptyBar + s, (k - 1) & 1u);
         unsigned char* dst = ring + (size_t)s * L::kBytes;
-        // fused dot: the tile's own x entries ride along (16-byte granularity: from the even row at or below r0)
-        const uint64_t ax = r0 & ~1ull;
-        const uint32_t nxr = DOT && XSMEM ? (uint32_t)((r1 - ax + 1) & ~1ull) : 0u;
-        mbarExpectTx(fullBar + s, nrp * 4 + nxr * 8 + (fits ? L::bytes(bs, be) : 0u));
-        bulkLoad(dst + L::kRpOff, rowPtr + a, nrp * 4, fullBar + s);
-        if (DOT && XSMEM && waited) bulkLoadKeep(ring + (size_t)S * L::kBytes + (size_t)s * kPipeXBytes, x + ax, nxr * 8, fullBar + s);
+        // fused dot: the tile's own x entries ride along (16-byte granularity: from the aligned row at or below r0)
+        const uint64_t ax = r0 & ~(kXAlign - 1);
+        const uint32_t nxr = DOT && XSMEM ? (uint32_t)((r1 - ax + kXAlign - 1) & ~(kXAlign - 1)) : 0u;
+        mbarExpectTx(fullBar + s, nrp * (uint32_t)sizeof(idx_t) + nxr * (uint32_t)sizeof(real_t) + (fits ? L::bytes(bs, be) : 0u));
+        bulkLoad(dst + L::kRpOff, rowPtr + a, nrp * (uint32_t)sizeof(idx_t), fullBar + s);
+        if (DOT && XSMEM && waited)
+          bulkLoadKeep(ring + (size_t)S * L::kBytes + (size_t)s * kPipeXBytes, x + ax, nxr * (uint32_t)sizeof(real_t), fullBar + s);
         if (fits) acc.request(dst, bs, be, fullBar + s);
       }
       if (!waited) {                                           // fewer than S + 1 tiles: nothing was waited for yet
         griddepWait();
         if (DOT && XSMEM) {
-          uint32_t j = 0;
+          idx_t j = 0;
           for (uint64_t t2 = blockIdx.x; j < S && t2 < nTiles; t2 += gridDim.x, j++) {
             uint64_t q0, q1;
             tileRange(t2, q0, q1);
-            const uint64_t ax = q0 & ~1ull;
-            bulkLoadKeep(ring + (size_t)S * L::kBytes + (size_t)j * kPipeXBytes, x + ax, (uint32_t)((q1 - ax + 1) & ~1ull) * 8, fullBar + j);
+            const uint64_t ax = q0 & ~(kXAlign - 1);
+            bulkLoadKeep(ring + (size_t)S * L::kBytes + (size_t)j * kPipeXBytes, x + ax,
+                (uint32_t)((q1 - ax + kXAlign - 1) & ~(kXAlign - 1)) * (uint32_t)sizeof(real_t), fullBar + j);
           }
         }
       }
@@ -584,12 +612,12 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
     griddepWait();                                             // x (and y) belong to the previous kernels
     const int sub = lane % LPR, grp = lane / LPR;
     bool gatePassed = false;
-    uint32_t i = 0;
+    idx_t i = 0;
     for (uint64_t t = blockIdx.x; t < nTiles; t += gridDim.x, i++) {
-      const uint32_t s = i % S, k = i / S;
+      const idx_t s = i % S, k = i / S;
       uint64_t r0, r1;
       const bool behindGate = tileRange(t, r0, r1);
-      const uint32_t nrows = (uint32_t)(r1 - r0);
+      const idx_t nrows = (idx_t)(r1 - r0);
       if (GATED && behindGate && !gatePassed) {
         if (lane == 0) gateWait(&gateSmem, gate.nsrc);
         __syncwarp();
@@ -597,26 +625,26 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
       }
       mbarWait(fullBar + s, k & 1u);
       const unsigned char* st = ring + (size_t)s * L::kBytes;
-      const uint32_t* rp = reinterpret_cast<const uint32_t*>(st + L::kRpOff) + (uint32_t)(r0 & 3ull);
-      const double* xrow = reinterpret_cast<const double*>(ring + (size_t)S * L::kBytes + (size_t)s * kPipeXBytes) + (uint32_t)(r0 & 1ull);   // x[r0 + i] (DOT && XSMEM only)
+      const idx_t* rp = reinterpret_cast<const idx_t*>(st + L::kRpOff) + (uint32_t)(r0 & 3ull);
+      const real_t* xrow = reinterpret_cast<const real_t*>(ring + (size_t)S * L::kBytes + (size_t)s * kPipeXBytes) + (uint32_t)(r0 & (kXAlign - 1));   // x[r0 + i] (DOT && XSMEM only)
       const uint64_t bs = rp[0], be = rp[nrows];
       const uint64_t org = L::origin(bs);
       const bool fits = be > bs && be - org <= L::kCap;
-      for (uint32_t g0 = warp * GPW; g0 < nrows; g0 += kPipeWarps * GPW) {
-        const uint32_t g = g0 + grp;
+      for (idx_t g0 = warp * GPW; g0 < nrows; g0 += kPipeWarps * GPW) {
+        const idx_t g = g0 + grp;
         const bool live = g < nrows;
-        const uint32_t rs = live ? rp[g] : 0u, re = live ? rp[g + 1] : 0u;
-        double sum = 0.0, xr = 0.0;
+        const idx_t rs = live ? rp[g] : 0u, re = live ? rp[g + 1] : 0u;
+        real_t sum = 0.0, xr = 0.0;
         if (DOT && EARLYX && live && sub == 0) xr = gatherX<GATED>(x + r0 + g);   // in flight together with the gathers below
         if (fits) {
           // lanes without a row get an empty range (0 - org would wrap and alias real entries)
-          const uint32_t first = live ? rs - (uint32_t)org : 0u;
-          const uint32_t end = live ? re - (uint32_t)org : 0u;
-          const uint32_t start = ALIGN ? min((first + (uint32_t)LPR - 1u) & ~((uint32_t)LPR - 1u), end) : first;
-          uint32_t idx = start + sub;
+          const idx_t first = live ? rs - (idx_t)org : 0u;
+          const idx_t end = live ? re - (idx_t)org : 0u;
+          const idx_t start = ALIGN ? min((first + (idx_t)LPR - 1u) & ~((idx_t)LPR - 1u), end) : first;
+          idx_t idx = start + sub;
           bool head = ALIGN && first + sub < start;     // this lane owns one of the leading elements
           do {
-            double vv[UN], xx[UN];
+            real_t vv[UN], xx[UN];
             if constexpr (L::kSplitFetch) {
               if (HEAD && head) xx[0] = gatherX<GATED>(x + L::fetchCol(st, first + sub));
 #pragma unroll
@@ -627,7 +655,7 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
               for (int u = HEAD; u < UN; u++)
                 if (idx + (u - HEAD) * LPR < end) vv[u] = L::fetchVal(st, idx + (u - HEAD) * LPR);
             } else {
-              uint32_t cc[UN];
+              idx_t cc[UN];
               if (HEAD && head) L::fetch(st, first + sub, cc[0], vv[0]);
 #pragma unroll
               for (int u = HEAD; u < UN; u++)
@@ -646,8 +674,8 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
           } while (__any_sync(0xffffffffu, idx < end));
         } else {
           for (uint64_t j = (uint64_t)rs + sub; j < re; j += LPR) {   // oversized tile: straight from global memory
-            uint32_t c;
-            double v;
+            idx_t c;
+            real_t v;
             acc.fetchGlobal(j, c, v);
             sum = mulAdd(sum, v, gatherX<GATED>(x + c));
           }
@@ -664,19 +692,19 @@ spmvRowsPipeKernel(L acc, const uint32_t* __restrict__ rowPtr, const double* __r
     }
   }
   if (DOT) {
-    const double b = blockSum(dotAcc, scratch);
+    const real_t b = blockSum(dotAcc, scratch);
     gridSum(b, partials, ticket, dotOut, accumulate, scratch, push.size ? &push : nullptr);
   }
 }
 
 struct RowsGate {                                     // extra arguments of a gated launch
-  uint32_t intLo, intHi;
+  idx_t intLo, intHi;
   HaloGate gate;
 };
 
 template <int LPR, typename L, bool GATED, int VAR>
-static void launchRowsPipe(L acc, const uint32_t* rowPtr, const double* x, double* y, uint32_t lo, uint32_t hi,
-    uint32_t tileRows, const DotArgs* dot, const RowsGate* g, cudaStream_t s)
+static void launchRowsPipe(L acc, const idx_t* rowPtr, const real_t* x, real_t* y, idx_t lo, idx_t hi,
+    idx_t tileRows, const DotArgs* dot, const RowsGate* g, cudaStream_t s)
 {
   Context& c = ctx();
   const size_t smemPlain = (size_t)L::kStages * L::kBytes;
@@ -691,7 +719,7 @@ static void launchRowsPipe(L acc, const uint32_t* rowPtr, const double* x, doubl
   uint64_t blocks = ((uint64_t)(hi - lo) + tileRows - 1) / tileRows + (GATED ? 2 : 0);
   if (blocks > (uint64_t)c.numSMs) blocks = c.numSMs;
   const int threads = (L::kWarps + 1) * 32;
-  const uint32_t intLo = g ? g->intLo : 0u, intHi = g ? g->intHi : 0u;
+  const idx_t intLo = g ? g->intLo : 0u, intHi = g ? g->intHi : 0u;
   const HaloGate gate = g ? g->gate : HaloGate();
   if (dot)
     launchPdl(spmvRowsPipeKernel<true, LPR, L, GATED, VAR>, dim3((unsigned)blocks), dim3(threads), smem, s, acc, rowPtr, x, y, lo, hi,
@@ -699,21 +727,23 @@ static void launchRowsPipe(L acc, const uint32_t* rowPtr, const double* x, doubl
         dot->push ? *dot->push : PeerReduce());
   else
     launchPdl(spmvRowsPipeKernel<false, LPR, L, GATED, VAR>, dim3((unsigned)blocks), dim3(threads), smem, s, acc, rowPtr, x, y, lo, hi,
-        tileRows, (double*)nullptr, (unsigned int*)nullptr, (double*)nullptr, false, intLo, intHi, gate, PeerReduce());
+        tileRows, (real_t*)nullptr, (unsigned int*)nullptr, (real_t*)nullptr, false, intLo, intHi, gate, PeerReduce());
   countLaunch();
 }
 
 // Register-staged sub-warp kernel (long rows, and the measured baseline): LANES consecutive lanes share a row,
 // partial sums are combined with xor-shuffles.
 struct CrsAccess {
-  const uint32_t* col;
-  const double* val;
+  const idx_t* col;
+  const real_t* val;
   template <int W, uint32_t CAP, uint32_t S> using Pipe = CrsPipe<W, CAP, S>;
   template <typename P> P pipe() const { return P { col, val }; }
-  static constexpr uint32_t kStagesFor3584 = 4, kStagesFor5376 = 3;   // 4 x 46 KB + the x slots of the fused dot
-  static constexpr int kDefaultCfg = 0;                 // 23 consumer warps (+1 producer = 6 warps per scheduler, 80 registers), 3 stages of 66 KB
+  // stages that fit 227 KB next to the x slots of the fused dot: 12 bytes per non-zero (double + u32) -> 4 x 46 KB / 3 x 66 KB
+  static constexpr bool kWide = sizeof(real_t) + sizeof(idx_t) > 12;     // 64-bit indices with double values: 16 bytes per non-zero
+  static constexpr uint32_t kStagesFor3584 = kWide ? 3 : 4, kStagesFor5376 = 3;
+  static constexpr int kDefaultCfg = kWide ? 1 : 0;     // 0: 23 consumer warps (+1 producer = 6 warps per scheduler, 80 registers), 3 stages of 66 KB
   static constexpr int kVar = 12;                       // spmvRowsPipeKernel VAR
-  __device__ __forceinline__ void load(uint64_t j, uint32_t& c, double& v) const
+  __device__ __forceinline__ void load(uint64_t j, idx_t& c, real_t& v) const
   {
     c = ldStream(col + j);
     v = ldStream(val + j);
@@ -723,28 +753,29 @@ struct CcrsAccess {
   const Entry* entries;
   template <int W, uint32_t CAP, uint32_t S> using Pipe = CcrsPipe<W, CAP, S>;
   template <typename P> P pipe() const { return P { entries }; }
+  static constexpr bool kWide = false;
   static constexpr uint32_t kStagesFor3584 = 3, kStagesFor5376 = 2;
   static constexpr int kDefaultCfg = 1;                 // 16 consumer warps, 3 stages of 59 KB (16-byte records)
   static constexpr int kVar = 4;
-  __device__ __forceinline__ void load(uint64_t j, uint32_t& c, double& v) const
+  __device__ __forceinline__ void load(uint64_t j, idx_t& c, real_t& v) const
   {
-    const double2 e = ldStream2(reinterpret_cast<const double*>(entries + j));   // one 16-byte record
-    c = (uint32_t)__double_as_longlong(e.x);
-    v = e.y;
+    const Entry e = ldStreamEntry(entries + j);       // one record
+    c = e.col;
+    v = e.val;
   }
 };
 
 template <int LANES, bool DOT, typename Access>
 __global__ void __launch_bounds__(256, 4)
-spmvRowsKernel(Access acc, const uint32_t* __restrict__ rowPtr, uint32_t nrTotal, const double* __restrict__ x,
-    double* __restrict__ y, uint32_t lo, uint32_t hi, double* partials, unsigned int* ticket, double* dotOut,
+spmvRowsKernel(Access acc, const idx_t* __restrict__ rowPtr, idx_t nrTotal, const real_t* __restrict__ x,
+    real_t* __restrict__ y, idx_t lo, idx_t hi, real_t* partials, unsigned int* ticket, real_t* dotOut,
     bool accumulate)
 {
-  __shared__ double scratch[32];
+  __shared__ real_t scratch[32];
   constexpr int kUnroll = 4;
   const int sub = threadIdx.x % LANES;
-  const uint32_t groupsPerBlock = blockDim.x / LANES;
-  double dotAcc = 0.0;
+  const idx_t groupsPerBlock = blockDim.x / LANES;
+  real_t dotAcc = 0.0;
   for (uint64_t first = (uint64_t)lo + (uint64_t)blockIdx.x * groupsPerBlock; first < hi;
        first += (uint64_t)gridDim.x * groupsPerBlock) {
     const uint64_t row = first + threadIdx.x / LANES;
@@ -754,10 +785,10 @@ spmvRowsKernel(Access acc, const uint32_t* __restrict__ rowPtr, uint32_t nrTotal
       j = (uint64_t)__ldg(rowPtr + row) + sub;
       end = __ldg(rowPtr + row + 1);
     }
-    double sum = 0.0;
+    real_t sum = 0.0;
     while (j < end) {
-      uint32_t cc[kUnroll];
-      double vv[kUnroll], xx[kUnroll];
+      idx_t cc[kUnroll];
+      real_t vv[kUnroll], xx[kUnroll];
 #pragma unroll
       for (int u = 0; u < kUnroll; u++)
         if (j + (uint64_t)u * LANES < end) acc.load(j + (uint64_t)u * LANES, cc[u], vv[u]);
@@ -777,17 +808,17 @@ spmvRowsKernel(Access acc, const uint32_t* __restrict__ rowPtr, uint32_t nrTotal
     }
   }
   if (DOT) {
-    const double b = blockSum(dotAcc, scratch);
+    const real_t b = blockSum(dotAcc, scratch);
     gridSum(b, partials, ticket, dotOut, accumulate, scratch);
   }
 }
 
 template <int LANES, typename Access>
-static void launchRows(Access acc, const uint32_t* rowPtr, uint32_t nr, const double* x, double* y, uint32_t lo,
-    uint32_t hi, const DotArgs* dot, cudaStream_t s)
+static void launchRows(Access acc, const idx_t* rowPtr, idx_t nr, const real_t* x, real_t* y, idx_t lo,
+    idx_t hi, const DotArgs* dot, cudaStream_t s)
 {
   Context& c = ctx();
-  const uint32_t groupsPerBlock = 256 / LANES;
+  const idx_t groupsPerBlock = 256 / LANES;
   uint64_t blocks = ((uint64_t)(hi - lo) + groupsPerBlock - 1) / groupsPerBlock;
   const uint64_t cap = (uint64_t)c.numSMs * 8;
   if (blocks > cap) blocks = cap;
@@ -805,14 +836,14 @@ static void launchRows(Access acc, const uint32_t* rowPtr, uint32_t nr, const do
 // lanes per row ~ avg/7 (one 8-deep batch per row); tile = as many passes of the consumer warps as fit a stage.
 // CRS and CCRS take the same decisions (same CAP), so their row sums are bit-identical to each other.
 template <typename Access, typename P>
-static bool tryRowsPipe(Access acc, const uint32_t* rowPtr, double avg, const double* x, double* y, uint32_t lo, uint32_t hi,
+static bool tryRowsPipe(Access acc, const idx_t* rowPtr, real_t avg, const real_t* x, real_t* y, idx_t lo, idx_t hi,
     const DotArgs* dot, const RowsGate* g, bool probeOnly, cudaStream_t s)
 {
   // every pipe layout has CAP / WARPS = 224 non-zeros per consumer warp and pass: lanes per row = avg / 7
   const int lpr = avg <= 7.0 ? 1 : avg <= 14.0 ? 2 : avg <= 28.0 ? 4 : avg <= 56.0 ? 8 : avg <= 112.0 ? 16 : 32;
-  const uint32_t rowsPerPass = (uint32_t)P::kWarps * (32u / (uint32_t)lpr);
-  const uint32_t fitRows = (uint32_t)((double)P::kCap / (avg > 1.0 ? avg : 1.0));
-  uint32_t tileRows = (fitRows / rowsPerPass) * rowsPerPass;
+  const idx_t rowsPerPass = (idx_t)P::kWarps * (32u / (idx_t)lpr);
+  const idx_t fitRows = (idx_t)((real_t)P::kCap / (avg > 1.0 ? avg : 1.0));
+  idx_t tileRows = (fitRows / rowsPerPass) * rowsPerPass;
   if (tileRows > kPipeMaxRows) tileRows = (kPipeMaxRows / rowsPerPass) * rowsPerPass;
   if (tileRows < rowsPerPass) return false;
   if (probeOnly) return true;
@@ -850,22 +881,22 @@ static bool tryRowsPipe(Access acc, const uint32_t* rowPtr, double avg, const do
 
 // returns false if the pipelined kernel cannot take this matrix (rows too long for a stage)
 template <typename Access>
-static bool launchRowsPipeAuto(Access acc, const uint32_t* rowPtr, uint32_t nr, uint64_t nnz, const double* x, double* y,
-    uint32_t lo, uint32_t hi, const DotArgs* dot, const RowsGate* g, bool probeOnly, cudaStream_t s)
+static bool launchRowsPipeAuto(Access acc, const idx_t* rowPtr, idx_t nr, uint64_t nnz, const real_t* x, real_t* y,
+    idx_t lo, idx_t hi, const DotArgs* dot, const RowsGate* g, bool probeOnly, cudaStream_t s)
 {
-  const double avg = nr ? (double)nnz / (double)nr : 0.0;
+  const real_t avg = nr ? (real_t)nnz / (real_t)nr : 0.0;
   if (useLegacyKernels()) return false;
   static const int cfg = envInt("SB_ROWS_CFG", Access::kDefaultCfg);   // tuning knob, measured in profiles/
-  if (cfg == 1)
+  if (cfg == 1 || Access::kWide)                          // the 5376-element stages do not fit with 16 bytes per non-zero
     return tryRowsPipe<Access, typename Access::template Pipe<16, 3584, Access::kStagesFor3584>>(acc, rowPtr, avg, x, y, lo, hi, dot, g, probeOnly, s);
   return tryRowsPipe<Access, typename Access::template Pipe<23, 5376, Access::kStagesFor5376>>(acc, rowPtr, avg, x, y, lo, hi, dot, g, probeOnly, s);
 }
 
 template <typename Access>
-static void launchRowsAuto(Access acc, const uint32_t* rowPtr, uint32_t nr, uint64_t nnz, const double* x, double* y,
-    uint32_t lo, uint32_t hi, const DotArgs* dot, cudaStream_t s)
+static void launchRowsAuto(Access acc, const idx_t* rowPtr, idx_t nr, uint64_t nnz, const real_t* x, real_t* y,
+    idx_t lo, idx_t hi, const DotArgs* dot, cudaStream_t s)
 {
-  const double avg = nr ? (double)nnz / (double)nr : 0.0;
+  const real_t avg = nr ? (real_t)nnz / (real_t)nr : 0.0;
   if (launchRowsPipeAuto(acc, rowPtr, nr, nnz, x, y, lo, hi, dot, nullptr, false, s)) return;
   if (avg <= 6.0) launchRows<2, Access>(acc, rowPtr, nr, x, y, lo, hi, dot, s);
   else if (avg <= 12.0) launchRows<4, Access>(acc, rowPtr, nr, x, y, lo, hi, dot, s);
@@ -874,25 +905,25 @@ static void launchRowsAuto(Access acc, const uint32_t* rowPtr, uint32_t nr, uint
   else launchRows<32, Access>(acc, rowPtr, nr, x, y, lo, hi, dot, s);
 }
 
-uint32_t spmvUnits(const Operator& A) { return A.fmt == SB_FMT_SCS ? A.sell.nChunks : A.nr; }
+idx_t spmvUnits(const Operator& A) { return A.fmt == SB_FMT_SCS ? A.sell.nChunks : A.nr; }
 
 // ---- interior / boundary split for the overlapped halo exchange (setup: once per converted matrix)
 // one warp per unit; bounds[0] = max(u+1) over halo-touching units u below the middle, bounds[1] = min(u) over
 // those at or above it
-__global__ void haloTouchKernel(Operator A, uint32_t units, uint32_t* bounds)
+__global__ void haloTouchKernel(Operator A, idx_t units, idx_t* bounds)
 {
-  const uint32_t mid = units / 2;
+  const idx_t mid = units / 2;
   const int lane = threadIdx.x & 31;
-  const uint32_t warpsTotal = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < units; u += warpsTotal) {
+  const idx_t warpsTotal = (gridDim.x * blockDim.x) >> 5;
+  for (idx_t u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < units; u += warpsTotal) {
     bool touch = false;
     if (A.fmt == SB_FMT_SCS) {
       const uint64_t b = A.sell.chunkPtr[u], e = b + (uint64_t)A.sell.chunkLens[u] * A.sell.C;
       for (uint64_t j = b + lane; j < e; j += 32) touch |= A.sell.col[j] >= A.nr;
     } else if (A.fmt == SB_FMT_CRS) {
-      for (uint32_t j = A.crs.rowPtr[u] + lane; j < A.crs.rowPtr[u + 1]; j += 32) touch |= A.crs.col[j] >= A.nr;
+      for (idx_t j = A.crs.rowPtr[u] + lane; j < A.crs.rowPtr[u + 1]; j += 32) touch |= A.crs.col[j] >= A.nr;
     } else {
-      for (uint32_t j = A.ccrs.rowPtr[u] + lane; j < A.ccrs.rowPtr[u + 1]; j += 32) touch |= A.ccrs.entries[j].col >= A.nr;
+      for (idx_t j = A.ccrs.rowPtr[u] + lane; j < A.ccrs.rowPtr[u + 1]; j += 32) touch |= A.ccrs.entries[j].col >= A.nr;
     }
     if (__any_sync(0xffffffffu, touch) && lane == 0) {
       if (u < mid) atomicMax(bounds, u + 1);
@@ -901,17 +932,17 @@ __global__ void haloTouchKernel(Operator A, uint32_t units, uint32_t* bounds)
   }
 }
 
-void spmvInteriorUnits(const Operator& A, uint32_t* lo, uint32_t* hi, cudaStream_t s)
+void spmvInteriorUnits(const Operator& A, idx_t* lo, idx_t* hi, cudaStream_t s)
 {
   if (A.split && A.split->valid) {
     *lo = A.split->lo;
     *hi = A.split->hi;
     return;
   }
-  const uint32_t units = spmvUnits(A);
-  uint32_t h[2] = { 0u, units };
+  const idx_t units = spmvUnits(A);
+  idx_t h[2] = { 0u, units };
   if (units > 0) {
-    uint32_t* d = (uint32_t*)sbAllocateDevice(64, 2 * sizeof(uint32_t));
+    idx_t* d = (idx_t*)sbAllocateDevice(64, 2 * sizeof(idx_t));
     SB_CUDA(cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, s));
     haloTouchKernel<<<ctx().numSMs * 8, 256, 0, s>>>(A, units, d);
     SB_CUDA(cudaGetLastError());
@@ -929,11 +960,11 @@ void spmvInteriorUnits(const Operator& A, uint32_t* lo, uint32_t* hi, cudaStream
   }
 }
 
-void launchSpmv(const Operator& A, const double* x, double* y, uint32_t lo, uint32_t hi, const DotArgs* dot,
+void launchSpmv(const Operator& A, const real_t* x, real_t* y, idx_t lo, idx_t hi, const DotArgs* dot,
     cudaStream_t s)
 {
   if (hi <= lo) {
-    if (dot && !dot->accumulate) SB_CUDA(cudaMemsetAsync(dot->out, 0, sizeof(double), s));
+    if (dot && !dot->accumulate) SB_CUDA(cudaMemsetAsync(dot->out, 0, sizeof(real_t), s));
     return;
   }
   Context& c = ctx();
@@ -977,12 +1008,12 @@ bool spmvGatedAvailable(const Operator& A)
   return launchRowsPipeAuto(CcrsAccess { A.ccrs.entries }, A.ccrs.rowPtr, A.nr, A.nnzTrue, nullptr, nullptr, 0, A.nr, nullptr, nullptr, true, nullptr);
 }
 
-void launchSpmvGated(const Operator& A, const double* x, double* y, uint32_t intLo, uint32_t intHi, const HaloGate& gate,
+void launchSpmvGated(const Operator& A, const real_t* x, real_t* y, idx_t intLo, idx_t intHi, const HaloGate& gate,
     const DotArgs* dot, cudaStream_t s)
 {
-  const uint32_t units = spmvUnits(A);
+  const idx_t units = spmvUnits(A);
   if (units == 0) {
-    if (dot && !dot->accumulate) SB_CUDA(cudaMemsetAsync(dot->out, 0, sizeof(double), s));
+    if (dot && !dot->accumulate) SB_CUDA(cudaMemsetAsync(dot->out, 0, sizeof(real_t), s));
     return;
   }
   if (intHi < intLo) intHi = intLo;

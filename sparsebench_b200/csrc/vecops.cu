@@ -20,49 +20,56 @@ static inline int vecGrid(uint64_t n, int perThread)
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// 16 bytes of vector: 2 doubles or 4 floats, moved with one 128-bit access
+constexpr int kVL = 16 / sizeof(real_t);
+struct alignas(16) RVec {
+  real_t v[kVL];
+};
+
 // MODE 0: w = x + beta*y   (alpha == 1, solver.c:24-27)
 // MODE 1: w = alpha*x + y  (beta == 1,  solver.c:29-32)
 // MODE 2: w = alpha*x + beta*y          (solver.c:34-37)
 template <int MODE>
-__device__ __forceinline__ double waxpbyOne(double alpha, double x, double beta, double y)
+__device__ __forceinline__ real_t waxpbyOne(real_t alpha, real_t x, real_t beta, real_t y)
 {
-  if (MODE == 0) return __dadd_rn(x, __dmul_rn(beta, y));
-  if (MODE == 1) return __dadd_rn(__dmul_rn(alpha, x), y);
-  return __dadd_rn(__dmul_rn(alpha, x), __dmul_rn(beta, y));
+  if (MODE == 0) return addRn(x, mulRn(beta, y));
+  if (MODE == 1) return addRn(mulRn(alpha, x), y);
+  return addRn(mulRn(alpha, x), mulRn(beta, y));
 }
 
 // w may alias x or y (the CG calls it in place, CGSolver.c:114,127,128): every element is read before it is
 // written by the same thread, so no __restrict__ here.
 template <int MODE, bool VEC>
 __global__ void __launch_bounds__(kVecThreads)
-waxpbyKernel(uint32_t n, double alpha, const double* x, double beta, const double* y, double* w)
+waxpbyKernel(idx_t n, real_t alpha, const real_t* x, real_t beta, const real_t* y, real_t* w)
 {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (VEC) {
-    const uint64_t n2 = n / 2;
-    const double2* x2 = reinterpret_cast<const double2*>(x);
-    const double2* y2 = reinterpret_cast<const double2*>(y);
-    double2* w2 = reinterpret_cast<double2*>(w);
+    const uint64_t n2 = n / kVL;
+    const RVec* x2 = reinterpret_cast<const RVec*>(x);
+    const RVec* y2 = reinterpret_cast<const RVec*>(y);
+    RVec* w2 = reinterpret_cast<RVec*>(w);
     for (uint64_t i = tid; i < n2; i += stride) {
-      const double2 a = x2[i], b = y2[i];
-      double2 r;
-      r.x = waxpbyOne<MODE>(alpha, a.x, beta, b.x);
-      r.y = waxpbyOne<MODE>(alpha, a.y, beta, b.y);
+      const RVec a = x2[i], b = y2[i];
+      RVec r;
+#pragma unroll
+      for (int c = 0; c < kVL; c++) r.v[c] = waxpbyOne<MODE>(alpha, a.v[c], beta, b.v[c]);
       w2[i] = r;
     }
-    if (tid == 0 && (n & 1u)) w[n - 1] = waxpbyOne<MODE>(alpha, x[n - 1], beta, y[n - 1]);
+    if (tid == 0)
+      for (uint64_t i = n2 * kVL; i < n; i++) w[i] = waxpbyOne<MODE>(alpha, x[i], beta, y[i]);
   } else {
     for (uint64_t i = tid; i < n; i += stride) w[i] = waxpbyOne<MODE>(alpha, x[i], beta, y[i]);
   }
 }
 
-void launchWaxpby(uint32_t n, double alpha, const double* x, double beta, const double* y, double* w, cudaStream_t s)
+void launchWaxpby(idx_t n, real_t alpha, const real_t* x, real_t beta, const real_t* y, real_t* w, cudaStream_t s)
 {
   if (n == 0) return;
   const bool vec = aligned16(x) && aligned16(y) && aligned16(w);
   const int grid = vecGrid(n, vec ? 4 : 2);
-  const int mode = (alpha == 1.0) ? 0 : (beta == 1.0) ? 1 : 2;
+  const int mode = (alpha == (real_t)1.0) ? 0 : (beta == (real_t)1.0) ? 1 : 2;
 #define SB_LAUNCH(M)                                                                        \
   do {                                                                                      \
     if (vec) waxpbyKernel<M, true><<<grid, kVecThreads, 0, s>>>(n, alpha, x, beta, y, w);   \
@@ -76,39 +83,47 @@ void launchWaxpby(uint32_t n, double alpha, const double* x, double beta, const 
   countLaunch();
 }
 
+// per-lane partial sums of a thread -> one value, fixed order ((0+1)+(2+3))
+__device__ __forceinline__ real_t sumLanes(const real_t (&part)[kVL])
+{
+  if (kVL == 2) return part[0] + part[1];
+  return (part[0] + part[1]) + (part[kVL - 2] + part[kVL - 1]);
+}
+
 template <bool VEC>
 __global__ void __launch_bounds__(kVecThreads)
-dotKernel(uint32_t n, const double* __restrict__ x, const double* __restrict__ y, double* partials, unsigned int* ticket,
-    double* out)
+dotKernel(idx_t n, const real_t* __restrict__ x, const real_t* __restrict__ y, real_t* partials, unsigned int* ticket,
+    real_t* out)
 {
-  __shared__ double scratch[32];
+  __shared__ real_t scratch[32];
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  double acc = 0.0;
+  real_t acc = 0.0;
   if (VEC) {
-    const uint64_t n2 = n / 2;
-    const double2* x2 = reinterpret_cast<const double2*>(x);
-    const double2* y2 = reinterpret_cast<const double2*>(y);
-    double a0 = 0.0, a1 = 0.0;
+    const uint64_t n2 = n / kVL;
+    const RVec* x2 = reinterpret_cast<const RVec*>(x);
+    const RVec* y2 = reinterpret_cast<const RVec*>(y);
+    real_t part[kVL] = {};
     for (uint64_t i = tid; i < n2; i += stride) {
-      const double2 a = x2[i], b = y2[i];
-      a0 = fma(a.x, b.x, a0);
-      a1 = fma(a.y, b.y, a1);
+      const RVec a = x2[i], b = y2[i];
+#pragma unroll
+      for (int c = 0; c < kVL; c++) part[c] = fma(a.v[c], b.v[c], part[c]);
     }
-    acc = a0 + a1;
-    if (tid == 0 && (n & 1u)) acc = fma(x[n - 1], y[n - 1], acc);
+    acc = sumLanes(part);
+    if (tid == 0)
+      for (uint64_t i = n2 * kVL; i < n; i++) acc = fma(x[i], y[i], acc);
   } else {
     for (uint64_t i = tid; i < n; i += stride) acc = fma(x[i], y[i], acc);
   }
-  const double b = blockSum(acc, scratch);
+  const real_t b = blockSum(acc, scratch);
   gridSum(b, partials, ticket, out, false, scratch);
 }
 
-void launchDot(uint32_t n, const double* x, const double* y, double* dResult, int slot, cudaStream_t s)
+void launchDot(idx_t n, const real_t* x, const real_t* y, real_t* dResult, int slot, cudaStream_t s)
 {
   Context& c = ctx();
   if (n == 0) {
-    SB_CUDA(cudaMemsetAsync(dResult, 0, sizeof(double), s));
+    SB_CUDA(cudaMemsetAsync(dResult, 0, sizeof(real_t), s));
     return;
   }
   const bool vec = aligned16(x) && aligned16(y);
@@ -139,42 +154,51 @@ __device__ __forceinline__ uint64_t l2EvictLastPolicy()
   return policy;
 }
 template <bool KEEP>
-__device__ __forceinline__ double2 ldVec(const double2* p, uint64_t policy)
+__device__ __forceinline__ RVec ldVec(const RVec* p, uint64_t policy)
 {
   if (!KEEP) return *p;
-  double2 v;
-  asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(policy) : "memory");
+  uint4 raw;
+  asm volatile("ld.global.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w)
+               : "l"(p), "l"(policy)
+               : "memory");
+  RVec v;
+  memcpy(&v, &raw, 16);
   return v;
 }
 template <bool KEEP>
-__device__ __forceinline__ void stVec(double2* p, double2 v, uint64_t policy)
+__device__ __forceinline__ void stVec(RVec* p, const RVec& v, uint64_t policy)
 {
   if (!KEEP) {
     *p = v;
     return;
   }
-  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(policy) : "memory");
+  uint4 raw;
+  memcpy(&raw, &v, 16);
+  asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(raw.x), "r"(raw.y), "r"(raw.z), "r"(raw.w),
+               "l"(policy)
+               : "memory");
 }
 // all CG vectors (r, p, Ap, x, b) of this size fit L2 with room for the stream
-static inline bool vectorsFitL2(uint32_t n)
+static inline bool vectorsFitL2(idx_t n)
 {
   static const int knob = getenv("SB_VEC_KEEP") ? atoi(getenv("SB_VEC_KEEP")) : 1;
-  return knob != 0 && (uint64_t)n * 8 * 5 <= ((uint64_t)96 << 20);
+  return knob != 0 && (uint64_t)n * sizeof(real_t) * 5 <= ((uint64_t)96 << 20);
 }
 
 // p = r + beta*p with beta = rho[k-1]/rho[k-2]  (CGSolver.c:111-114); k == 1: p = r + 0*r (:109).
 template <bool KEEP>
 __global__ void __launch_bounds__(kVecThreads)
-cgUpdatePKernel(uint32_t n, int k, double* rho, const double* __restrict__ r, double* __restrict__ p, PeerReduce collectRho,
-    FusedPut put, double* hostRho)
+cgUpdatePKernel(idx_t n, int k, real_t* rho, const real_t* __restrict__ r, real_t* __restrict__ p, PeerReduce collectRho,
+    FusedPut put, real_t* hostRho)
 {
-  __shared__ double peerVals[kMaxRanks];
+  __shared__ real_t peerVals[kMaxRanks];
   __shared__ unsigned int delivered[kMaxFusedDests];     // halo elements this block stored at each neighbour
   griddepLaunchDependents();
   griddepWait();
   if (put.ndest > 0 && threadIdx.x < kMaxFusedDests) delivered[threadIdx.x] = 0;
   // multi-GPU: a freshly computed p[e] that a neighbour needs goes straight behind that neighbour's local rows
-  auto deliver = [&](uint32_t e, double v) {
+  auto deliver = [&](idx_t e, real_t v) {
 #pragma unroll
     for (int d = 0; d < kMaxFusedDests; d++)
       if (d < put.ndest && e >= put.lo[d] && e <= put.hi[d]) {
@@ -187,28 +211,28 @@ cgUpdatePKernel(uint32_t n, int k, double* rho, const double* __restrict__ r, do
   };
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  const uint64_t n2 = n / 2;
-  const double2* r2 = reinterpret_cast<const double2*>(r);
-  double2* p2 = reinterpret_cast<double2*>(p);
+  const uint64_t n2 = n / kVL;
+  const RVec* r2 = reinterpret_cast<const RVec*>(r);
+  RVec* p2 = reinterpret_cast<RVec*>(p);
   const uint64_t keep = KEEP ? l2EvictLastPolicy() : 0;
   // multi-GPU: rho[k-1] was pushed to the peer windows by the previous x/r update; sum it here (every block gets
   // the same bits) and let one thread store the global value for the host's convergence test
-  double rtrans = 0.0;
+  real_t rtrans = 0.0;
   if (k > 1) {
     if (collectRho.size > 0) {
       rtrans = peerCollect(collectRho, peerVals);
       if (tid == 0) {
         rho[k - 1] = rtrans;
-        if (hostRho) *(volatile double*)(hostRho + k - 1) = rtrans;   // the global value, for the host's convergence test
+        if (hostRho) *(volatile real_t*)(hostRho + k - 1) = rtrans;   // the global value, for the host's convergence test
       }
     } else {
       rtrans = rho[k - 1];
     }
   }
   // k == 1: p = r + 0*r, i.e. beta = 0 applied to r itself (waxpby(1, r, 0, r, p))
-  const double beta = k == 1 ? 0.0 : __ddiv_rn(rtrans, rho[k - 2]);
+  const real_t beta = k == 1 ? (real_t)0.0 : divRn(rtrans, rho[k - 2]);
   for (uint64_t i0 = tid; i0 < n2; i0 += kVecUnroll * stride) {
-    double2 a[kVecUnroll], b[kVecUnroll];
+    RVec a[kVecUnroll], b[kVecUnroll];
 #pragma unroll
     for (int u = 0; u < kVecUnroll; u++)
       if (i0 + u * stride < n2) {
@@ -218,22 +242,23 @@ cgUpdatePKernel(uint32_t n, int k, double* rho, const double* __restrict__ r, do
 #pragma unroll
     for (int u = 0; u < kVecUnroll; u++)
       if (i0 + u * stride < n2) {
-        double2 o;
-        o.x = __dadd_rn(a[u].x, __dmul_rn(beta, b[u].x));
-        o.y = __dadd_rn(a[u].y, __dmul_rn(beta, b[u].y));
+        RVec o;
+#pragma unroll
+        for (int c = 0; c < kVL; c++) o.v[c] = addRn(a[u].v[c], mulRn(beta, b[u].v[c]));
         stVec<KEEP>(p2 + i0 + u * stride, o, keep);
         if (put.ndest > 0) {
-          const uint32_t e = (uint32_t)(2 * (i0 + u * stride));
-          deliver(e, o.x);
-          deliver(e + 1, o.y);
+          const idx_t e = (idx_t)(kVL * (i0 + u * stride));
+#pragma unroll
+          for (int c = 0; c < kVL; c++) deliver(e + c, o.v[c]);
         }
       }
   }
-  if (tid == 0 && (n & 1u)) {
-    const double v = __dadd_rn(r[n - 1], __dmul_rn(beta, k == 1 ? r[n - 1] : p[n - 1]));
-    p[n - 1] = v;
-    if (put.ndest > 0) deliver(n - 1, v);
-  }
+  if (tid == 0)
+    for (uint64_t i = n2 * kVL; i < n; i++) {
+      const real_t v = addRn(r[i], mulRn(beta, k == 1 ? r[i] : p[i]));
+      p[i] = v;
+      if (put.ndest > 0) deliver((idx_t)i, v);
+    }
   if (put.ndest > 0) {
     // the barrier orders every thread's peer stores before the signalling threads' release (system scope)
     __syncthreads();
@@ -248,34 +273,34 @@ cgUpdatePKernel(uint32_t n, int k, double* rho, const double* __restrict__ r, do
 // next iteration, which reads the same r)
 template <bool KEEP>
 __global__ void __launch_bounds__(kVecThreads)
-cgUpdateXRKernel(uint32_t n, int k, double* rho, double* pAp, double* __restrict__ x,
-    double* __restrict__ r, const double* __restrict__ p, const double* __restrict__ Ap, double* partials,
-    unsigned int* ticket, PeerReduce collectPAp, PeerReduce pushRho, double* hostRho)
+cgUpdateXRKernel(idx_t n, int k, real_t* rho, real_t* pAp, real_t* __restrict__ x,
+    real_t* __restrict__ r, const real_t* __restrict__ p, const real_t* __restrict__ Ap, real_t* partials,
+    unsigned int* ticket, PeerReduce collectPAp, PeerReduce pushRho, real_t* hostRho)
 {
-  __shared__ double scratch[32];
-  __shared__ double peerVals[kMaxRanks];
+  __shared__ real_t scratch[32];
+  __shared__ real_t peerVals[kMaxRanks];
   griddepLaunchDependents();
   griddepWait();
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  double pApK;
+  real_t pApK;
   if (collectPAp.size > 0) {                         // multi-GPU: p.Ap was pushed to the peer windows by the SpMV
     pApK = peerCollect(collectPAp, peerVals);
     if (tid == 0) pAp[k] = pApK;
   } else {
     pApK = pAp[k];
   }
-  const double alpha = __ddiv_rn(rho[k - 1], pApK);
-  const double nalpha = -alpha;
-  const uint64_t n2 = n / 2;
-  double2* x2 = reinterpret_cast<double2*>(x);
-  double2* r2 = reinterpret_cast<double2*>(r);
-  const double2* p2 = reinterpret_cast<const double2*>(p);
-  const double2* q2 = reinterpret_cast<const double2*>(Ap);
+  const real_t alpha = divRn(rho[k - 1], pApK);
+  const real_t nalpha = -alpha;
+  const uint64_t n2 = n / kVL;
+  RVec* x2 = reinterpret_cast<RVec*>(x);
+  RVec* r2 = reinterpret_cast<RVec*>(r);
+  const RVec* p2 = reinterpret_cast<const RVec*>(p);
+  const RVec* q2 = reinterpret_cast<const RVec*>(Ap);
   const uint64_t keep = KEEP ? l2EvictLastPolicy() : 0;
-  double a0 = 0.0, a1 = 0.0;
+  real_t part[kVL] = {};
   for (uint64_t i0 = tid; i0 < n2; i0 += 2 * stride) {
-    double2 xv[2], pv[2], rv[2], qv[2];
+    RVec xv[2], pv[2], rv[2], qv[2];
 #pragma unroll
     for (int u = 0; u < 2; u++)
       if (i0 + u * stride < n2) {
@@ -287,69 +312,69 @@ cgUpdateXRKernel(uint32_t n, int k, double* rho, double* pAp, double* __restrict
 #pragma unroll
     for (int u = 0; u < 2; u++)
       if (i0 + u * stride < n2) {
-        double2 xo, ro;
-        xo.x = __dadd_rn(xv[u].x, __dmul_rn(alpha, pv[u].x));
-        xo.y = __dadd_rn(xv[u].y, __dmul_rn(alpha, pv[u].y));
-        ro.x = __dadd_rn(rv[u].x, __dmul_rn(nalpha, qv[u].x));
-        ro.y = __dadd_rn(rv[u].y, __dmul_rn(nalpha, qv[u].y));
+        RVec xo, ro;
+#pragma unroll
+        for (int c = 0; c < kVL; c++) {
+          xo.v[c] = addRn(xv[u].v[c], mulRn(alpha, pv[u].v[c]));
+          ro.v[c] = addRn(rv[u].v[c], mulRn(nalpha, qv[u].v[c]));
+          part[c] = fma(ro.v[c], ro.v[c], part[c]);
+        }
         stVec<KEEP>(x2 + i0 + u * stride, xo, keep);
         stVec<KEEP>(r2 + i0 + u * stride, ro, keep);
-        a0 = fma(ro.x, ro.x, a0);
-        a1 = fma(ro.y, ro.y, a1);
       }
   }
-  double acc = a0 + a1;
-  if (tid == 0 && (n & 1u)) {
-    const uint32_t i = n - 1;
-    x[i] = __dadd_rn(x[i], __dmul_rn(alpha, p[i]));
-    const double ro = __dadd_rn(r[i], __dmul_rn(nalpha, Ap[i]));
-    r[i] = ro;
-    acc = fma(ro, ro, acc);
-  }
-  const double b = blockSum(acc, scratch);
+  real_t acc = sumLanes(part);
+  if (tid == 0)
+    for (uint64_t i = n2 * kVL; i < n; i++) {
+      x[i] = addRn(x[i], mulRn(alpha, p[i]));
+      const real_t ro = addRn(r[i], mulRn(nalpha, Ap[i]));
+      r[i] = ro;
+      acc = fma(ro, ro, acc);
+    }
+  const real_t b = blockSum(acc, scratch);
   gridSum(b, partials, ticket, rho + k, false, scratch, pushRho.size ? &pushRho : nullptr, hostRho ? hostRho + k : nullptr);
 }
 
-void launchCgUpdateP(uint32_t n, int k, double* rho, const double* r, double* p, const PeerReduce* collectRho,
-    const FusedPut* put, double* hostRho, cudaStream_t s)
+void launchCgUpdateP(idx_t n, int k, real_t* rho, const real_t* r, real_t* p, const PeerReduce* collectRho,
+    const FusedPut* put, real_t* hostRho, cudaStream_t s)
 {
   if (n == 0 && !collectRho) return;
   launchPdl(vectorsFitL2(n) ? cgUpdatePKernel<true> : cgUpdatePKernel<false>, dim3((unsigned)vecGrid(n, 2 * kVecUnroll)),
       dim3(kVecThreads), 0, s, n, k, rho, r, p, collectRho ? *collectRho : PeerReduce(), put ? *put : FusedPut(),
-      collectRho ? hostRho : (double*)nullptr);
+      collectRho ? hostRho : (real_t*)nullptr);
   countLaunch();
 }
 
-void launchCgUpdateXR(uint32_t n, int k, double* rho, double* pAp, double* x, double* r, const double* p,
-    const double* Ap, int slot, const PeerReduce* collectPAp, const PeerReduce* pushRho, double* hostRho, cudaStream_t s)
+void launchCgUpdateXR(idx_t n, int k, real_t* rho, real_t* pAp, real_t* x, real_t* r, const real_t* p,
+    const real_t* Ap, int slot, const PeerReduce* collectPAp, const PeerReduce* pushRho, real_t* hostRho, cudaStream_t s)
 {
   Context& c = ctx();
   if (n == 0 && !collectPAp && !pushRho) {
-    SB_CUDA(cudaMemsetAsync(rho + k, 0, sizeof(double), s));
-    if (hostRho) SB_CUDA(cudaMemcpyAsync(hostRho + k, rho + k, sizeof(double), cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaMemsetAsync(rho + k, 0, sizeof(real_t), s));
+    if (hostRho) SB_CUDA(cudaMemcpyAsync(hostRho + k, rho + k, sizeof(real_t), cudaMemcpyDeviceToHost, s));
     return;
   }
   // with pushRho the local sum is not the global one yet: the next p update publishes that
   launchPdl(vectorsFitL2(n) ? cgUpdateXRKernel<true> : cgUpdateXRKernel<false>, dim3((unsigned)vecGrid(n, 4)), dim3(kVecThreads), 0,
       s, n, k, rho, pAp, x, r, p, Ap,
       c.partials + (size_t)slot * kMaxPartials, c.tickets + slot, collectPAp ? *collectPAp : PeerReduce(),
-      pushRho ? *pushRho : PeerReduce(), pushRho ? (double*)nullptr : hostRho);
+      pushRho ? *pushRho : PeerReduce(), pushRho ? (real_t*)nullptr : hostRho);
   countLaunch();
 }
 
 // ------------------------------------------------------------------------------------------- setup helpers
 // initVectors (CGSolver.c:19-38): x = 0, b = 27 - (rowLen - 1) for generated matrices, else b = 1.
-__global__ void initVectorsKernel(uint32_t n, const uint32_t* __restrict__ rowPtr, const uint32_t* __restrict__ rowLen,
-    int generated, double* __restrict__ x, double* __restrict__ b)
+__global__ void initVectorsKernel(idx_t n, const idx_t* __restrict__ rowPtr, const idx_t* __restrict__ rowLen,
+    int generated, real_t* __restrict__ x, real_t* __restrict__ b)
 {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  for (idx_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int len = rowLen ? (int)rowLen[i] : (int)(rowPtr[i + 1] - rowPtr[i]);
     x[i] = 0.0;
-    b[i] = generated ? 27.0 - (double)(len - 1) : 1.0;
+    b[i] = generated ? 27.0 - (real_t)(len - 1) : 1.0;
   }
 }
 
-void launchInitVectors(uint32_t n, const uint32_t* rowPtr, const uint32_t* rowLen, bool generated, double* x, double* b,
+void launchInitVectors(idx_t n, const idx_t* rowPtr, const idx_t* rowLen, bool generated, real_t* x, real_t* b,
     cudaStream_t s)
 {
   if (n == 0) return;
@@ -359,22 +384,22 @@ void launchInitVectors(uint32_t n, const uint32_t* rowPtr, const uint32_t* rowLe
 }
 
 // out[map[i]] = in[i]  /  out[i] = in[map[i]]  (SELL row permutation of the CG vectors)
-__global__ void scatterKernel(uint32_t n, const uint32_t* __restrict__ map, const double* __restrict__ in, double* __restrict__ out)
+__global__ void scatterKernel(idx_t n, const idx_t* __restrict__ map, const real_t* __restrict__ in, real_t* __restrict__ out)
 {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[map[i]] = in[i];
+  for (idx_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[map[i]] = in[i];
 }
-__global__ void gatherKernel(uint32_t n, const uint32_t* __restrict__ map, const double* __restrict__ in, double* __restrict__ out)
+__global__ void gatherKernel(idx_t n, const idx_t* __restrict__ map, const real_t* __restrict__ in, real_t* __restrict__ out)
 {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = in[map[i]];
+  for (idx_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = in[map[i]];
 }
-void launchScatter(uint32_t n, const uint32_t* map, const double* in, double* out, cudaStream_t s)
+void launchScatter(idx_t n, const idx_t* map, const real_t* in, real_t* out, cudaStream_t s)
 {
   if (n == 0) return;
   scatterKernel<<<vecGrid(n, 1), kVecThreads, 0, s>>>(n, map, in, out);
   SB_CUDA(cudaGetLastError());
   countLaunch();
 }
-void launchGather(uint32_t n, const uint32_t* map, const double* in, double* out, cudaStream_t s)
+void launchGather(idx_t n, const idx_t* map, const real_t* in, real_t* out, cudaStream_t s)
 {
   if (n == 0) return;
   gatherKernel<<<vecGrid(n, 1), kVecThreads, 0, s>>>(n, map, in, out);
@@ -382,11 +407,11 @@ void launchGather(uint32_t n, const uint32_t* map, const double* in, double* out
   countLaunch();
 }
 
-__global__ void permuteIndicesKernel(uint32_t n, const uint32_t* __restrict__ map, const int* __restrict__ in, int* __restrict__ out)
+__global__ void permuteIndicesKernel(idx_t n, const idx_t* __restrict__ map, const int* __restrict__ in, int* __restrict__ out)
 {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = (int)map[in[i]];
+  for (idx_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = (int)map[in[i]];
 }
-void launchPermuteIndices(uint32_t n, const uint32_t* map, const int* in, int* out, cudaStream_t s)
+void launchPermuteIndices(idx_t n, const idx_t* map, const int* in, int* out, cudaStream_t s)
 {
   if (n == 0) return;
   permuteIndicesKernel<<<vecGrid(n, 1), kVecThreads, 0, s>>>(n, map, in, out);
@@ -398,12 +423,12 @@ void launchPermuteIndices(uint32_t n, const uint32_t* map, const int* in, int* o
 // reference loop (CGSolver.c:50-53). Non-negative doubles order like their bit patterns, so the grid maximum is an
 // integer atomicMax.
 __global__ void __launch_bounds__(kVecThreads)
-maxErrKernel(uint32_t n, const double* __restrict__ x, unsigned long long* out)
+maxErrKernel(idx_t n, const real_t* __restrict__ x, unsigned long long* out)
 {
   __shared__ double sm[kVecThreads / 32];
   double m = 0.0;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-    const double d = fabs(x[i] - 1.0);
+    const double d = fabs((double)(real_t)(x[i] - (real_t)1.0));      // CG_FLOAT diff = fabs(x[i] - xexact[i]), CGSolver.c:50
     if (d > m) m = d;
   }
 #pragma unroll
@@ -419,7 +444,7 @@ maxErrKernel(uint32_t n, const double* __restrict__ x, unsigned long long* out)
     atomicMax(out, (unsigned long long)__double_as_longlong(m));
   }
 }
-void launchMaxErr(uint32_t n, const double* x, double* out, cudaStream_t s)
+void launchMaxErr(idx_t n, const real_t* x, double* out, cudaStream_t s)
 {
   SB_CUDA(cudaMemsetAsync(out, 0, sizeof(double), s));
   if (n == 0) return;
@@ -449,9 +474,9 @@ void ddot(const CG_UINT n, const CG_FLOAT* x, const CG_FLOAT* y, CG_FLOAT* resul
   ensureOnDevice(x);
   ensureOnDevice(y);
   launchDot(n, x, y, c.dScalar, 0, c.stream);
-  SB_CUDA(cudaMemcpyAsync(c.hScalar, c.dScalar, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  SB_CUDA(cudaMemcpyAsync(c.hScalar, c.dScalar, sizeof(real_t), cudaMemcpyDeviceToHost, c.stream));
   SB_CUDA(cudaStreamSynchronize(c.stream));
-  double sum = c.hScalar[0];
+  real_t sum = c.hScalar[0];
   commReduction(&sum, SB_SUM);      // solver.c:60
   *result = sum;
 }

@@ -34,6 +34,17 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert not missing, missing
 
 
+@pytest.mark.parametrize("variant", ["f32", "u64", "f32u64"])
+def test_type_variant_libraries_load_and_export_every_declared_symbol(variant):
+    """util.h:35-53 as build variants: same sources, other CG_FLOAT / CG_UINT; loaded RTLD_LOCAL next to the default one"""
+    L = C.CDLL(os.path.join(ROOT, "sparsebench_b200", "libsparsebench_b200_%s.so" % variant))
+    missing = [n for n in declared_symbols() if not hasattr(L, n)]
+    assert not missing, missing
+    for fmt in ("CRS", "SCS", "CCRS"):
+        S = C.CDLL(os.path.join(ROOT, "sparsebench_b200", "libsparsebench_b200_%s_%s.so" % (fmt, variant)))
+        assert all(hasattr(S, n) for n in ("convertMatrix", "spMVM", "solveCG"))
+
+
 @pytest.mark.parametrize("fmt", ["CRS", "SCS", "CCRS"])
 def test_dropin_shims_export_reference_names(fmt):
     S = _lib.load_dropin(fmt)
