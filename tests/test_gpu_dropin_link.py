@@ -147,3 +147,32 @@ def test_reference_driver_spmv_mode(fmt, n):
     # PROFILE's getTimeStamp pair drains the device before and after every call: ~15 us of launch + wake-up per call
     assert per_call_ms <= 1.03 * direct_ms + 0.020, (per_call_ms, direct_ms)
     assert per_call_ms >= 0.9 * direct_ms, (per_call_ms, direct_ms)          # and it really ran the kernel
+
+
+@pytest.mark.parametrize("fmt,variant,tol", [("CRS", "f32", 2e-3), ("SCS", "f32", 2e-3), ("CRS", "u64", 2e-6)])
+def test_reference_driver_of_a_type_variant(fmt, variant, tol):
+    """The unmodified main.c compiled with the reference's type switches (-DPRECISION=1 / -DUINT_TYPE=2, util.h:35-53)
+    and linked against the matching variant library, against the reference's own executable built with the same
+    switches (oracle/_ref/sparseBench-CRS-ref-<v>, run here on the CPU): same lines, same iteration count, residuals
+    equal within the precision's tolerance."""
+    exe = os.path.join(ROOT, "integration", "_build", "sparseBench-%s-B200-%s" % (fmt, variant))
+    ref = os.path.join(ROOT, "oracle", "_ref", "sparseBench-CRS-ref-%s" % variant)
+    if not (os.path.exists(exe) and os.path.exists(ref)):
+        pytest.skip("variant driver / reference executable not built (make -C integration; make -C oracle ref)")
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    args = ["-x", "16", "-y", "16", "-z", "16", "-i", "20"]
+    out = {}
+    for name, cmd in (("ref", [ref] + args), ("b200", [exe] + args)):
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        out[name] = [re.sub(r"and took .*", "and took", ln) for ln in r.stdout.splitlines() if KEEP.match(ln)]
+    assert len(out["ref"]) == len(out["b200"]) >= 12, out
+    first = None
+    for a, b in zip(out["b200"], out["ref"]):
+        assert NUM.split(a) == NUM.split(b), (a, b)
+        for x, y in zip(NUM.findall(a), NUM.findall(b)):
+            fx, fy = float(x), float(y)
+            first = fy if first is None else first
+            assert abs(fx - fy) <= tol * max(abs(fx), abs(fy)) + 1e-5 * tol * first, (a, b)
