@@ -265,6 +265,19 @@ void* sbCGCreate(Comm* comm, Parameter* param, void* matrix, int fmt, SbCGInfo* 
 int sbCGIterate(void* solver, int untilK);
 int sbCGFinish(void* solver, SbCGInfo* info, double loopMs);
 
+/* ---------------------------------------------------------------- the solver types main.c:22 names but never implements
+ * (`-t gmres` prints its name and returns, main.c:217-222; `-t cheb` has no case). No reference behaviour exists; both are
+ * built on the same SpMV kernels, halo exchange and deterministic reductions as the CG.
+ * sbSolveGMRES: restarted GMRES(restart) (classical Gram-Schmidt with fused projections, Givens rotations on the host);
+ *   b / x / history / flags as in sbSolveCG; history[k] = |g_{k+1}| (the Arnoldi residual estimate) after k
+ *   matrix-vector products; stops when it is <= param->eps or after param->itermax - 1 products; returns their number.
+ * sbChebyshevFilter: y = sum_{k<=degree} coef[k] T_k(A~) x (coef == NULL: y = T_degree(A~) x; y == NULL: moments only) and
+ *   moments[k] = x . T_k(A~) x, A~ = (A - c I) / e with c, e from [lambdaMin, lambdaMax] -- the kernel of Chebyshev filter
+ *   diagonalisation / the kernel polynomial method. x, y: nr entries, host or device; moments: degree + 1, host or device. */
+int sbSolveGMRES(Comm* comm, Parameter* param, void* matrix, int fmt, SbCGInfo* info, int restart);
+void sbChebyshevFilter(Comm* comm, void* matrix, int fmt, int degree, double lambdaMin, double lambdaMax, const CG_FLOAT* coef,
+    const CG_FLOAT* x, CG_FLOAT* y, CG_FLOAT* moments);
+
 /* ---------------------------------------------------------------- communication (comm.c) */
 void commInit(Comm* c, int argc, char** argv);                                /* comm.h:48, comm.c:863-878 */
 void commPrintBanner(Comm* c);                                                /* comm.h:59, comm.c:185-274 (one line per rank: GPU instead of CPU affinity) */

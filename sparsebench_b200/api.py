@@ -146,6 +146,10 @@ def lib():
         L.sbCGIterate.restype = C.c_int
         L.sbCGFinish.argtypes = [C.c_void_p, C.POINTER(CGInfo), C.c_double]
         L.sbCGFinish.restype = C.c_int
+        L.sbSolveGMRES.argtypes = [C.POINTER(Comm), C.POINTER(Parameter), C.c_void_p, C.c_int, C.POINTER(CGInfo), C.c_int]
+        L.sbSolveGMRES.restype = C.c_int
+        L.sbChebyshevFilter.argtypes = [C.POINTER(Comm), C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]
         L.commInit.argtypes = [C.POINTER(Comm), C.c_int, C.c_void_p]
         L.commFinalize.argtypes = [C.POINTER(Comm)]
         L.commPartition.argtypes = [C.POINTER(Comm), C.POINTER(GMatrix)]
@@ -373,3 +377,40 @@ def solveCG(m, itermax, eps, comm=None, generated=True, b=None, x=None, flags=CG
             info.x = xo.ctypes.data
     k = lib().sbSolveCG(C.byref(comm), C.byref(p), C.byref(m), m._fmt, C.byref(info))
     return k, hist[:info.nhist].copy(), xo, info
+
+
+# ------------------------------------------------------------------ the solver types main.c:22 only names
+def solveGMRES(m, itermax, eps, restart=30, comm=None, generated=True, b=None, x=None, want_x=False):
+    """Restarted GMRES(restart). Returns (k, history, x_or_None, info); history[j] = residual estimate after j products."""
+    if comm is None:
+        comm = Comm()
+        comm.rank, comm.size = 0, 1
+    p = Parameter(b"generate" if generated else b"matrix.mtx", 0, 0, 0, itermax, eps)
+    info = CGInfo()
+    info.flags = 0
+    hist = np.zeros(itermax + 4)
+    info.history = hist.ctypes.data_as(C.POINTER(C.c_double))
+    info.historyCap = len(hist)
+    keep = []
+    if b is not None:
+        b = vec(b); keep.append(b); info.b = b.ctypes.data
+    xo = None
+    if x is not None or want_x:
+        xo = np.zeros(m.nr, RDT) if x is None else np.array(x, RDT)
+        info.x = xo.ctypes.data
+    k = lib().sbSolveGMRES(C.byref(comm), C.byref(p), C.byref(m), m._fmt, C.byref(info), restart)
+    return k, hist[:info.nhist].copy(), xo, info
+
+
+def chebyshevFilter(m, x, degree, lmin, lmax, coef=None, comm=None, want_y=True):
+    """y = sum_k coef[k] T_k(A~) x (coef None: T_degree) and moments[k] = x . T_k(A~) x. Returns (y_or_None, moments)."""
+    if comm is None:
+        comm = Comm()
+        comm.rank, comm.size = 0, 1
+    xv = vec(x)
+    y = np.zeros(m.nr, RDT) if want_y else None
+    mu = np.zeros(degree + 1, RDT)
+    cf = None if coef is None else vec(coef)
+    lib().sbChebyshevFilter(C.byref(comm), C.byref(m), m._fmt, degree, lmin, lmax, None if cf is None else cf.ctypes.data,
+                            xv.ctypes.data, None if y is None else y.ctypes.data, mu.ctypes.data)
+    return y, mu

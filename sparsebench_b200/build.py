@@ -13,7 +13,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libsparsebench_b200.so")
-SOURCES = ["runtime.cu", "generate.cu", "formats.cu", "spmv.cu", "vecops.cu", "cg.cu", "comm.cu", "partition.cpp", "mmio.cpp"]
+SOURCES = ["runtime.cu", "generate.cu", "formats.cu", "spmv.cu", "vecops.cu", "cg.cu", "krylov.cu", "comm.cu", "partition.cpp", "mmio.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "--extended-lambda", "-Xcompiler", "-fPIC,-fvisibility=default",
               "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]

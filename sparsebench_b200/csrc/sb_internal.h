@@ -178,7 +178,7 @@ struct HaloGate {
 };
 // The same delivery fused into the kernel that produces the values (the CG's p update): element e of the vector
 // goes to position inv[d][e - lo[d]] of destination d's halo (negative: not sent there).
-constexpr int kMaxFusedDests = 4;
+constexpr int kMaxFusedDests = 8;   // up to 8 neighbours per rank: every rank of an 8-GPU box may neighbour all others
 struct FusedPut {
   int ndest = 0;                                           // 0: not in use
   idx_t lo[kMaxFusedDests] = {}, hi[kMaxFusedDests] = {};   // inclusive element range that holds everything sent to d

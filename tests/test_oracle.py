@@ -237,3 +237,24 @@ def test_live_waxpby_ddot():
     res = C.c_double(0)
     L.ddot(1001, x.ctypes.data, y.ctypes.data, C.byref(res))
     assert res.value == orc.ddot(x, y)
+
+
+def test_krylov_restatement_against_dense_math():
+    """oracle/krylov_ref.py (GMRES(m), Chebyshev filter: no reference behaviour exists) against dense linear algebra"""
+    import scipy.sparse as sp
+
+    from oracle import krylov_ref as kr
+    m = orc.generate(6, 5, 4)
+    x0, b, _ = orc.init_vectors(m)
+    for restart in (4, 30):
+        k, h, x = kr.gmres(m, b, x0, 80, 1e-10, restart)
+        assert h[-1] <= 1e-10 and np.max(np.abs(x - 1.0)) <= 1e-9
+        assert abs(np.linalg.norm(b - kr.spmv(m, x)) - h[-1]) <= 1e-9
+        assert len(h) == k + 1 and np.all(np.diff(h) <= 1e-12 * h[0])          # GMRES residuals never grow
+    D = sp.csr_matrix((m.val, m.col.astype(np.int64), m.rowPtr.astype(np.int64)), shape=(m.nr, m.nr)).toarray()
+    xx = 1.0 + 0.01 * np.arange(m.nr)
+    w, Q = np.linalg.eigh((D - 27.0 * np.eye(m.nr)) / 27.0)
+    for degree in (0, 1, 2, 9):
+        y, mu = kr.chebyshev(m, xx, degree, 0.0, 54.0)
+        T = Q @ np.diag(np.cos(degree * np.arccos(np.clip(w, -1, 1)))) @ Q.T
+        assert np.max(np.abs(y - T @ xx)) <= 1e-11 and abs(mu[degree] - xx @ (T @ xx)) <= 1e-10
