@@ -88,6 +88,22 @@ def main():
             k, hist, _, _ = api.solveCG(A, itermax, eps, comm=comm, flags=api.CG_FUSED)
             ok = k == kref and len(hist) == len(href) and float(np.max(np.abs(hist - href) / np.maximum(href, 1e-10 * href[0]))) <= CG_TOL
             check(ok, "%dx%dx%d fmt=%s sigma=%d: interleaved re-solve k=%d/%d" % (nx, ny, nz, api.FMT_NAMES[fmt], sigma, k, kref), failures)
+        if (nx, ny, nz) == (16, 16, 6):
+            # GMRES(m) and the Chebyshev filter on the same partition (no reference behaviour: vs the numpy restatement
+            # of the same algorithms on the global problem, oracle/krylov_ref.py)
+            from oracle import krylov_ref as kr
+            kg, hg, xg = kr.gmres(mg, b, x0, 50, 1e-8, 8)
+            xin = 1.0 + 0.01 * (np.arange(mg.nr) % 13)
+            yc, muc = kr.chebyshev(mg, xin, 9, 0.0, 54.0)
+            for A, (fmt, sigma) in zip(mats, fmts):
+                tag = "%dx%dx%d fmt=%s sigma=%d" % (nx, ny, nz, api.FMT_NAMES[fmt], sigma)
+                k, hist, x, _ = api.solveGMRES(A, 50, 1e-8, restart=8, comm=comm, want_x=True)
+                ok = k == kg and len(hist) == len(hg) and float(np.max(np.abs(hist - hg) / np.maximum(hg, 1e-10 * hg[0]))) <= 1e-7
+                check(ok, "%s: GMRES k=%d/%d" % (tag, k, kg), failures)
+                check(float(np.max(np.abs(x - xg[rank * n:(rank + 1) * n]))) <= 1e-8, "%s: GMRES solution" % tag, failures)
+                y, mu = api.chebyshevFilter(A, xin[rank * n:(rank + 1) * n], 9, 0.0, 54.0, comm=comm)
+                check(float(np.max(np.abs(y - yc[rank * n:(rank + 1) * n]))) <= 1e-11 * float(np.max(np.abs(yc))), "%s: Chebyshev filter" % tag, failures)
+                check(float(np.max(np.abs(mu - muc))) <= 1e-11 * float(np.max(np.abs(muc))), "%s: Chebyshev moments" % tag, failures)
         for A in mats:
             api.destroyMatrix(A)
         L.sbFreeGMatrix(C.byref(g))

@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--ordered", action="store_true")
     ap.add_argument("--dot", action="store_true", help="also time the fused SpMV + dot kernel (sbSpmvDot)")
     ap.add_argument("--cg", type=int, default=0, help="also run this many fused CG iterations")
+    ap.add_argument("--gmres", type=int, default=0, help="also run this many GMRES(30) steps")
+    ap.add_argument("--cheb", type=int, default=0, help="also apply a Chebyshev filter of this degree")
     a = ap.parse_args()
     L = api.lib()
     n, nz = a.n, (a.nz or a.n)
@@ -107,6 +109,20 @@ def main():
         print("cg k=%d residual %.6e  loop %.4f ms/it" % (k, hist[-1], info.solveMs / a.cg))
         k, hist, _, info = api.solveCG(A, a.cg + 1, 0.0, flags=api.CG_FUSED | api.CG_PROFILE)
         print("cg regions ms/it:", {r: round(info.regionMs[i] / a.cg, 4) for i, r in enumerate(api.REGIONS)})
+    if a.gmres:
+        api.solveGMRES(A, 8, 0.0, restart=30)
+        k, hist, _, info = api.solveGMRES(A, a.gmres + 1, 0.0, restart=30)
+        print("gmres(30) k=%d residual %.6e  %.4f ms per step (SpMV + 2 Gram-Schmidt passes over on average %d basis vectors + host Givens)"
+              % (k, hist[-1], info.solveMs / max(k, 1), min(k, 30) // 2))
+    if a.cheb:
+        xh = np.ones(N)
+        api.chebyshevFilter(A, xh, 4, 0.0, 54.0)
+        import time
+        L.sbDeviceSynchronize()
+        t0 = time.perf_counter()
+        _, mu = api.chebyshevFilter(A, xh, a.cheb, 0.0, 54.0, want_y=False)
+        dt = time.perf_counter() - t0
+        print("chebyshev degree %d: %.4f ms per degree incl. upload of x (SpMV + one fused vector pass), mu[-1] = %.6e" % (a.cheb, dt * 1e3 / a.cheb, mu[-1]))
     return 0
 
 
