@@ -46,7 +46,10 @@ def test_gmres_against_the_numpy_restatement(fmt, case):
     k, hist, x, info = api.solveGMRES(A, itermax, eps, restart=restart, generated=generated, b=None if generated else b, want_x=True)
     assert k == kref and len(hist) == len(href)
     scale = np.maximum(href, 1e-10 * href[0])
-    assert float(np.max(np.abs(hist - href) / scale)) <= 1e-7          # classical Gram-Schmidt in another summation order
+    # classical Gram-Schmidt in another summation order; every restart recomputes b - A x, whose round-off floor
+    # (a few ulp of the initial residual) is an ABSOLUTE error, visible once the residual has dropped by 1e8
+    noise = 64 * np.finfo(np.float64).eps * href[0]
+    assert float(np.max((np.abs(hist - href) - noise) / scale)) <= 1e-7
     assert float(np.max(np.abs(x - xref))) <= 1e-8 * max(1.0, float(np.max(np.abs(xref))))
     true = float(np.linalg.norm(b - kr.spmv(m, x.astype(np.float64))))
     assert abs(true - hist[-1]) <= 1e-6 * hist[0] and true <= 10 * eps + 1e-9 * hist[0] or k == itermax - 1
