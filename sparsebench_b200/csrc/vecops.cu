@@ -187,7 +187,9 @@ static inline bool vectorsFitL2(idx_t n)
 }
 
 // p = r + beta*p with beta = rho[k-1]/rho[k-2]  (CGSolver.c:111-114); k == 1: p = r + 0*r (:109).
-template <bool KEEP>
+// PUT: this launch also delivers the halo elements of p to the neighbours (FusedPut); without it the kernel carries
+// none of that code.
+template <bool KEEP, bool PUT>
 __global__ void __launch_bounds__(kVecThreads)
 cgUpdatePKernel(idx_t n, int k, real_t* rho, const real_t* __restrict__ r, real_t* __restrict__ p, PeerReduce collectRho,
     FusedPut put, real_t* hostRho)
@@ -196,12 +198,14 @@ cgUpdatePKernel(idx_t n, int k, real_t* rho, const real_t* __restrict__ r, real_
   __shared__ unsigned int delivered[kMaxFusedDests];     // halo elements this block stored at each neighbour
   griddepLaunchDependents();
   griddepWait();
-  if (put.ndest > 0 && threadIdx.x < kMaxFusedDests) delivered[threadIdx.x] = 0;
+  if (PUT && threadIdx.x < kMaxFusedDests) delivered[threadIdx.x] = 0;
   // multi-GPU: a freshly computed p[e] that a neighbour needs goes straight behind that neighbour's local rows
+  // (a rolled loop over the ACTUAL destinations: unrolled to kMaxFusedDests predicated range tests it cost the
+  // 2-rank p update 6 us of issue slots; the parameter arrays are indexed in the constant bank)
   auto deliver = [&](idx_t e, real_t v) {
-#pragma unroll
-    for (int d = 0; d < kMaxFusedDests; d++)
-      if (d < put.ndest && e >= put.lo[d] && e <= put.hi[d]) {
+#pragma unroll 1
+    for (int d = 0; d < put.ndest; d++)
+      if (e >= put.lo[d] && e <= put.hi[d]) {
         const int pos = __ldg(put.inv[d] + (e - put.lo[d]));
         if (pos >= 0) {
           put.remote[d][pos] = v;
@@ -246,7 +250,7 @@ cgUpdatePKernel(idx_t n, int k, real_t* rho, const real_t* __restrict__ r, real_
 #pragma unroll
         for (int c = 0; c < kVL; c++) o.v[c] = addRn(a[u].v[c], mulRn(beta, b[u].v[c]));
         stVec<KEEP>(p2 + i0 + u * stride, o, keep);
-        if (put.ndest > 0) {
+        if (PUT) {
           const idx_t e = (idx_t)(kVL * (i0 + u * stride));
 #pragma unroll
           for (int c = 0; c < kVL; c++) deliver(e + c, o.v[c]);
@@ -257,9 +261,9 @@ cgUpdatePKernel(idx_t n, int k, real_t* rho, const real_t* __restrict__ r, real_
     for (uint64_t i = n2 * kVL; i < n; i++) {
       const real_t v = addRn(r[i], mulRn(beta, k == 1 ? r[i] : p[i]));
       p[i] = v;
-      if (put.ndest > 0) deliver((idx_t)i, v);
+      if (PUT) deliver((idx_t)i, v);
     }
-  if (put.ndest > 0) {
+  if (PUT) {
     // the barrier orders every thread's peer stores before the signalling threads' release (system scope)
     __syncthreads();
     if ((int)threadIdx.x < put.ndest && delivered[threadIdx.x] > 0)
@@ -339,7 +343,9 @@ void launchCgUpdateP(idx_t n, int k, real_t* rho, const real_t* r, real_t* p, co
     const FusedPut* put, real_t* hostRho, cudaStream_t s)
 {
   if (n == 0 && !collectRho) return;
-  launchPdl(vectorsFitL2(n) ? cgUpdatePKernel<true> : cgUpdatePKernel<false>, dim3((unsigned)vecGrid(n, 2 * kVecUnroll)),
+  const bool keep = vectorsFitL2(n), fused = put && put->ndest > 0;
+  launchPdl(fused ? (keep ? cgUpdatePKernel<true, true> : cgUpdatePKernel<false, true>)
+                  : (keep ? cgUpdatePKernel<true, false> : cgUpdatePKernel<false, false>), dim3((unsigned)vecGrid(n, 2 * kVecUnroll)),
       dim3(kVecThreads), 0, s, n, k, rho, r, p, collectRho ? *collectRho : PeerReduce(), put ? *put : FusedPut(),
       collectRho ? hostRho : (real_t*)nullptr);
   countLaunch();
