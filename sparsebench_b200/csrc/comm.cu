@@ -804,7 +804,9 @@ void commAllreduceDevice(Comm* c, real_t* d, int count, int op, cudaStream_t s)
 {
   CommExt* e = ext(c);
   if (!e) return;
-  if (e->mode == COMM_PEER) {
+  // peer windows: one value per launch (the CG's fused kernels carry their own); a longer vector (the GMRES
+  // projections) goes through one NCCL all-reduce instead of `count` launches
+  if (e->mode == COMM_PEER && count <= 2) {
     for (int i = 0; i < count; i++) {
       e->redEpoch++;
       peerAllreduceKernel<<<1, kMaxRanks, 0, s>>>(e->ctrl, e->dPeerCtrl, e->rank, e->size, e->redEpoch, d + i, op);

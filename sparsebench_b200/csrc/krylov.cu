@@ -40,6 +40,51 @@ struct BasisPtrs {
   const real_t* v[kMaxBasis];
 };
 
+// 16 bytes of a vector (2 doubles / 4 floats): every pass below moves the vectors with 128-bit accesses, two per
+// thread and vector in flight (the buffers come from sbAllocateDevice: 256-byte aligned)
+constexpr int kPL = 16 / sizeof(real_t);
+struct alignas(16) Pack {
+  real_t v[kPL];
+};
+
+// acc[g] += V_{g0+g} . w for G basis vectors in one pass over w
+template <int G>
+__device__ __forceinline__ void dotGroup(idx_t n, const BasisPtrs& V, int g0, const real_t* __restrict__ w, real_t (&acc)[kDotGroup])
+{
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t n2 = n / kPL;
+  const Pack* w2 = reinterpret_cast<const Pack*>(w);
+  const Pack* v2[G];
+#pragma unroll
+  for (int g = 0; g < G; g++) v2[g] = reinterpret_cast<const Pack*>(V.v[g0 + g]);
+  for (uint64_t i = tid; i < n2; i += 2 * stride) {
+    const bool second = i + stride < n2;
+    const uint64_t i1 = second ? i + stride : i;
+    const Pack wa = w2[i], wb = w2[i1];
+    Pack va[G], vb[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      va[g] = v2[g][i];
+      vb[g] = v2[g][i1];
+    }
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+#pragma unroll
+      for (int c = 0; c < kPL; c++) acc[g] = fma(va[g].v[c], wa.v[c], acc[g]);
+      if (second) {
+#pragma unroll
+        for (int c = 0; c < kPL; c++) acc[g] = fma(vb[g].v[c], wb.v[c], acc[g]);
+      }
+    }
+  }
+  if (tid == 0)
+    for (uint64_t i = n2 * kPL; i < n; i++) {
+#pragma unroll
+      for (int g = 0; g < G; g++) acc[g] = fma(V.v[g0 + g][i], w[i], acc[g]);
+    }
+}
+
 // out[i] = V_i . w for i in [0, count): w is read once per group of kDotGroup basis vectors; deterministic: every
 // block deposits its `count` partial sums, the last block adds them in block order.
 __global__ void __launch_bounds__(kThreads)
@@ -47,17 +92,19 @@ multiDotKernel(idx_t n, int count, BasisPtrs V, const real_t* __restrict__ w, re
 {
   __shared__ real_t scratch[32];
   __shared__ bool amLast;
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   for (int g0 = 0; g0 < count; g0 += kDotGroup) {
     real_t acc[kDotGroup];
 #pragma unroll
     for (int g = 0; g < kDotGroup; g++) acc[g] = 0.0;
-    for (uint64_t i = tid; i < n; i += stride) {
-      const real_t wi = w[i];
-#pragma unroll
-      for (int g = 0; g < kDotGroup; g++)
-        if (g0 + g < count) acc[g] = fma(V.v[g0 + g][i], wi, acc[g]);
+    switch (count - g0 < kDotGroup ? count - g0 : kDotGroup) {
+      case 1: dotGroup<1>(n, V, g0, w, acc); break;
+      case 2: dotGroup<2>(n, V, g0, w, acc); break;
+      case 3: dotGroup<3>(n, V, g0, w, acc); break;
+      case 4: dotGroup<4>(n, V, g0, w, acc); break;
+      case 5: dotGroup<5>(n, V, g0, w, acc); break;
+      case 6: dotGroup<6>(n, V, g0, w, acc); break;
+      case 7: dotGroup<7>(n, V, g0, w, acc); break;
+      default: dotGroup<8>(n, V, g0, w, acc); break;
     }
 #pragma unroll
     for (int g = 0; g < kDotGroup; g++) {
@@ -72,16 +119,21 @@ multiDotKernel(idx_t n, int count, BasisPtrs V, const real_t* __restrict__ w, re
   }
   __syncthreads();
   if (amLast) {
+    // one warp per projection: lanes stride over the blocks, fixed shuffle tree (same bits for the same grid)
     __threadfence();
-    for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = warp; i < count; i += kThreads / 32) {
       real_t s = 0.0;
-      for (unsigned int b = 0; b < gridDim.x; b++) s += __ldcg(partials + (size_t)b * kMaxBasis + i);
-      out[i] = s;
+      for (unsigned int b = lane; b < gridDim.x; b += 32) s += __ldcg(partials + (size_t)b * kMaxBasis + i);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+      if (lane == 0) out[i] = s;
     }
   }
 }
 
-// w -= sum_i h[i] V_i  and  *norm2 = w . w  (second half of a classical Gram-Schmidt step)
+// w -= sum_i h[i] V_i  and  *norm2 = w . w  (second half of a classical Gram-Schmidt step); the projections are
+// subtracted one after the other in index order, each product rounded (as the numpy restatement does)
 __global__ void __launch_bounds__(kThreads)
 projectOutKernel(idx_t n, int count, BasisPtrs V, const real_t* __restrict__ h, real_t* __restrict__ w, real_t* partials,
     unsigned int* ticket, real_t* norm2)
@@ -91,13 +143,54 @@ projectOutKernel(idx_t n, int count, BasisPtrs V, const real_t* __restrict__ h, 
   for (int i = threadIdx.x; i < count; i += blockDim.x) hs[i] = h[i];
   __syncthreads();
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t n2 = n / kPL;
+  Pack* w2 = reinterpret_cast<Pack*>(w);
   real_t acc = 0.0;
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
-    real_t wi = w[i];
-    for (int k = 0; k < count; k++) wi = addRn(wi, -mulRn(hs[k], V.v[k][i]));
-    w[i] = wi;
-    acc = fma(wi, wi, acc);
+  for (uint64_t i = tid; i < n2; i += 2 * stride) {
+    const bool second = i + stride < n2;
+    const uint64_t i1 = second ? i + stride : i;
+    Pack wa = w2[i], wb = w2[i1];
+    int k = 0;
+    for (; k + 4 <= count; k += 4) {                        // 8 independent 16-byte loads in flight
+      Pack va[4], vb[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        va[u] = reinterpret_cast<const Pack*>(V.v[k + u])[i];
+        vb[u] = reinterpret_cast<const Pack*>(V.v[k + u])[i1];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int c = 0; c < kPL; c++) {
+          wa.v[c] = addRn(wa.v[c], -mulRn(hs[k + u], va[u].v[c]));
+          wb.v[c] = addRn(wb.v[c], -mulRn(hs[k + u], vb[u].v[c]));
+        }
+    }
+    for (; k < count; k++) {
+      const Pack va = reinterpret_cast<const Pack*>(V.v[k])[i], vb = reinterpret_cast<const Pack*>(V.v[k])[i1];
+#pragma unroll
+      for (int c = 0; c < kPL; c++) {
+        wa.v[c] = addRn(wa.v[c], -mulRn(hs[k], va.v[c]));
+        wb.v[c] = addRn(wb.v[c], -mulRn(hs[k], vb.v[c]));
+      }
+    }
+    w2[i] = wa;
+#pragma unroll
+    for (int c = 0; c < kPL; c++) acc = fma(wa.v[c], wa.v[c], acc);
+    if (second) {
+      w2[i1] = wb;
+#pragma unroll
+      for (int c = 0; c < kPL; c++) acc = fma(wb.v[c], wb.v[c], acc);
+    }
   }
+  if (tid == 0)
+    for (uint64_t i = n2 * kPL; i < n; i++) {
+      real_t wi = w[i];
+      for (int k = 0; k < count; k++) wi = addRn(wi, -mulRn(hs[k], V.v[k][i]));
+      w[i] = wi;
+      acc = fma(wi, wi, acc);
+    }
   const real_t b = blockSum(acc, scratch);
   gridSum(b, partials, ticket, norm2, false, scratch);
 }
@@ -128,20 +221,38 @@ combineKernel(idx_t n, int count, BasisPtrs V, const real_t* __restrict__ y, rea
 // One Chebyshev step after the SpMV q = A t:  tNext = a (q - c t) - tPrev  (a = 2/e, or 1/e for the first step with
 // tPrev ignored),  y += coef * tNext,  *moment = x0 . tNext -- one pass, everything that needs tNext fused.
 __global__ void __launch_bounds__(kThreads)
-chebStepKernel(idx_t n, real_t a, real_t c, int first, const real_t* __restrict__ q, const real_t* __restrict__ t,
-    const real_t* tPrev, real_t* tNext, real_t coef, real_t* __restrict__ y, const real_t* __restrict__ x0, real_t* partials,
+chebStepKernel(idx_t n, real_t a, real_t c, int first, const real_t* __restrict__ q, const real_t* t,
+    const real_t* tPrev, real_t* tNext, real_t coef, real_t* __restrict__ y, const real_t* x0, real_t* partials,
     unsigned int* ticket, real_t* moment)
 {
   __shared__ real_t scratch[32];
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t n2 = n / kPL;
   real_t acc = 0.0;
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
-    real_t v = a * (q[i] - c * t[i]);
-    if (!first) v -= tPrev[i];                              // tNext may alias tPrev: read before written, same thread
-    tNext[i] = v;
-    if (y) y[i] = fma(coef, v, y[i]);
-    acc = fma(x0[i], v, acc);
+  auto step = [&](real_t qi, real_t ti, real_t pi) { return first ? a * (qi - c * ti) : a * (qi - c * ti) - pi; };
+  for (uint64_t i = tid; i < n2; i += stride) {
+    const Pack q2 = reinterpret_cast<const Pack*>(q)[i], t2 = reinterpret_cast<const Pack*>(t)[i];
+    const Pack x2 = reinterpret_cast<const Pack*>(x0)[i];
+    Pack p2 = t2, y2 = t2, o;
+    if (!first) p2 = reinterpret_cast<const Pack*>(tPrev)[i];      // tNext may alias tPrev: read before written, same thread
+    if (y) y2 = reinterpret_cast<const Pack*>(y)[i];
+#pragma unroll
+    for (int k = 0; k < kPL; k++) {
+      o.v[k] = step(q2.v[k], t2.v[k], p2.v[k]);
+      y2.v[k] = fma(coef, o.v[k], y2.v[k]);
+      acc = fma(x2.v[k], o.v[k], acc);
+    }
+    reinterpret_cast<Pack*>(tNext)[i] = o;
+    if (y) reinterpret_cast<Pack*>(y)[i] = y2;
   }
+  if (tid == 0)
+    for (uint64_t i = n2 * kPL; i < n; i++) {
+      const real_t v = step(q[i], t[i], first ? (real_t)0.0 : tPrev[i]);
+      tNext[i] = v;
+      if (y) y[i] = fma(coef, v, y[i]);
+      acc = fma(x0[i], v, acc);
+    }
   const real_t b = blockSum(acc, scratch);
   gridSum(b, partials, ticket, moment, false, scratch);
 }
@@ -243,8 +354,11 @@ int sbSolveGMRES(Comm* comm, Parameter* param, void* matrix, int fmt, SbCGInfo* 
   real_t* x = (real_t*)sbAllocateDevice(64, sizeof(real_t) * colSlots);
   real_t* b = (real_t*)sbAllocateDevice(64, sizeof(real_t) * rowSlots);
   real_t* stage = (real_t*)sbAllocateDevice(64, sizeof(real_t) * rowSlots);
-  real_t* dH = (real_t*)sbAllocateDevice(64, sizeof(real_t) * (kMaxBasis + 2));      // projections + ||w||^2 of one step
-  real_t* hH = (real_t*)sbAllocateHost(sizeof(real_t) * (kMaxBasis + 2));
+  constexpr size_t kSlot = kMaxBasis + 2;                                  // projections + ||w||^2 of one step
+  real_t* dH = (real_t*)sbAllocateDevice(64, sizeof(real_t) * kSlot * (size_t)(m + 1));
+  real_t* hH = (real_t*)sbAllocateHost(sizeof(real_t) * kSlot * (size_t)(m + 1));
+  std::vector<cudaEvent_t> stepDone((size_t)m);
+  for (auto& e : stepDone) SB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   real_t* dY = (real_t*)sbAllocateDevice(64, sizeof(real_t) * kMaxBasis);
   SB_CUDA(cudaMemsetAsync(x, 0, sizeof(real_t) * colSlots, s));
   launchInitVectors(n, A.rowPtr, A.rowLen, generated, x, b, s);            // x = 0, b = the CG's right-hand side rule
@@ -284,44 +398,53 @@ int sbSolveGMRES(Comm* comm, Parameter* param, void* matrix, int fmt, SbCGInfo* 
     if (!(beta > eps) || k >= itermax - 1) break;
     std::fill(g.begin(), g.end(), 0.0);
     g[0] = beta;
-    int j = 0;
-    for (; j < m && k < itermax - 1; j++) {
-      applyOperator(comm, A, elems, V[(size_t)j], w, s);                   // w = A v_j
-      multiDotKernel<<<gridV, kThreads, 0, s>>>(n, j + 1, ptrs, w, partialsK, c.tickets + 0, dH);
+    // The device never waits for the host inside a cycle: step e+1 is enqueued before the host reads the Hessenberg
+    // column of step e (own slot of dH/hH, own event), applies the rotations and tests the residual. On convergence
+    // the one step already enqueued is simply not used (x += V y takes the first j columns).
+    auto enqueueStep = [&](int e) {
+      real_t* d = dH + (size_t)e * kSlot;
+      applyOperator(comm, A, elems, V[(size_t)e], w, s);                   // w = A v_e
+      multiDotKernel<<<gridV, kThreads, 0, s>>>(n, e + 1, ptrs, w, partialsK, c.tickets + 0, d);
       countLaunch();
-      allreduce(comm, dH, j + 1, s);
-      projectOutKernel<<<gridV, kThreads, 0, s>>>(n, j + 1, ptrs, dH, w, partials + 3 * (size_t)kMaxPartials, c.tickets + 3, dH + j + 1);
+      allreduce(comm, d, e + 1, s);
+      projectOutKernel<<<gridV, kThreads, 0, s>>>(n, e + 1, ptrs, d, w, partials + 3 * (size_t)kMaxPartials, c.tickets + 3, d + e + 1);
       countLaunch();
-      allreduce(comm, dH + j + 1, 1, s);
-      normalizeKernel<<<gridV, kThreads, 0, s>>>(n, w, dH + j + 1, V[(size_t)j + 1]);
+      allreduce(comm, d + e + 1, 1, s);
+      normalizeKernel<<<gridV, kThreads, 0, s>>>(n, w, d + e + 1, V[(size_t)e + 1]);
       countLaunch();
-      SB_CUDA(cudaMemcpyAsync(hH, dH, sizeof(real_t) * (size_t)(j + 2), cudaMemcpyDeviceToHost, s));
-      SB_CUDA(cudaStreamSynchronize(s));
+      SB_CUDA(cudaMemcpyAsync(hH + (size_t)e * kSlot, d, sizeof(real_t) * (size_t)(e + 2), cudaMemcpyDeviceToHost, s));
+      SB_CUDA(cudaEventRecord(stepDone[(size_t)e], s));
+    };
+    // column e of the Hessenberg matrix, previous rotations, new rotation (host, double); true: converged
+    auto absorbStep = [&](int e) {
+      SB_CUDA(cudaEventSynchronize(stepDone[(size_t)e]));
+      const real_t* h = hH + (size_t)e * kSlot;
       k++;
-      // column j of the Hessenberg matrix, previous rotations, new rotation (host, double)
-      double* col = &H[(size_t)j * (m + 1)];
-      for (int i = 0; i <= j; i++) col[i] = (double)hH[i];
-      col[j + 1] = sqrt((double)hH[j + 1]);
-      for (int i = 0; i < j; i++) {
+      double* col = &H[(size_t)e * (m + 1)];
+      for (int i = 0; i <= e; i++) col[i] = (double)h[i];
+      col[e + 1] = sqrt((double)h[e + 1]);
+      for (int i = 0; i < e; i++) {
         const double a = cs[(size_t)i] * col[i] + sn[(size_t)i] * col[i + 1];
         col[i + 1] = -sn[(size_t)i] * col[i] + cs[(size_t)i] * col[i + 1];
         col[i] = a;
       }
-      const double d = hypot(col[j], col[j + 1]);
-      cs[(size_t)j] = d > 0.0 ? col[j] / d : 1.0;
-      sn[(size_t)j] = d > 0.0 ? col[j + 1] / d : 0.0;
-      col[j] = d;
-      col[j + 1] = 0.0;
-      g[(size_t)j + 1] = -sn[(size_t)j] * g[(size_t)j];
-      g[(size_t)j] = cs[(size_t)j] * g[(size_t)j];
-      resid = fabs(g[(size_t)j + 1]);
+      const double d = hypot(col[e], col[e + 1]);
+      cs[(size_t)e] = d > 0.0 ? col[e] / d : 1.0;
+      sn[(size_t)e] = d > 0.0 ? col[e + 1] / d : 0.0;
+      col[e] = d;
+      col[e + 1] = 0.0;
+      g[(size_t)e + 1] = -sn[(size_t)e] * g[(size_t)e];
+      g[(size_t)e] = cs[(size_t)e] * g[(size_t)e];
+      resid = fabs(g[(size_t)e + 1]);
       hist.push_back(resid);
       if (print) printf("Iteration = %d Residual = %E\n", k, resid);
-      if (!(resid > eps)) {
-        j++;
-        done = true;
-        break;
-      }
+      return !(resid > eps);
+    };
+    int j = 0;                                                            // columns absorbed in this cycle
+    int enq = 0;                                                          // steps enqueued in this cycle
+    while (!done && j < m && k < itermax - 1) {
+      while (enq < m && enq <= j + 1 && k + (enq - j) < itermax - 1) enqueueStep(enq++);
+      if (absorbStep(j++)) done = true;
     }
     if (k >= itermax - 1) done = true;
     // y = R^-1 g (back substitution), x += V y
@@ -368,6 +491,7 @@ int sbSolveGMRES(Comm* comm, Parameter* param, void* matrix, int fmt, SbCGInfo* 
   for (auto v : V) sbFree(v);
   sbFree(w); sbFree(x); sbFree(b); sbFree(stage); sbFree(dH); sbFree(dY); sbFree(partialsK);
   sbFreeHost(hH);
+  for (auto e : stepDone) SB_CUDA(cudaEventDestroy(e));
   return k;
 }
 
