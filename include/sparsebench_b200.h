@@ -220,6 +220,11 @@ int sbSpmvOrdered(void* matrix, int fmt, const CG_FLOAT* x, CG_FLOAT* y, CG_UINT
 /* y = A x fused with *dDot = x . y (dDot: device scalar) -- spMVM + ddot of CGSolver.c:123-125 in one pass, asynchronous.
  * Vectors in solver order (SCS with sigma > 1: permuted row order for x and y, as inside sbSolveCG). */
 void sbSpmvDot(void* matrix, int fmt, const CG_FLOAT* x, CG_FLOAT* y, CG_FLOAT* dDot);
+/* Which SpMV kernel family takes this matrix (decided once per matrix from its row lengths; blocks the stream the
+ * first time): 0 SELL-32 bulk-copy rings, 1 CRS/CCRS tiles of a fixed row count through the bulk-copy pipeline
+ * (near-uniform rows: the stencil), 2 CRS/CCRS blocks of bounded non-zero count (uneven rows: longest row >
+ * 1.25 avg + 4), 3 register-staged kernels (SELL with C != 32, rows too long for a tile, SB_SPMV_LEGACY). */
+int sbSpmvKernelFamily(void* matrix, int fmt);
 void sbCRS_destroyMatrix(SbCRSMatrix* m);
 void sbSCS_destroyMatrix(SbSCSMatrix* m);
 void sbCCRS_destroyMatrix(SbCCRSMatrix* m);

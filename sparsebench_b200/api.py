@@ -135,6 +135,8 @@ def lib():
         L.sbSpmvOrdered.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, U, U]
         L.sbSpmvOrdered.restype = C.c_int
         L.sbSpmvDot.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sbSpmvKernelFamily.restype = C.c_int
+        L.sbSpmvKernelFamily.argtypes = [C.c_void_p, C.c_int]
         L.sbTrimPool.argtypes = []
         L.waxpby.argtypes = [U, F, C.c_void_p, F, C.c_void_p, C.c_void_p]
         L.ddot.argtypes = [U, C.c_void_p, C.c_void_p, C.POINTER(F)]

@@ -33,7 +33,10 @@ CrsExt* crsExt(const void* key, bool create)
   std::lock_guard<std::mutex> l(g_extMutex);
   auto it = g_crs.find(key);
   if (it != g_crs.end()) {
-    if (create) *it->second = CrsExt();
+    if (create) {
+      if (it->second->blocks.start) sbFree(it->second->blocks.start);
+      *it->second = CrsExt();
+    }
     return it->second;
   }
   if (!create) return nullptr;
@@ -45,7 +48,11 @@ void eraseExt(const void* key)
   auto a = g_scs.find(key);
   if (a != g_scs.end()) { delete a->second; g_scs.erase(a); }
   auto b = g_crs.find(key);
-  if (b != g_crs.end()) { delete b->second; g_crs.erase(b); }
+  if (b != g_crs.end()) {
+    if (b->second->blocks.start) sbFree(b->second->blocks.start);
+    delete b->second;
+    g_crs.erase(b);
+  }
 }
 
 // Device view of the input GMatrix (uploads host arrays; owns what it uploaded).
@@ -198,6 +205,7 @@ Operator makeOperator(void* matrix, int fmt)
     CrsExt* e = crsExt(m->val, false);
     A.nnzTrue = e ? e->nnzTrue : 0;
     A.split = e ? &e->split : nullptr;
+    A.blocks = e ? &e->blocks : nullptr;
   } else if (fmt == SB_FMT_CCRS) {
     SbCCRSMatrix* m = (SbCCRSMatrix*)matrix;
     A.nr = m->nr; A.nc = m->nc; A.nrPadded = m->nr;
@@ -206,6 +214,7 @@ Operator makeOperator(void* matrix, int fmt)
     CrsExt* e = crsExt(m->entries, false);
     A.nnzTrue = e ? e->nnzTrue : 0;
     A.split = e ? &e->split : nullptr;
+    A.blocks = e ? &e->blocks : nullptr;
   } else if (fmt == SB_FMT_SCS) {
     SbSCSMatrix* m = (SbSCSMatrix*)matrix;
     ScsExt* e = scsExt(m->val, false);

@@ -98,11 +98,19 @@ struct HaloSplit {
   bool valid = false;
   idx_t lo = 0, hi = 0;
 };
+// CRS / CCRS with skewed row lengths: consecutive rows grouped into blocks of bounded non-zero count (built once per
+// matrix, at its first SpMV); rows [start[b], start[b+1]) form block b
+struct RowBlocks {
+  int state = 0;                  // 0 not looked at yet, 1 near-uniform rows (tiles of a fixed row count), 2 skewed (this table)
+  idx_t* start = nullptr;
+  uint32_t count = 0;
+};
 
 // A sparse operator as the CG driver sees it.
 struct Operator {
   int fmt;
   HaloSplit* split = nullptr;              // cache slot in the matrix's side table
+  RowBlocks* blocks = nullptr;             // CRS / CCRS: cache slot in the matrix's side table
   idx_t nr = 0, nc = 0, nrPadded = 0;   // vectors written by spmv need nrPadded slots
   uint64_t nnzTrue = 0;
   const idx_t* rowPtr = nullptr;        // CRS/CCRS: device rowPtr (b = 27-(len-1) rule); SCS: original-order rowLen
@@ -211,6 +219,7 @@ struct ScsExt {
 };
 struct CrsExt {
   HaloSplit split;
+  RowBlocks blocks;
   uint64_t nnzTrue = 0;
   bool ownsArrays = true;
 };

@@ -833,6 +833,206 @@ static void launchRows(Access acc, const idx_t* rowPtr, idx_t nr, const real_t* 
   countLaunch();
 }
 
+// ---- CRS / CCRS with uneven row lengths ----------------------------------------------------------------------------
+// The pipelined kernel above gives every row the same number of lanes and walks them in lockstep: right for the
+// stencil (27 +- 0), wasteful once the lengths vary (5..45: 0.24 ms where this kernel needs 0.19) and pathological
+// with a heavy tail (one 20 000-entry row on 4 lanes: 3.3 ms for a 0.5 GB matrix, 0.29 here). Matrices whose longest
+// row exceeds 1.25 avg + 4 take this kernel instead (one rule for CRS and CCRS, so the two stay bit-identical): the
+// rows are cut into blocks of at most kStreamNnz non-zeros and kStreamMaxRows rows (RowBlocks, built once per matrix);
+// a CTA
+//   A  forms ALL products val * x[col] of its block with one thread per non-zero -- coalesced matrix reads, perfectly
+//      balanced whatever the row lengths -- into shared memory,
+//   B  adds every row's products left to right with one thread per row (the reference's own order,
+//      matrix-CRS.c:58-61),
+//   C  gives rows longer than kStreamSeqLen a warp; a row longer than a whole block gets the whole CTA straight
+//      from global memory.
+// Deterministic: every sum has one fixed order. (A variant that staged the blocks through the bulk-copy engine was
+// slower, 0.27 ms on the 5..45 case: its 4 x 50 KB of stages leave the x gathers 28 KB of L1.)
+constexpr int kStreamThreads = 256, kStreamPerThread = 8;
+constexpr uint32_t kStreamNnz = kStreamThreads * kStreamPerThread;
+constexpr uint32_t kStreamSeqLen = 64;
+constexpr uint32_t kStreamMaxRows = 2048;
+
+template <bool DOT, typename Access>
+__global__ void __launch_bounds__(kStreamThreads, 5)
+spmvRowsStreamKernel(Access acc, const idx_t* __restrict__ rowPtr, const idx_t* __restrict__ blockStart, uint32_t nBlocks,
+    const real_t* __restrict__ x, real_t* __restrict__ y, real_t* partials, unsigned int* ticket, real_t* dotOut,
+    bool accumulate, PeerReduce push)
+{
+  __shared__ real_t prod[kStreamNnz];
+  __shared__ real_t scratch[32];
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  real_t dotAcc = 0.0;
+  // geometry of the next block is loaded one block ahead: blockStart -> rowPtr is a dependent pair of misses
+  idx_t nr0 = 0, nr1 = 0, nbs = 0, nbe = 0;
+  if (blockIdx.x < nBlocks) {
+    nr0 = __ldg(blockStart + blockIdx.x);
+    nr1 = __ldg(blockStart + blockIdx.x + 1);
+    nbs = __ldg(rowPtr + nr0);
+    nbe = __ldg(rowPtr + nr1);
+  }
+  for (uint32_t b = blockIdx.x; b < nBlocks; b += gridDim.x) {
+    const idx_t r0 = nr0, r1 = nr1, bs = nbs, be = nbe;
+    if ((uint64_t)b + gridDim.x < nBlocks) {
+      nr0 = __ldg(blockStart + b + gridDim.x);
+      nr1 = __ldg(blockStart + b + gridDim.x + 1);
+      nbs = __ldg(rowPtr + nr0);
+      nbe = __ldg(rowPtr + nr1);
+    }
+    const uint64_t nnz = (uint64_t)be - bs;
+    if (nnz <= kStreamNnz) {
+      const uint32_t n32 = (uint32_t)nnz;
+      // A: products (slots past the end re-read the block's first element: defined values, nothing stored)
+#pragma unroll 1
+      for (uint32_t i0 = tid; i0 < n32; i0 += 4 * kStreamThreads) {
+        idx_t cc[4];
+        real_t vv[4], xx[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc.load((uint64_t)bs + (i0 + u * kStreamThreads < n32 ? i0 + u * kStreamThreads : 0u), cc[u], vv[u]);
+#pragma unroll
+        for (int u = 0; u < 4; u++) xx[u] = __ldg(x + cc[u]);
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (i0 + u * kStreamThreads < n32) prod[i0 + u * kStreamThreads] = mulRn(vv[u], xx[u]);
+      }
+      __syncthreads();
+      // B: one thread per row, left to right
+      const uint32_t nrows = (uint32_t)(r1 - r0);
+      int longSeen = 0;
+      for (uint32_t r = tid; r < nrows; r += kStreamThreads) {
+        const uint32_t a = (uint32_t)(__ldg(rowPtr + r0 + r) - bs), e = (uint32_t)(__ldg(rowPtr + r0 + r + 1) - bs);
+        if (e - a <= kStreamSeqLen) {
+          real_t sum = 0.0;
+          for (uint32_t k = a; k < e; k++) sum = addRn(sum, prod[k]);
+          y[r0 + r] = sum;
+          if (DOT) dotAcc = fma(sum, __ldg(x + r0 + r), dotAcc);
+        } else {
+          longSeen = 1;
+        }
+      }
+      if (__syncthreads_or(longSeen)) {                       // (also the barrier before prod is overwritten)
+        // C: one warp per long row
+        for (uint32_t r = warp; r < nrows; r += kStreamThreads / 32) {
+          const uint32_t a = (uint32_t)(__ldg(rowPtr + r0 + r) - bs), e = (uint32_t)(__ldg(rowPtr + r0 + r + 1) - bs);
+          if (e - a > kStreamSeqLen) {
+            real_t sum = 0.0;
+            for (uint32_t k = a + lane; k < e; k += 32) sum = addRn(sum, prod[k]);
+            sum = warpSum(sum);
+            if (lane == 0) {
+              y[r0 + r] = sum;
+              if (DOT) dotAcc = fma(sum, __ldg(x + r0 + r), dotAcc);
+            }
+          }
+        }
+        __syncthreads();
+      }
+    } else {
+      // a single row longer than a block: the whole CTA, four independent accumulators per thread
+      real_t part[4] = { 0.0, 0.0, 0.0, 0.0 };
+      for (uint64_t j = (uint64_t)bs + tid; j < be; j += 4 * kStreamThreads) {
+        idx_t cc[4];
+        real_t vv[4], xx[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc.load(j + u * kStreamThreads < be ? j + u * kStreamThreads : (uint64_t)bs, cc[u], vv[u]);
+#pragma unroll
+        for (int u = 0; u < 4; u++) xx[u] = __ldg(x + cc[u]);
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (j + u * kStreamThreads < be) part[u] = mulAdd(part[u], vv[u], xx[u]);
+      }
+      const real_t tot = blockSum((part[0] + part[1]) + (part[2] + part[3]), scratch);
+      if (tid == 0) {
+        y[r0] = tot;
+        if (DOT) dotAcc = fma(tot, __ldg(x + r0), dotAcc);
+      }
+    }
+  }
+  if (DOT) {
+    const real_t bsum = blockSum(dotAcc, scratch);
+    gridSum(bsum, partials, ticket, dotOut, accumulate, scratch, push.size ? &push : nullptr);
+  }
+}
+
+__global__ void maxRowLenKernel(idx_t nr, const idx_t* __restrict__ rowPtr, unsigned long long* out)
+{
+  unsigned long long m = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nr; i += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned long long len = (unsigned long long)(rowPtr[i + 1] - rowPtr[i]);
+    m = len > m ? len : m;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, m, o);
+    m = other > m ? other : m;
+  }
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// Decides once per matrix which kernel family takes it, and builds the block table for the skewed ones (host greedy
+// pass over the row pointers: setup, like the SELL conversion). Blocks the stream.
+static bool rowsAreSkewed(RowBlocks* rb, const idx_t* rowPtr, idx_t nr, uint64_t nnz, cudaStream_t s)
+{
+  if (!rb || useLegacyKernels()) return false;
+  if (rb->state == 0) {
+    static const int knob = envInt("SB_ROWS_BALANCED", -1);      // -1: decide by the row lengths, 0: never, 1: always
+    Context& c = ctx();
+    bool skewed = knob == 1;
+    if (knob < 0 && nr > 0) {
+      unsigned long long* dMax = (unsigned long long*)sbAllocateDevice(64, sizeof(unsigned long long));
+      unsigned long long hMax = 0;
+      SB_CUDA(cudaMemsetAsync(dMax, 0, sizeof(unsigned long long), s));
+      uint64_t blocks = ((uint64_t)nr + 255) / 256;
+      if (blocks > (uint64_t)c.numSMs * 8) blocks = (uint64_t)c.numSMs * 8;
+      maxRowLenKernel<<<(int)blocks, 256, 0, s>>>(nr, rowPtr, dMax);
+      SB_CUDA(cudaMemcpyAsync(&hMax, dMax, sizeof(hMax), cudaMemcpyDeviceToHost, s));
+      SB_CUDA(cudaStreamSynchronize(s));
+      sbFree(dMax);
+      skewed = (double)hMax > 1.25 * ((double)nnz / (double)nr) + 4.0;
+    }
+    if (skewed && nr > 0) {
+      std::vector<idx_t> rp((size_t)nr + 1), start;
+      SB_CUDA(cudaMemcpyAsync(rp.data(), rowPtr, sizeof(idx_t) * ((size_t)nr + 1), cudaMemcpyDeviceToHost, s));
+      SB_CUDA(cudaStreamSynchronize(s));
+      start.reserve((size_t)(nnz / (kStreamNnz / 2)) + 16);
+      idx_t r = 0;
+      while (r < nr) {
+        start.push_back(r);
+        const idx_t base = rp[(size_t)r];
+        idx_t e = r + 1;                                        // a row longer than a block stands alone
+        while (e < nr && e - r < kStreamMaxRows && rp[(size_t)e + 1] - base <= kStreamNnz) e++;
+        r = e;
+      }
+      start.push_back(nr);
+      if (start.size() - 1 > 0xffffffffull) SB_FATAL("row block table: more than 2^32 blocks");
+      rb->count = (uint32_t)(start.size() - 1);
+      rb->start = (idx_t*)sbAllocateDevice(64, sizeof(idx_t) * start.size());
+      SB_CUDA(cudaMemcpyAsync(rb->start, start.data(), sizeof(idx_t) * start.size(), cudaMemcpyHostToDevice, s));
+      SB_CUDA(cudaStreamSynchronize(s));
+    }
+    rb->state = skewed && nr > 0 ? 2 : 1;
+  }
+  return rb->state == 2;
+}
+
+template <typename Access>
+static void launchRowsStream(Access acc, const idx_t* rowPtr, const RowBlocks& rb, const real_t* x, real_t* y, const DotArgs* dot,
+    cudaStream_t s)
+{
+  Context& c = ctx();
+  uint64_t blocks = rb.count;
+  const uint64_t cap = (uint64_t)c.numSMs * 5;
+  if (blocks > cap) blocks = cap;
+  if (blocks > (uint64_t)kMaxPartials) blocks = kMaxPartials;
+  if (dot)
+    spmvRowsStreamKernel<true, Access><<<(int)blocks, kStreamThreads, 0, s>>>(acc, rowPtr, rb.start, rb.count, x, y,
+        c.partials + (size_t)dot->slot * kMaxPartials, c.tickets + dot->slot, dot->out, dot->accumulate, dot->push ? *dot->push : PeerReduce());
+  else
+    spmvRowsStreamKernel<false, Access><<<(int)blocks, kStreamThreads, 0, s>>>(acc, rowPtr, rb.start, rb.count, x, y, nullptr, nullptr,
+        nullptr, false, PeerReduce());
+  SB_CUDA(cudaGetLastError());
+  countLaunch();
+}
+
 // lanes per row ~ avg/7 (one 8-deep batch per row); tile = as many passes of the consumer warps as fit a stage.
 // CRS and CCRS take the same decisions (same CAP), so their row sums are bit-identical to each other.
 template <typename Access, typename P>
@@ -894,9 +1094,13 @@ static bool launchRowsPipeAuto(Access acc, const idx_t* rowPtr, idx_t nr, uint64
 
 template <typename Access>
 static void launchRowsAuto(Access acc, const idx_t* rowPtr, idx_t nr, uint64_t nnz, const real_t* x, real_t* y,
-    idx_t lo, idx_t hi, const DotArgs* dot, cudaStream_t s)
+    idx_t lo, idx_t hi, const DotArgs* dot, RowBlocks* rb, cudaStream_t s)
 {
   const real_t avg = nr ? (real_t)nnz / (real_t)nr : 0.0;
+  if (lo == 0 && hi == nr && rowsAreSkewed(rb, rowPtr, nr, nnz, s)) {      // (a sub-range keeps the tiled kernels)
+    launchRowsStream(acc, rowPtr, *rb, x, y, dot, s);
+    return;
+  }
   if (launchRowsPipeAuto(acc, rowPtr, nr, nnz, x, y, lo, hi, dot, nullptr, false, s)) return;
   if (avg <= 6.0) launchRows<2, Access>(acc, rowPtr, nr, x, y, lo, hi, dot, s);
   else if (avg <= 12.0) launchRows<4, Access>(acc, rowPtr, nr, x, y, lo, hi, dot, s);
@@ -993,9 +1197,9 @@ void launchSpmv(const Operator& A, const real_t* x, real_t* y, idx_t lo, idx_t h
     SB_CUDA(cudaGetLastError());
     countLaunch();
   } else if (A.fmt == SB_FMT_CRS) {
-    launchRowsAuto(CrsAccess { A.crs.col, A.crs.val }, A.crs.rowPtr, A.nr, A.nnzTrue, x, y, lo, hi, dot, s);
+    launchRowsAuto(CrsAccess { A.crs.col, A.crs.val }, A.crs.rowPtr, A.nr, A.nnzTrue, x, y, lo, hi, dot, A.blocks, s);
   } else {
-    launchRowsAuto(CcrsAccess { A.ccrs.entries }, A.ccrs.rowPtr, A.nr, A.nnzTrue, x, y, lo, hi, dot, s);
+    launchRowsAuto(CcrsAccess { A.ccrs.entries }, A.ccrs.rowPtr, A.nr, A.nnzTrue, x, y, lo, hi, dot, A.blocks, s);
   }
 }
 
@@ -1003,6 +1207,8 @@ bool spmvGatedAvailable(const Operator& A)
 {
   if (useLegacyKernels()) return false;
   if (A.fmt == SB_FMT_SCS) return A.sell.C == 32;
+  // skewed row lengths: the nnz-balanced kernel has no gated form; the halo exchange completes before its launch
+  if (rowsAreSkewed(A.blocks, A.rowPtr, A.nr, A.nnzTrue, ctx().stream)) return false;
   if (A.fmt == SB_FMT_CRS)
     return launchRowsPipeAuto(CrsAccess { A.crs.col, A.crs.val }, A.crs.rowPtr, A.nr, A.nnzTrue, nullptr, nullptr, 0, A.nr, nullptr, nullptr, true, nullptr);
   return launchRowsPipeAuto(CcrsAccess { A.ccrs.entries }, A.ccrs.rowPtr, A.nr, A.nnzTrue, nullptr, nullptr, 0, A.nr, nullptr, nullptr, true, nullptr);
@@ -1064,6 +1270,15 @@ int sbSpmvOrdered(void* matrix, int fmt, const CG_FLOAT* x, CG_FLOAT* y, CG_UINT
   ensureOnDevice(y);
   launchSpmvGated(A, x, y, intLo, intHi, HaloGate(), nullptr, ctx().stream);
   return 1;
+}
+
+int sbSpmvKernelFamily(void* matrix, int fmt)
+{
+  Operator A = makeOperator(matrix, fmt);
+  if (useLegacyKernels()) return 3;
+  if (fmt == SB_FMT_SCS) return A.sell.C == 32 ? 0 : 3;
+  if (rowsAreSkewed(A.blocks, A.rowPtr, A.nr, A.nnzTrue, ctx().stream)) return 2;
+  return spmvGatedAvailable(A) ? 1 : 3;
 }
 
 void sbSpmvDot(void* matrix, int fmt, const CG_FLOAT* x, CG_FLOAT* y, CG_FLOAT* dDot)
