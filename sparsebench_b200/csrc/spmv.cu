@@ -837,7 +837,7 @@ static void launchRows(Access acc, const idx_t* rowPtr, idx_t nr, const real_t* 
 // The pipelined kernel above gives every row the same number of lanes and walks them in lockstep: right for the
 // stencil (27 +- 0), wasteful once the lengths vary (5..45: 0.24 ms where this kernel needs 0.19) and pathological
 // with a heavy tail (one 20 000-entry row on 4 lanes: 3.3 ms for a 0.5 GB matrix, 0.29 here). Matrices whose longest
-// row exceeds 1.25 avg + 4 take this kernel instead (one rule for CRS and CCRS, so the two stay bit-identical): the
+// row exceeds 1.2 avg + 4 take this kernel instead (one rule for CRS and CCRS, so the two stay bit-identical): the
 // rows are cut into blocks of at most kStreamNnz non-zeros and kStreamMaxRows rows (RowBlocks, built once per matrix);
 // a CTA
 //   A  forms ALL products val * x[col] of its block with one thread per non-zero -- coalesced matrix reads, perfectly
@@ -987,7 +987,7 @@ static bool rowsAreSkewed(RowBlocks* rb, const idx_t* rowPtr, idx_t nr, uint64_t
       SB_CUDA(cudaMemcpyAsync(&hMax, dMax, sizeof(hMax), cudaMemcpyDeviceToHost, s));
       SB_CUDA(cudaStreamSynchronize(s));
       sbFree(dMax);
-      skewed = (double)hMax > 1.25 * ((double)nnz / (double)nr) + 4.0;
+      skewed = (double)hMax > 1.2 * ((double)nnz / (double)nr) + 4.0;
     }
     if (skewed && nr > 0) {
       std::vector<idx_t> rp((size_t)nr + 1), start;
