@@ -150,6 +150,37 @@ def main():
         api.destroyMatrix(B)
         L.sbFreeGMatrix(C.byref(g))
 
+    # ---- uneven row lengths: the row-block kernel (spmvRowsStreamKernel) against the reference's CRS spMVM
+    rng = np.random.default_rng(9)
+    n = 2500
+    lens = np.minimum(2 + (rng.pareto(1.1, n) * 5).astype(np.int64), 1200)
+    lens[::89] = 0
+    lens[1000] = 2049                                           # longer than one block: the whole-CTA path
+    rp = np.zeros(n + 1, np.int64)
+    np.cumsum(lens, out=rp[1:])
+    rows = np.repeat(np.arange(n), lens)
+    col = rng.integers(0, n, int(rp[-1]))
+    col = col[np.lexsort((col, rows))]
+    val = rng.uniform(-1.0, 1.0, int(rp[-1])).astype(RDT)
+    g = api.gmatrix_from_csr(rp, col, val)
+    x = (1.0 + np.cos(np.arange(n) * 0.37)).astype(RDT)
+    Ar = api.CRSMatrix()
+    RC.convertMatrix(C.byref(Ar), C.byref(g))
+    yr = np.zeros(n, RDT)
+    RC.spMVM(C.byref(Ar), x.ctypes.data, yr.ctypes.data)
+    absrow = np.zeros(n)
+    np.add.at(absrow, rows, np.abs(val.astype(np.float64) * x.astype(np.float64)[col]))
+    A = api.convertMatrix(api.FMT_CRS, g)
+    B = api.convertMatrix(api.FMT_CCRS, g)
+    check(L.sbSpmvKernelFamily(C.byref(A), api.FMT_CRS) == 2 and L.sbSpmvKernelFamily(C.byref(B), api.FMT_CCRS) == 2, "uneven rows: kernel family")
+    y = spmv_dev(A, x, n)
+    tol = TOL * np.maximum(1.0, lens / 27.0)                    # TOL is stated for 27-term rows; rounding errors add up per term
+    check(np.all(np.abs(y.astype(np.float64) - yr.astype(np.float64)) <= tol * absrow), "uneven rows: CRS SpMV, worst %.3e" % float(
+        np.max(np.abs(y.astype(np.float64) - yr.astype(np.float64)) / np.maximum(tol * absrow, 1e-300))))
+    check(np.array_equal(spmv_dev(B, x, n), y), "uneven rows: CCRS differs from CRS")
+    api.destroyMatrix(A)
+    api.destroyMatrix(B)
+
     # ---- CG against the reference's own solveCG (strict build: residuals printed with %.17g)
     for (n, itermax, eps) in [(8, 12, 0.0), (16, 20, 1.0), (16, 40, 0.0)]:
         gr = ref_generate(RC, n, n, n)
