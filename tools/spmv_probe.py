@@ -86,6 +86,19 @@ def main():
                 L.sbSpmvOrdered(C.byref(A), fmt, x.ptr, y.ptr, lo, hi)
                 times.append(t.stop_ms())
             print("ordered single-launch kernel, interior [%d,%d): min %.4f median %.4f ms" % (lo, hi, min(times), sorted(times)[len(times) // 2]))
+        # interleaved back-to-back blocks: what the gated kernel variant itself costs (no gate to wait for, ordinary memory)
+        pb, ob = [], []
+        for rnd in range(6):
+            t.start()
+            for i in range(a.reps):
+                api.spMVM(A, x, y)
+            pb.append(t.stop_ms() / a.reps)
+            t.start()
+            for i in range(a.reps):
+                L.sbSpmvOrdered(C.byref(A), fmt, x.ptr, y.ptr, plane, units - plane)
+            ob.append(t.stop_ms() / a.reps)
+        pm, om = sorted(pb)[len(pb) // 2], sorted(ob)[len(ob) // 2]
+        print("interleaved back-to-back blocks: plain %.4f ms, ordered/gated variant %.4f ms (%+.1f us)" % (pm, om, (om - pm) * 1e3))
     if a.dirty:
         # the CG context: a vector update that leaves x dirty in L2 right before every SpMV
         r = api.to_device(np.zeros(N))
