@@ -17,6 +17,8 @@ SOURCES = ["runtime.cu", "generate.cu", "formats.cu", "spmv.cu", "vecops.cu", "c
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "--extended-lambda", "-Xcompiler", "-fPIC,-fvisibility=default",
               "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
+if os.environ.get("SB_BUILD_SWEEPS"):       # every CRS/CCRS pipeline configuration of the sweeps in profiles/ (SB_ROWS_VAR, SB_ROWS_CFG): 4x the compile time
+    NVCC_FLAGS.append("-DSB_TUNING_SWEEPS")
 
 
 def _newer(src_list, target):
@@ -46,16 +48,18 @@ def lib_path(variant=""):
 
 
 def build(force=False, verbose=False, variants=None):
-    """builds the default library and (variants=None: all) the type variants; returns the default library's path"""
-    for v in (VARIANTS if variants is None else variants):
-        _build_one(v, force, verbose)
+    """builds the default library and (variants=None: all) the type variants; returns the default library's path.
+    All variants' compilations run concurrently (a clean build of the four is bounded by 4 x spmv.cu otherwise)."""
+    todo = list(VARIANTS if variants is None else variants)
+    started = [(v, _compile(v, force, verbose)) for v in todo]
+    for v, (objs, procs) in started:
+        _link(v, objs, procs, force, verbose)
     return LIB
 
 
-def _build_one(variant, force, verbose):
+def _compile(variant, force, verbose):
     defs = VARIANTS[variant]
     obj_dir = OBJ + ("_" + variant if variant else "")
-    lib = lib_path(variant)
     os.makedirs(obj_dir, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs, procs = [], []
@@ -66,11 +70,18 @@ def _build_one(variant, force, verbose):
         if force or _newer([s] + _headers(), o):
             cmd = [nvcc] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    return objs, procs
+
+
+def _link(variant, objs, procs, force, verbose):
+    defs = VARIANTS[variant]
+    lib = lib_path(variant)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     failed = False
     for src, p in procs:
         out, _ = p.communicate()
         if p.returncode != 0 or verbose:
-            sys.stderr.write("---- %s\n%s\n" % (src, out))
+            sys.stderr.write("---- %s (variant %r)\n%s\n" % (src, variant, out))
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed (variant %r)" % variant)

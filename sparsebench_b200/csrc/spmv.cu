@@ -1061,11 +1061,12 @@ static bool tryRowsPipe(Access acc, const idx_t* rowPtr, real_t avg, const real_
     else launchRowsPipe<LPRV, P, false, V>(acc.template pipe<P>(), rowPtr, x, y, lo, hi, tileRows, dot, nullptr, s); \
   } while (0)
 #define SB_PIPE(LPRV) SB_PIPE_V(LPRV, Access::kVar)
-  static const int var = envInt("SB_ROWS_VAR", Access::kVar);       // tuning knob for the 4-lanes-per-row case (the stencil)
   switch (lpr) {
   case 1: SB_PIPE(1); break;
   case 2: SB_PIPE(2); break;
-  case 4:
+  case 4: {
+#ifdef SB_TUNING_SWEEPS                                              // builds for tools/gpu_rows_var.sh: every VAR of the stencil case
+    static const int var = envInt("SB_ROWS_VAR", Access::kVar);
     switch (var) {
     case 0: SB_PIPE_V(4, 0); break;
     case 1: SB_PIPE_V(4, 1); break;
@@ -1077,7 +1078,11 @@ static bool tryRowsPipe(Access acc, const idx_t* rowPtr, real_t avg, const real_
     case 12: SB_PIPE_V(4, 12); break;
     default: SB_PIPE(4); break;
     }
+#else
+    SB_PIPE(4);
+#endif
     break;
+  }
   case 8: SB_PIPE(8); break;
   case 16: SB_PIPE(16); break;
   default: SB_PIPE(32); break;
@@ -1094,10 +1099,18 @@ static bool launchRowsPipeAuto(Access acc, const idx_t* rowPtr, idx_t nr, uint64
 {
   const real_t avg = nr ? (real_t)nnz / (real_t)nr : 0.0;
   if (useLegacyKernels()) return false;
-  static const int cfg = envInt("SB_ROWS_CFG", Access::kDefaultCfg);   // tuning knob, measured in profiles/
+  // the measured best per format (profiles/README.md); the other stage layout is compiled only into sweep builds
+#ifdef SB_TUNING_SWEEPS
+  static const int cfg = envInt("SB_ROWS_CFG", Access::kDefaultCfg);
   if (cfg == 1 || Access::kWide)                          // the 5376-element stages do not fit with 16 bytes per non-zero
     return tryRowsPipe<Access, typename Access::template Pipe<16, 3584, Access::kStagesFor3584>>(acc, rowPtr, avg, x, y, lo, hi, dot, g, probeOnly, s);
   return tryRowsPipe<Access, typename Access::template Pipe<23, 5376, Access::kStagesFor5376>>(acc, rowPtr, avg, x, y, lo, hi, dot, g, probeOnly, s);
+#else
+  if constexpr (Access::kDefaultCfg == 1 || Access::kWide)
+    return tryRowsPipe<Access, typename Access::template Pipe<16, 3584, Access::kStagesFor3584>>(acc, rowPtr, avg, x, y, lo, hi, dot, g, probeOnly, s);
+  else
+    return tryRowsPipe<Access, typename Access::template Pipe<23, 5376, Access::kStagesFor5376>>(acc, rowPtr, avg, x, y, lo, hi, dot, g, probeOnly, s);
+#endif
 }
 
 template <typename Access>

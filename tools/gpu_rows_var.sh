@@ -1,4 +1,5 @@
 #!/bin/bash
+# needs a sweep build: SB_BUILD_SWEEPS=1 python -m sparsebench_b200.build --force  (the default build carries only the chosen configuration)
 # SB_ROWS_VAR sweep of the CRS pipeline kernel (4 lanes per row): plain vs fused-dot SpMV at 256^3, CG at 128^3
 set -u
 mkdir -p gpurun_out
