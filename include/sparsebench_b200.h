@@ -223,7 +223,8 @@ void sbSpmvDot(void* matrix, int fmt, const CG_FLOAT* x, CG_FLOAT* y, CG_FLOAT* 
 /* Which SpMV kernel family takes this matrix (decided once per matrix from its row lengths; blocks the stream the
  * first time): 0 SELL-32 bulk-copy rings, 1 CRS/CCRS tiles of a fixed row count through the bulk-copy pipeline
  * (near-uniform rows: the stencil), 2 CRS/CCRS blocks of bounded non-zero count (uneven rows: longest row >
- * 1.2 avg + 4), 3 register-staged kernels (SELL with C != 32, rows too long for a tile, SB_SPMV_LEGACY). */
+ * 1.2 avg + 4), 3 register-staged kernels (SELL with C != 32, rows too long for a tile, SB_SPMV_LEGACY), 4 SELL-32 rings for
+ * the ordinary chunks + one CTA per chunk longer than 256 columns (heavy-tailed matrices: longest chunk > 4x the average). */
 int sbSpmvKernelFamily(void* matrix, int fmt);
 void sbCRS_destroyMatrix(SbCRSMatrix* m);
 void sbSCS_destroyMatrix(SbSCSMatrix* m);

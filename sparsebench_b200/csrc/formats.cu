@@ -9,6 +9,8 @@
 #include <mutex>
 #include <unordered_map>
 
+#include <vector>
+
 #include "sb_internal.h"
 
 namespace sb {
@@ -223,6 +225,7 @@ Operator makeOperator(void* matrix, int fmt)
     A.rowLen = e->rowLenPerm;
     A.nnzTrue = e->nnzTrue;
     A.split = &e->split;
+    A.longc = (e->longc.count > 0 && m->C == 32) ? &e->longc : nullptr;
     if (!e->identityPerm) { A.oldToNew = m->oldToNewPerm; A.newToOld = m->newToOldPerm; A.permKey = e->id; }
     A.sell = SellView { m->nChunks, m->nr, m->C, m->chunkPtr, m->chunkLens, e->identityPerm ? m->colInd : e->colPerm, m->val };
   } else {
@@ -401,6 +404,30 @@ void sbSCS_convertMatrix(SbSCSMatrix* m, GMatrix* im)
 
   sbFree(keys); sbFree(keysSorted); sbFree(idx); sbFree(idxSorted); sbFree(chunkElems); sbFree(chunkPtr64); sbFree(notIdentity);
   in.release();
+  if (C == 32 && nChunks > 0) {
+    // a few very long chunks (heavy-tailed row lengths) would each keep one warp of the ring kernel busy long after
+    // the rest is done: list them for the long-chunk kernel (spmv.cu)
+    std::vector<idx_t> lens((size_t)nChunks);
+    SB_CUDA(cudaMemcpyAsync(lens.data(), m->chunkLens, sizeof(idx_t) * (size_t)nChunks, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    idx_t longest = 0;
+    for (idx_t l : lens) longest = l > longest ? l : longest;
+    const double avg = (double)m->nElems / 32.0 / (double)nChunks;
+    if (longest > 256 && (double)longest > 4.0 * avg) {
+      std::vector<idx_t> list;
+      for (size_t i = 0; i < lens.size(); i++)
+        if (lens[i] > 256) {
+          list.push_back((idx_t)i);
+          lens[i] = 0;
+        }
+      ext->longc.count = (uint32_t)list.size();
+      ext->longc.shortLens = (idx_t*)sbAllocateDevice(64, sizeof(idx_t) * lens.size());
+      ext->longc.list = (idx_t*)sbAllocateDevice(64, sizeof(idx_t) * list.size());
+      SB_CUDA(cudaMemcpyAsync(ext->longc.shortLens, lens.data(), sizeof(idx_t) * lens.size(), cudaMemcpyHostToDevice, s));
+      SB_CUDA(cudaMemcpyAsync(ext->longc.list, list.data(), sizeof(idx_t) * list.size(), cudaMemcpyHostToDevice, s));
+      SB_CUDA(cudaStreamSynchronize(s));
+    }
+  }
   {
     // register the side table under the val pointer
     ScsExt* slot = scsExt(m->val, true);
@@ -412,7 +439,7 @@ void sbSCS_convertMatrix(SbSCSMatrix* m, GMatrix* im)
 void sbSCS_destroyMatrix(SbSCSMatrix* m)
 {
   ScsExt* e = scsExt(m->val, false);
-  if (e) { sbFree(e->colPerm); sbFree(e->rowLenPerm); sbFree(e->rowLenOrig); }
+  if (e) { sbFree(e->colPerm); sbFree(e->rowLenPerm); sbFree(e->rowLenOrig); sbFree(e->longc.shortLens); sbFree(e->longc.list); }
   eraseExt(m->val);
   sbFree(m->colInd); sbFree(m->val); sbFree(m->chunkPtr); sbFree(m->chunkLens); sbFree(m->oldToNewPerm); sbFree(m->newToOldPerm);
   m->colInd = m->chunkPtr = m->chunkLens = m->oldToNewPerm = m->newToOldPerm = nullptr; m->val = nullptr;

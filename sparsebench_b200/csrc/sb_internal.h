@@ -106,11 +106,20 @@ struct RowBlocks {
   uint32_t count = 0;
 };
 
+// SELL-32 with a few very long chunks (longest > 256 columns and > 4x the average): those chunks are taken out of the
+// ring kernel -- it is handed `shortLens`, where they have length 0 -- and multiplied by one CTA each.
+struct LongChunks {
+  idx_t* shortLens = nullptr;      // chunkLens with the long chunks zeroed
+  idx_t* list = nullptr;           // their chunk ids, ascending
+  uint32_t count = 0;
+};
+
 // A sparse operator as the CG driver sees it.
 struct Operator {
   int fmt;
   HaloSplit* split = nullptr;              // cache slot in the matrix's side table
   RowBlocks* blocks = nullptr;             // CRS / CCRS: cache slot in the matrix's side table
+  const LongChunks* longc = nullptr;       // SELL-32: set when the matrix has long chunks
   idx_t nr = 0, nc = 0, nrPadded = 0;   // vectors written by spmv need nrPadded slots
   uint64_t nnzTrue = 0;
   const idx_t* rowPtr = nullptr;        // CRS/CCRS: device rowPtr (b = 27-(len-1) rule); SCS: original-order rowLen
@@ -215,6 +224,7 @@ struct ScsExt {
   bool identityPerm = true;
   uint64_t nnzTrue = 0;
   idx_t nc = 0;               // columns incl. halo (the reference's SCS struct drops it, matrix-SCS.c:38)
+  LongChunks longc;
   uint64_t id = 0;               // unique per conversion, never reused
 };
 struct CrsExt {

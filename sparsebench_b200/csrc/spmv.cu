@@ -253,6 +253,59 @@ spmvSell32TmaKernel(SellView A, const real_t* __restrict__ x, real_t* __restrict
   }
 }
 
+// SELL-32 chunks longer than 256 columns (LongChunks, sb_internal.h): one CTA per chunk, its warps split the COLUMNS
+// -- a lane still owns one row -- and the per-warp partial sums are added in warp order. Only these rows leave the
+// reference's strict left-to-right order (matrix-SCS.c:213-222); what they gain: a 20 000-column chunk is streamed by
+// eight warps with eight loads each in flight instead of by one warp through a ring sized for 27 columns.
+constexpr int kLongWarps = 8;
+template <bool DOT>
+__global__ void __launch_bounds__(kLongWarps * 32)
+spmvSellLongChunksKernel(SellView A, const idx_t* __restrict__ list, uint32_t count, const real_t* __restrict__ x,
+    real_t* __restrict__ y, real_t* partials, unsigned int* ticket, real_t* dotOut, bool accumulate)
+{
+  __shared__ real_t part[kLongWarps][32];
+  __shared__ real_t scratch[32];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  real_t dotAcc = 0.0;
+  for (uint32_t q = blockIdx.x; q < count; q += gridDim.x) {
+    const idx_t ch = __ldg(list + q);
+    const uint64_t len = __ldg(A.chunkLens + ch);
+    const uint64_t base = (uint64_t)__ldg(A.chunkPtr + ch) + lane;
+    const uint64_t j1 = len * (warp + 1) / kLongWarps;
+    uint64_t j = len * warp / kLongWarps;
+    real_t sum = 0.0;
+    for (; j + 8 <= j1; j += 8) {
+      idx_t cc[8];
+      real_t vv[8], xx[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        cc[u] = ldStream(A.col + base + (j + u) * 32);
+        vv[u] = ldStream(A.val + base + (j + u) * 32);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) xx[u] = __ldg(x + cc[u]);
+#pragma unroll
+      for (int u = 0; u < 8; u++) sum = mulAdd(sum, vv[u], xx[u]);
+    }
+    for (; j < j1; j++) sum = mulAdd(sum, ldStream(A.val + base + j * 32), __ldg(x + ldStream(A.col + base + j * 32)));
+    part[warp][lane] = sum;
+    __syncthreads();
+    if (warp == 0) {
+      real_t t = part[0][lane];
+#pragma unroll
+      for (int w = 1; w < kLongWarps; w++) t = addRn(t, part[w][lane]);
+      const uint64_t row = (uint64_t)ch * 32 + lane;
+      y[row] = t;
+      if (DOT && row < A.nr) dotAcc = fma(t, __ldg(x + row), dotAcc);
+    }
+    __syncthreads();
+  }
+  if (DOT) {
+    const real_t b = blockSum(dotAcc, scratch);
+    gridSum(b, partials, ticket, dotOut, accumulate, scratch);
+  }
+}
+
 struct SellGate {                                     // nullptr-able extra arguments of a gated launch
   idx_t rot, nInterior;
   HaloGate gate;
@@ -1204,6 +1257,22 @@ void launchSpmv(const Operator& A, const real_t* x, real_t* y, idx_t lo, idx_t h
       spmvSellAnyCKernel<false><<<(int)blocks, 256, 0, s>>>(A.sell, x, y, lo, hi, nullptr, nullptr, nullptr, false);
     SB_CUDA(cudaGetLastError());
     countLaunch();
+  } else if (A.fmt == SB_FMT_SCS && !useLegacyKernels() && A.longc && lo == 0 && hi == A.sell.nChunks && !(dot && dot->push)) {
+    // heavy-tailed chunk lengths: free-running warps for the ordinary chunks (nothing to keep in step), then the long
+    // chunks by a CTA each; the second kernel adds its share of the fused dot to the first one's
+    SellView shortView = A.sell;
+    shortView.chunkLens = A.longc->shortLens;
+    launchSell32TmaCfg<32, 4, 3, 4, false, false>(shortView, x, y, lo, hi, dot, nullptr, s);
+    uint64_t blocks = A.longc->count;
+    if (blocks > (uint64_t)c.numSMs * 4) blocks = (uint64_t)c.numSMs * 4;
+    if (dot)
+      spmvSellLongChunksKernel<true><<<(int)blocks, kLongWarps * 32, 0, s>>>(A.sell, A.longc->list, A.longc->count, x, y,
+          c.partials + (size_t)dot->slot * kMaxPartials, c.tickets + dot->slot, dot->out, true);
+    else
+      spmvSellLongChunksKernel<false><<<(int)blocks, kLongWarps * 32, 0, s>>>(A.sell, A.longc->list, A.longc->count, x, y, nullptr,
+          nullptr, nullptr, false);
+    SB_CUDA(cudaGetLastError());
+    countLaunch();
   } else if (A.fmt == SB_FMT_SCS && !useLegacyKernels()) {
     launchSell32Tma(A.sell, x, y, lo, hi, dot, nullptr, s);
   } else if (A.fmt == SB_FMT_SCS) {
@@ -1227,7 +1296,7 @@ void launchSpmv(const Operator& A, const real_t* x, real_t* y, idx_t lo, idx_t h
 bool spmvGatedAvailable(const Operator& A)
 {
   if (useLegacyKernels()) return false;
-  if (A.fmt == SB_FMT_SCS) return A.sell.C == 32;
+  if (A.fmt == SB_FMT_SCS) return A.sell.C == 32 && !A.longc;       // long chunks: two launches, no gated form
   // skewed row lengths: the nnz-balanced kernel has no gated form; the halo exchange completes before its launch
   if (rowsAreSkewed(A.blocks, A.rowPtr, A.nr, A.nnzTrue, ctx().stream)) return false;
   if (A.fmt == SB_FMT_CRS)
@@ -1297,7 +1366,7 @@ int sbSpmvKernelFamily(void* matrix, int fmt)
 {
   Operator A = makeOperator(matrix, fmt);
   if (useLegacyKernels()) return 3;
-  if (fmt == SB_FMT_SCS) return A.sell.C == 32 ? 0 : 3;
+  if (fmt == SB_FMT_SCS) return A.sell.C != 32 ? 3 : A.longc ? 4 : 0;
   if (rowsAreSkewed(A.blocks, A.rowPtr, A.nr, A.nnzTrue, ctx().stream)) return 2;
   return spmvGatedAvailable(A) ? 1 : 3;
 }

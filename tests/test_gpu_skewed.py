@@ -14,7 +14,7 @@ from matrices import irregular_spd
 
 pytestmark = pytest.mark.gpu
 
-FAMILY_TILED, FAMILY_BLOCKS = 1, 2
+FAMILY_TILED, FAMILY_BLOCKS, FAMILY_SELL_LONG = 1, 2, 4
 
 
 def skewed(n, lens, seed, local=False):
@@ -92,12 +92,47 @@ def test_skewed_spmv_against_the_oracle(name, m):
     api.destroyMatrix(B)
 
 
+@pytest.mark.parametrize("sigma", [1, 256, 4096])
+@pytest.mark.parametrize("name,m", [c for c in CASES if c[0] in ("heavy_tail", "long_ends")], ids=["heavy_tail", "long_ends"])
+def test_sell_long_chunks_against_the_oracle(name, m, sigma):
+    """SELL-32-sigma with chunks longer than 256 columns: those rows are summed by eight warps (componentwise bound),
+    every other row keeps the reference's order bit for bit"""
+    n = m.nr
+    x = 1.0 + np.cos(np.arange(n) * 0.37)
+    s = orc.scs_convert(m, 32, sigma)
+    yref = orc.spmv_scs(s, x)
+    bound = np.zeros(s.nrPadded)
+    bound[s.oldToNewPerm.astype(np.int64)] = orc.spmv_crs(orc.Csr(m.rowPtr, m.col, np.abs(m.val)), np.abs(x))
+    long_rows = np.repeat(s.chunkLens.astype(np.int64) > 256, 32)
+    assert long_rows.any() and not long_rows.all()
+    A = api.convertMatrix(api.FMT_SCS, api.gmatrix_from_csr(m.rowPtr, m.col, m.val), 32, sigma)
+    assert api.lib().sbSpmvKernelFamily(C.byref(A), api.FMT_SCS) == FAMILY_SELL_LONG
+    y = spmv(A, x, s.nrPadded)
+    assert np.array_equal(y[~long_rows], yref[~long_rows])
+    assert np.all(np.abs(y - yref)[long_rows] <= 1e-12 * bound[long_rows])
+    assert np.array_equal(spmv(A, x, s.nrPadded), y)
+    # fused dot (vectors in the permuted order of the solver): same y, dot within the summation bound
+    xp = np.zeros(s.nrPadded)
+    xp[s.oldToNewPerm.astype(np.int64)] = x
+    xd, yd, dd = api.to_device(xp), api.to_device(np.zeros(s.nrPadded)), api.to_device(np.zeros(8))
+    api.lib().sbSpmvDot(C.byref(A), api.FMT_SCS, xd.ptr, yd.ptr, dd.ptr)
+    yp = api.to_host(yd, np.float64, s.nrPadded)
+    d = float(api.to_host(dd, np.float64, 1)[0])
+    assert abs(d - float(np.dot(xp, yp))) <= 1e-12 * float(np.dot(np.abs(xp), np.abs(yp)) + 1.0) * 64
+    for b in (xd, yd, dd):
+        b.free()
+    api.destroyMatrix(A)
+
+
 def test_the_stencil_keeps_the_tiled_pipeline():
     g = api.matrixGenerate(24, 24, 24, device=True)
     for fmt in (api.FMT_CRS, api.FMT_CCRS):
         A = api.convertMatrix(fmt, g)
         assert api.lib().sbSpmvKernelFamily(C.byref(A), fmt) == FAMILY_TILED
         api.destroyMatrix(A)
+    A = api.convertMatrix(api.FMT_SCS, g, 32, 256)
+    assert api.lib().sbSpmvKernelFamily(C.byref(A), api.FMT_SCS) == 0           # the ring kernel alone
+    api.destroyMatrix(A)
     api.lib().sbFreeGMatrix(C.byref(g))
 
 
@@ -121,13 +156,14 @@ def heavy_tailed_spd(n, seed=21):
     return orc.Csr(S.indptr.astype(np.uint32), S.indices.astype(np.uint32), S.data.astype(np.float64))
 
 
-@pytest.mark.parametrize("fmt", [api.FMT_CRS, api.FMT_CCRS])
+@pytest.mark.parametrize("fmt", [api.FMT_CRS, api.FMT_CCRS, api.FMT_SCS])
 def test_cg_on_a_heavy_tailed_spd_matrix(fmt):
     m = heavy_tailed_spd(2500)
     b = np.cos(np.arange(m.nr) * 0.11) + 1.5
     kref, href, xref = orc.cg_crs(m, b, np.zeros(m.nr), 60, 1e-9)
-    A = api.convertMatrix(fmt, api.gmatrix_from_csr(m.rowPtr, m.col, m.val))
-    assert api.lib().sbSpmvKernelFamily(C.byref(A), fmt) == FAMILY_BLOCKS
+    g = api.gmatrix_from_csr(m.rowPtr, m.col, m.val)
+    A = api.convertMatrix(fmt, g, 32, 256) if fmt == api.FMT_SCS else api.convertMatrix(fmt, g)
+    assert api.lib().sbSpmvKernelFamily(C.byref(A), fmt) == (FAMILY_SELL_LONG if fmt == api.FMT_SCS else FAMILY_BLOCKS)
     for flags in (api.CG_FUSED, 0):
         k, hist, x, _ = api.solveCG(A, 60, 1e-9, generated=False, b=b, flags=flags, want_x=True)
         assert k == kref and len(hist) == len(href)
