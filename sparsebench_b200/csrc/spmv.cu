@@ -914,8 +914,8 @@ constexpr uint32_t kStreamNnz = kStreamThreads * kStreamPerThread;
 constexpr uint32_t kStreamSeqLen = 64;
 constexpr uint32_t kStreamMaxRows = 2048;
 
-template <bool DOT, typename Access>
-__global__ void __launch_bounds__(kStreamThreads, 5)
+template <bool DOT, typename Access, int ROUND>
+__global__ void __launch_bounds__(kStreamThreads, ROUND == 8 ? 4 : 5)
 spmvRowsStreamKernel(Access acc, const idx_t* __restrict__ rowPtr, const idx_t* __restrict__ blockStart, uint32_t nBlocks,
     const real_t* __restrict__ x, real_t* __restrict__ y, real_t* partials, unsigned int* ticket, real_t* dotOut,
     bool accumulate, PeerReduce push)
@@ -945,15 +945,15 @@ spmvRowsStreamKernel(Access acc, const idx_t* __restrict__ rowPtr, const idx_t* 
       const uint32_t n32 = (uint32_t)nnz;
       // A: products (slots past the end re-read the block's first element: defined values, nothing stored)
 #pragma unroll 1
-      for (uint32_t i0 = tid; i0 < n32; i0 += 4 * kStreamThreads) {
-        idx_t cc[4];
-        real_t vv[4], xx[4];
+      for (uint32_t i0 = tid; i0 < n32; i0 += ROUND * kStreamThreads) {
+        idx_t cc[ROUND];
+        real_t vv[ROUND], xx[ROUND];
 #pragma unroll
-        for (int u = 0; u < 4; u++) acc.load((uint64_t)bs + (i0 + u * kStreamThreads < n32 ? i0 + u * kStreamThreads : 0u), cc[u], vv[u]);
+        for (int u = 0; u < ROUND; u++) acc.load((uint64_t)bs + (i0 + u * kStreamThreads < n32 ? i0 + u * kStreamThreads : 0u), cc[u], vv[u]);
 #pragma unroll
-        for (int u = 0; u < 4; u++) xx[u] = __ldg(x + cc[u]);
+        for (int u = 0; u < ROUND; u++) xx[u] = __ldg(x + cc[u]);
 #pragma unroll
-        for (int u = 0; u < 4; u++)
+        for (int u = 0; u < ROUND; u++)
           if (i0 + u * kStreamThreads < n32) prod[i0 + u * kStreamThreads] = mulRn(vv[u], xx[u]);
       }
       __syncthreads();
@@ -1075,23 +1075,32 @@ static bool rowsAreSkewed(RowBlocks* rb, const idx_t* rowPtr, idx_t nr, uint64_t
   return rb->state == 2;
 }
 
-template <typename Access>
-static void launchRowsStream(Access acc, const idx_t* rowPtr, const RowBlocks& rb, const real_t* x, real_t* y, const DotArgs* dot,
+template <typename Access, int ROUND>
+static void launchRowsStreamCfg(Access acc, const idx_t* rowPtr, const RowBlocks& rb, const real_t* x, real_t* y, const DotArgs* dot,
     cudaStream_t s)
 {
   Context& c = ctx();
   uint64_t blocks = rb.count;
-  const uint64_t cap = (uint64_t)c.numSMs * 5;
+  const uint64_t cap = (uint64_t)c.numSMs * (ROUND == 8 ? 4 : 5);
   if (blocks > cap) blocks = cap;
   if (blocks > (uint64_t)kMaxPartials) blocks = kMaxPartials;
   if (dot)
-    spmvRowsStreamKernel<true, Access><<<(int)blocks, kStreamThreads, 0, s>>>(acc, rowPtr, rb.start, rb.count, x, y,
+    spmvRowsStreamKernel<true, Access, ROUND><<<(int)blocks, kStreamThreads, 0, s>>>(acc, rowPtr, rb.start, rb.count, x, y,
         c.partials + (size_t)dot->slot * kMaxPartials, c.tickets + dot->slot, dot->out, dot->accumulate, dot->push ? *dot->push : PeerReduce());
   else
-    spmvRowsStreamKernel<false, Access><<<(int)blocks, kStreamThreads, 0, s>>>(acc, rowPtr, rb.start, rb.count, x, y, nullptr, nullptr,
+    spmvRowsStreamKernel<false, Access, ROUND><<<(int)blocks, kStreamThreads, 0, s>>>(acc, rowPtr, rb.start, rb.count, x, y, nullptr, nullptr,
         nullptr, false, PeerReduce());
   SB_CUDA(cudaGetLastError());
   countLaunch();
+}
+
+template <typename Access>
+static void launchRowsStream(Access acc, const idx_t* rowPtr, const RowBlocks& rb, const real_t* x, real_t* y, const DotArgs* dot,
+    cudaStream_t s)
+{
+  static const int round = envInt("SB_STREAM_ROUND", 4);
+  if (round == 8) launchRowsStreamCfg<Access, 8>(acc, rowPtr, rb, x, y, dot, s);
+  else launchRowsStreamCfg<Access, 4>(acc, rowPtr, rb, x, y, dot, s);
 }
 
 // lanes per row ~ avg/7 (one 8-deep batch per row); tile = as many passes of the consumer warps as fit a stage.
