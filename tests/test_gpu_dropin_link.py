@@ -133,19 +133,23 @@ def test_reference_driver_spmv_mode(fmt, n):
     # few runs, for a GPU that dropped its clocks while the driver spent seconds generating the matrix on the host
     # (0.05 - 1 s until they are back up). Two iteration counts separate the steady state from the one-time part, the
     # minimum over repeated runs drops the clock ramps; pairs of runs are added until the estimate is sane.
+    # The 3 % claim is made at 256^3 (0.82 ms per call). At 128^3 a call takes 0.11 ms and the driver's own report
+    # (a rate printed with two decimals over 100 calls) resolves no better than ~10 us per call on a busy box: those
+    # cases check that the driver runs the real kernel at about its rate (10 % + 30 us).
+    rel, slack = (1.03, 0.020) if n >= 256 else (1.10, 0.030)
     short, long_ = 31, 131
     shorts, longs = [], []
-    for attempt in range(4):
+    for attempt in range(6):
         shorts.append(_run_spmv_mode(exe, n, short))
         longs.append(_run_spmv_mode(exe, n, long_))
         per_call_ms = (min(longs) - min(shorts)) / (long_ - short) * 1e3
-        if attempt >= 1 and 0.9 * direct_ms <= per_call_ms <= 1.03 * direct_ms + 0.020:
+        if attempt >= 1 and 0.9 * direct_ms <= per_call_ms <= rel * direct_ms + slack:
             break
     first_call_extra_ms = min(shorts) * 1e3 - (short - 1) * per_call_ms
     print("%s %d^3 -t spmv: %.4f ms per call reported by the reference driver (steady state; one-time move of x, y to the GPU "
           "%.2f ms), %.4f ms back to back through the API" % (fmt, n, per_call_ms, first_call_extra_ms, direct_ms))
     # PROFILE's getTimeStamp pair drains the device before and after every call: ~15 us of launch + wake-up per call
-    assert per_call_ms <= 1.03 * direct_ms + 0.020, (per_call_ms, direct_ms)
+    assert per_call_ms <= rel * direct_ms + slack, (per_call_ms, direct_ms)
     assert per_call_ms >= 0.9 * direct_ms, (per_call_ms, direct_ms)          # and it really ran the kernel
 
 
