@@ -259,7 +259,7 @@ spmvSell32TmaKernel(SellView A, const real_t* __restrict__ x, real_t* __restrict
 // eight warps with eight loads each in flight instead of by one warp through a ring sized for 27 columns.
 constexpr int kLongWarps = 8;
 template <bool DOT>
-__global__ void __launch_bounds__(kLongWarps * 32)
+__global__ void __launch_bounds__(kLongWarps * 32, 4)
 spmvSellLongChunksKernel(SellView A, const idx_t* __restrict__ list, uint32_t count, const real_t* __restrict__ x,
     real_t* __restrict__ y, real_t* partials, unsigned int* ticket, real_t* dotOut, bool accumulate)
 {
